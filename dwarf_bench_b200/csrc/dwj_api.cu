@@ -1,0 +1,563 @@
+// dwj_api.cu -- C ABI (include/dwj.h) over the sm_100a join kernels.  No CPU fallback.
+#include "../../include/dwj.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include <cuda_runtime.h>
+
+#include "build.cuh"
+#include "partition.cuh"
+#include "probe.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(_e == cudaErrorMemoryAllocation ? DWJ_ERR_OOM : DWJ_ERR_CUDA, "%s: %s (%s:%d)",  \
+                  #call, cudaGetErrorString(_e), __FILE__, __LINE__);                              \
+  } while (0)
+
+struct DeviceGuard {   // callers (torch, other engines) may have another device current
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+uint64_t next_pow2(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+constexpr int PROBE_THREADS = 256;
+constexpr int PROBE_ITEMS_4 = 8;    // rows per thread, 4-byte keys
+constexpr int PROBE_ITEMS_8 = 4;    // rows per thread, 8-byte keys
+constexpr uint64_t HOST_CHUNK_BYTES = 64ull << 20;   // per column per pipeline stage in dwj_join_host
+
+}  // namespace
+
+struct dwj_engine {
+  dwj_config cfg{};
+  int W = 4;
+  cudaDeviceProp prop{};
+  void *table = nullptr;
+  uint64_t slots = 0, buckets = 0, table_bytes = 0;
+  uint64_t build_rows = 0;
+  bool built = false;
+  bool l2_window = false;
+  cudaAccessPolicyWindow window{};
+  // events
+  cudaEvent_t ev_build[2]{}, ev_probe[2]{}, ev_part[2]{};
+  bool have_build = false, have_probe = false, have_part = false;
+  // scan / counters scratch
+  unsigned long long *tile_state = nullptr;
+  uint64_t tile_state_cap = 0;                 // in descriptors
+  unsigned long long *counter = nullptr;       // device uint64 used when the caller passes no d_n_matches
+  unsigned long long *part_scratch = nullptr;  // hist[256] + cursor[256]
+  uint32_t launches_build = 0, launches_probe = 0;
+  // dwj_join_host staging
+  void *stage = nullptr;
+  uint64_t stage_bytes = 0;
+  cudaStream_t hs[2]{};
+  cudaEvent_t hev[6]{};
+  dwj_timing last_host{};
+};
+
+namespace {
+
+template <class Kern, class Args>
+cudaError_t launch(dwj_engine *e, Kern kern, dim3 grid, dim3 block, cudaStream_t s, Args args, bool table_window) {
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = grid;
+  lc.blockDim = block;
+  lc.dynamicSmemBytes = 0;
+  lc.stream = s;
+  cudaLaunchAttribute attr[1];
+  if (table_window && e->l2_window) {
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow = e->window;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&lc, kern, args);
+}
+
+int ensure_tile_state(dwj_engine *e, uint64_t tiles, cudaStream_t s) {
+  if (tiles + 1 <= e->tile_state_cap) return DWJ_OK;
+  if (e->tile_state) {
+    CU(cudaStreamSynchronize(s));
+    CU(cudaFree(e->tile_state));
+    e->tile_state = nullptr;
+    e->tile_state_cap = 0;
+  }
+  const uint64_t cap = std::max<uint64_t>(tiles + 1, 1024);
+  CU(cudaMalloc(&e->tile_state, cap * sizeof(unsigned long long)));
+  e->tile_state_cap = cap;
+  return DWJ_OK;
+}
+
+template <int W> int build_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, cudaStream_t s) {
+  using K = typename dwj::KeyT<W>::type;
+  CU(cudaEventRecord(e->ev_build[0], s));
+  CU(cudaMemsetAsync(e->table, 0xFF, e->table_bytes, s));
+  e->launches_build = 1;
+  if (n) {
+    dwj::BuildArgs<W> a{(const K *)keys, (const K *)vals, n, e->table, e->buckets - 1, e->cfg.hash_seed};
+    constexpr int ROWS = 4;
+    const uint64_t want = (n + 256ull * ROWS - 1) / (256ull * ROWS);
+    const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)e->prop.multiProcessorCount * 32);
+    CU(launch(e, dwj::build_kernel<W, ROWS>, dim3(grid), dim3(256), s, a, true));
+    e->launches_build = 2;
+  }
+  CU(cudaEventRecord(e->ev_build[1], s));
+  e->have_build = true;
+  e->build_rows = n;
+  e->built = true;
+  return DWJ_OK;
+}
+
+template <int W, int MODE, bool UNIQUE>
+int probe_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
+  constexpr int ITEMS = W == 4 ? PROBE_ITEMS_4 : PROBE_ITEMS_8;
+  constexpr uint64_t TILE = (uint64_t)PROBE_THREADS * ITEMS;
+  const uint64_t tiles = (a.n + TILE - 1) / TILE;
+  a.num_tiles = tiles;
+  e->launches_probe = 0;
+  if (MODE == dwj::PROBE_PAIRS) {
+    int rc = ensure_tile_state(e, tiles, s);
+    if (rc) return rc;
+    a.tile_state = e->tile_state;
+    CU(cudaMemsetAsync(e->tile_state, 0, (tiles + 1) * sizeof(unsigned long long), s));
+    e->launches_probe++;
+  }
+  if (MODE == dwj::PROBE_PAIRS || MODE == dwj::PROBE_COUNT) {
+    CU(cudaMemsetAsync(a.n_matches, 0, sizeof(unsigned long long), s));
+    e->launches_probe++;
+  }
+  if (tiles) {
+    if (tiles > 0x7fffffffull) return fail(DWJ_ERR_INVALID, "probe of %llu rows needs more than 2^31 tiles", (unsigned long long)a.n);
+    CU(launch(e, dwj::probe_kernel<W, MODE, UNIQUE, PROBE_THREADS, ITEMS>, dim3((unsigned)tiles), dim3(PROBE_THREADS), s, a, true));
+    e->launches_probe++;
+  }
+  return DWJ_OK;
+}
+
+template <int W>
+int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint64_t n, void *ok, void *ob, void *op,
+               uint32_t *flags, uint64_t capacity, uint64_t *d_n, uint64_t *h_n, cudaStream_t s) {
+  using K = typename dwj::KeyT<W>::type;
+  if (!e->built) return fail(DWJ_ERR_STATE, "probe before dwj_build");
+  dwj::ProbeArgs<W> a{};
+  a.keys = (const K *)keys;
+  a.vals = (const K *)vals;
+  a.n = n;
+  a.table = e->table;
+  a.bucket_mask = e->buckets - 1;
+  a.seed = e->cfg.hash_seed;
+  a.out_key = (K *)ok;
+  a.out_build_val = (K *)ob;
+  a.out_probe_val = (K *)op;
+  a.out_flags = flags;
+  a.capacity = capacity;
+  a.n_matches = d_n ? (unsigned long long *)d_n : e->counter;
+  const bool unique = (e->cfg.flags & DWJ_FLAG_UNIQUE_BUILD_KEYS) != 0;
+  CU(cudaEventRecord(e->ev_probe[0], s));
+  int rc;
+  switch (mode) {
+  case dwj::PROBE_ALIGNED: rc = probe_launch<W, dwj::PROBE_ALIGNED, true>(e, a, s); break;
+  case dwj::PROBE_CONTAINS: rc = probe_launch<W, dwj::PROBE_CONTAINS, true>(e, a, s); break;
+  case dwj::PROBE_COUNT:
+    rc = unique ? probe_launch<W, dwj::PROBE_COUNT, true>(e, a, s) : probe_launch<W, dwj::PROBE_COUNT, false>(e, a, s);
+    break;
+  default:
+    rc = unique ? probe_launch<W, dwj::PROBE_PAIRS, true>(e, a, s) : probe_launch<W, dwj::PROBE_PAIRS, false>(e, a, s);
+  }
+  if (rc) return rc;
+  CU(cudaEventRecord(e->ev_probe[1], s));
+  e->have_probe = true;
+  if (h_n) {
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, a.n_matches, sizeof(total), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *h_n = total;
+    if (mode == dwj::PROBE_PAIRS && total > capacity)
+      return fail(DWJ_ERR_OVERFLOW, "join produced %llu rows, output capacity is %llu", total, (unsigned long long)capacity);
+  }
+  return DWJ_OK;
+}
+
+template <int W>
+int partition_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, uint32_t log2_parts, void *ok, void *ov,
+                   uint64_t *d_offsets, cudaStream_t s) {
+  using K = typename dwj::KeyT<W>::type;
+  dwj::PartitionArgs<W> a{};
+  a.keys = (const K *)keys;
+  a.vals = (const K *)vals;
+  a.n = n;
+  a.log2_parts = log2_parts;
+  a.seed = e->cfg.hash_seed;
+  a.out_keys = (K *)ok;
+  a.out_vals = (K *)ov;
+  a.hist = e->part_scratch;
+  a.cursor = e->part_scratch + dwj::PART_MAX;
+  a.offsets = (unsigned long long *)d_offsets;
+  CU(cudaEventRecord(e->ev_part[0], s));
+  CU(cudaMemsetAsync(e->part_scratch, 0, 2 * dwj::PART_MAX * sizeof(unsigned long long), s));
+  const unsigned sms = (unsigned)e->prop.multiProcessorCount;
+  if (n) {
+    const uint64_t want = (n + 256ull * 8 - 1) / (256ull * 8);
+    CU(launch(e, dwj::partition_hist_kernel<W>, dim3((unsigned)std::min<uint64_t>(want, sms * 8ull)), dim3(dwj::PART_THREADS), s, a, false));
+  }
+  CU(launch(e, dwj::partition_offsets_kernel<W>, dim3(1), dim3(32), s, a, false));
+  if (n) {
+    constexpr int ITEMS = W == 4 ? 16 : 8;
+    const uint64_t tiles = (n + (uint64_t)dwj::PART_THREADS * ITEMS - 1) / ((uint64_t)dwj::PART_THREADS * ITEMS);
+    CU(launch(e, dwj::partition_scatter_kernel<W, ITEMS>, dim3((unsigned)std::min<uint64_t>(tiles, sms * 4ull)), dim3(dwj::PART_THREADS), s, a, false));
+  }
+  CU(cudaEventRecord(e->ev_part[1], s));
+  e->have_part = true;
+  return DWJ_OK;
+}
+
+int check_engine(const dwj_engine *e) { return e ? DWJ_OK : fail(DWJ_ERR_INVALID, "null engine"); }
+
+}  // namespace
+
+extern "C" {
+
+int dwj_abi_version(void) { return DWJ_ABI_VERSION; }
+const char *dwj_last_error(void) { return g_err; }
+
+int dwj_create(const dwj_config *cfg, dwj_engine **out) {
+  if (!cfg || !out) return fail(DWJ_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->key_bytes != 4 && cfg->key_bytes != 8) return fail(DWJ_ERR_INVALID, "key_bytes must be 4 or 8, got %d", cfg->key_bytes);
+  if (cfg->payload_bytes != cfg->key_bytes) return fail(DWJ_ERR_INVALID, "payload_bytes must equal key_bytes");
+  double lf = cfg->load_factor == 0.0 ? 0.5 : cfg->load_factor;
+  if (!(lf > 0.0 && lf <= 0.9)) return fail(DWJ_ERR_INVALID, "load_factor must be in (0, 0.9], got %g", cfg->load_factor);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(DWJ_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(ce));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(DWJ_ERR_INVALID, "device %d out of range (have %d)", cfg->device, ndev);
+
+  dwj_engine *e = new (std::nothrow) dwj_engine();
+  if (!e) return fail(DWJ_ERR_OOM, "host allocation failed");
+  e->cfg = *cfg;
+  e->cfg.load_factor = lf;
+  e->W = cfg->key_bytes;
+  DeviceGuard g(cfg->device);
+  auto bail = [&](int rc) { dwj_destroy(e); return rc; };
+  if (cudaGetDeviceProperties(&e->prop, cfg->device) != cudaSuccess) return bail(fail(DWJ_ERR_CUDA, "cudaGetDeviceProperties failed"));
+  if (e->prop.major < 10) return bail(fail(DWJ_ERR_CUDA, "device %d is sm_%d%d; this library holds sm_100a code only", cfg->device, e->prop.major, e->prop.minor));
+
+  const uint32_t spb = 32u / (2u * (uint32_t)e->W);
+  uint64_t need = (uint64_t)((double)std::max<uint64_t>(cfg->max_build_rows, 1) / lf + 0.999999);
+  e->slots = std::max<uint64_t>(next_pow2(need), spb);
+  e->buckets = e->slots / spb;
+  e->table_bytes = e->buckets * 32ull;
+  cudaError_t me = cudaMalloc(&e->table, e->table_bytes);
+  if (me != cudaSuccess) return bail(fail(DWJ_ERR_OOM, "cudaMalloc of a %llu-byte table failed: %s", (unsigned long long)e->table_bytes, cudaGetErrorString(me)));
+  if (cudaMalloc(&e->counter, 64) != cudaSuccess || cudaMalloc(&e->part_scratch, 2 * dwj::PART_MAX * sizeof(unsigned long long)) != cudaSuccess)
+    return bail(fail(DWJ_ERR_OOM, "scratch allocation failed"));
+  for (int i = 0; i < 2; ++i)
+    if (cudaEventCreate(&e->ev_build[i]) != cudaSuccess || cudaEventCreate(&e->ev_probe[i]) != cudaSuccess ||
+        cudaEventCreate(&e->ev_part[i]) != cudaSuccess)
+      return bail(fail(DWJ_ERR_CUDA, "cudaEventCreate failed"));
+
+  if ((cfg->flags & DWJ_FLAG_L2_PERSIST) && e->prop.persistingL2CacheMaxSize > 0 && e->prop.accessPolicyMaxWindowSize > 0) {
+    const size_t carve = std::min<size_t>((size_t)e->prop.persistingL2CacheMaxSize, (size_t)e->table_bytes);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+      e->window.base_ptr = e->table;
+      e->window.num_bytes = std::min<size_t>((size_t)e->table_bytes, (size_t)e->prop.accessPolicyMaxWindowSize);
+      e->window.hitRatio = (float)std::min(1.0, (double)carve / (double)e->window.num_bytes);
+      e->window.hitProp = cudaAccessPropertyPersisting;
+      e->window.missProp = cudaAccessPropertyStreaming;
+      e->l2_window = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  *out = e;
+  return DWJ_OK;
+}
+
+int dwj_destroy(dwj_engine *e) {
+  if (!e) return DWJ_OK;
+  DeviceGuard g(e->cfg.device);
+  cudaDeviceSynchronize();
+  if (e->l2_window) cudaCtxResetPersistingL2Cache();
+  cudaFree(e->table);
+  cudaFree(e->tile_state);
+  cudaFree(e->counter);
+  cudaFree(e->part_scratch);
+  cudaFree(e->stage);
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_build[i]) cudaEventDestroy(e->ev_build[i]);
+    if (e->ev_probe[i]) cudaEventDestroy(e->ev_probe[i]);
+    if (e->ev_part[i]) cudaEventDestroy(e->ev_part[i]);
+    if (e->hs[i]) cudaStreamDestroy(e->hs[i]);
+  }
+  for (auto &ev : e->hev)
+    if (ev) cudaEventDestroy(ev);
+  cudaGetLastError();
+  delete e;
+  return DWJ_OK;
+}
+
+int dwj_get_info(const dwj_engine *e, dwj_info *info) {
+  if (!e || !info) return fail(DWJ_ERR_INVALID, "null argument");
+  info->slots = e->slots;
+  info->table_bytes = e->table_bytes;
+  info->build_rows = e->build_rows;
+  info->slot_bytes = 2u * (uint32_t)e->W;
+  info->slots_per_bucket = 32u / info->slot_bytes;
+  info->l2_persist = e->l2_window ? 1u : 0u;
+  info->sm_count = (uint32_t)e->prop.multiProcessorCount;
+  info->l2_bytes = (uint64_t)e->prop.l2CacheSize;
+  info->launches_build = e->launches_build;
+  info->launches_probe = e->launches_probe;
+  return DWJ_OK;
+}
+
+int dwj_build(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  if (n_rows && (!d_keys || !d_vals)) return fail(DWJ_ERR_INVALID, "null build column");
+  if (n_rows > e->cfg.max_build_rows && (double)n_rows > 0.9 * (double)e->slots)
+    return fail(DWJ_ERR_CAPACITY, "%llu build rows exceed the table created for %llu", (unsigned long long)n_rows,
+                (unsigned long long)e->cfg.max_build_rows);
+  DeviceGuard g(e->cfg.device);
+  return e->W == 4 ? build_impl<4>(e, d_keys, d_vals, n_rows, (cudaStream_t)stream)
+                   : build_impl<8>(e, d_keys, d_vals, n_rows, (cudaStream_t)stream);
+}
+
+int dwj_probe_aligned(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *d_out_key,
+                      void *d_out_build_val, void *d_out_probe_val, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  if (n_rows && (!d_keys || !d_vals || !d_out_key || !d_out_build_val || !d_out_probe_val))
+    return fail(DWJ_ERR_INVALID, "null probe column or output");
+  DeviceGuard g(e->cfg.device);
+  return e->W == 4 ? probe_impl<4>(e, dwj::PROBE_ALIGNED, d_keys, d_vals, n_rows, d_out_key, d_out_build_val, d_out_probe_val, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream)
+                   : probe_impl<8>(e, dwj::PROBE_ALIGNED, d_keys, d_vals, n_rows, d_out_key, d_out_build_val, d_out_probe_val, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int dwj_probe_contains(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t *d_out_flags, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  if (n_rows && (!d_keys || !d_out_flags)) return fail(DWJ_ERR_INVALID, "null probe column or output");
+  DeviceGuard g(e->cfg.device);
+  return e->W == 4 ? probe_impl<4>(e, dwj::PROBE_CONTAINS, d_keys, nullptr, n_rows, nullptr, nullptr, nullptr, d_out_flags, 0, nullptr, nullptr, (cudaStream_t)stream)
+                   : probe_impl<8>(e, dwj::PROBE_CONTAINS, d_keys, nullptr, n_rows, nullptr, nullptr, nullptr, d_out_flags, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int dwj_probe_pairs(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *d_out_key,
+                    void *d_out_build_val, void *d_out_probe_val, uint64_t capacity, uint64_t *d_n_matches,
+                    uint64_t *n_matches, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  if (n_rows && (!d_keys || !d_vals)) return fail(DWJ_ERR_INVALID, "null probe column");
+  if (capacity && (!d_out_build_val || !d_out_probe_val)) return fail(DWJ_ERR_INVALID, "null output column");
+  DeviceGuard g(e->cfg.device);
+  return e->W == 4 ? probe_impl<4>(e, dwj::PROBE_PAIRS, d_keys, d_vals, n_rows, d_out_key, d_out_build_val, d_out_probe_val, nullptr, capacity, d_n_matches, n_matches, (cudaStream_t)stream)
+                   : probe_impl<8>(e, dwj::PROBE_PAIRS, d_keys, d_vals, n_rows, d_out_key, d_out_build_val, d_out_probe_val, nullptr, capacity, d_n_matches, n_matches, (cudaStream_t)stream);
+}
+
+int dwj_probe_count(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint64_t *d_n_matches, uint64_t *n_matches,
+                    void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  if (n_rows && !d_keys) return fail(DWJ_ERR_INVALID, "null probe column");
+  DeviceGuard g(e->cfg.device);
+  return e->W == 4 ? probe_impl<4>(e, dwj::PROBE_COUNT, d_keys, nullptr, n_rows, nullptr, nullptr, nullptr, nullptr, 0, d_n_matches, n_matches, (cudaStream_t)stream)
+                   : probe_impl<8>(e, dwj::PROBE_COUNT, d_keys, nullptr, n_rows, nullptr, nullptr, nullptr, nullptr, 0, d_n_matches, n_matches, (cudaStream_t)stream);
+}
+
+int dwj_timings(dwj_engine *e, dwj_timing *t) {
+  if (!e || !t) return fail(DWJ_ERR_INVALID, "null argument");
+  DeviceGuard g(e->cfg.device);
+  *t = e->last_host;
+  if (e->have_build) {
+    CU(cudaEventSynchronize(e->ev_build[1]));
+    CU(cudaEventElapsedTime(&t->build_ms, e->ev_build[0], e->ev_build[1]));
+  }
+  if (e->have_probe) {
+    CU(cudaEventSynchronize(e->ev_probe[1]));
+    CU(cudaEventElapsedTime(&t->probe_ms, e->ev_probe[0], e->ev_probe[1]));
+  }
+  if (e->have_part) {
+    CU(cudaEventSynchronize(e->ev_part[1]));
+    CU(cudaEventElapsedTime(&t->partition_ms, e->ev_part[0], e->ev_part[1]));
+  }
+  if (t->total_ms == 0.f) t->total_ms = t->build_ms + t->probe_ms;
+  return DWJ_OK;
+}
+
+int dwj_partition(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_parts,
+                  void *d_out_keys, void *d_out_vals, uint64_t *d_offsets, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  if (n_parts == 0 || n_parts > (uint32_t)dwj::PART_MAX || (n_parts & (n_parts - 1)))
+    return fail(DWJ_ERR_INVALID, "n_parts must be a power of two in [1, %d], got %u", dwj::PART_MAX, n_parts);
+  if (!d_offsets || (n_rows && (!d_keys || !d_out_keys))) return fail(DWJ_ERR_INVALID, "null partition argument");
+  if ((d_vals == nullptr) != (d_out_vals == nullptr)) return fail(DWJ_ERR_INVALID, "d_vals and d_out_vals must both be given or both be null");
+  uint32_t lg = 0;
+  while ((1u << lg) < n_parts) ++lg;
+  DeviceGuard g(e->cfg.device);
+  return e->W == 4 ? partition_impl<4>(e, d_keys, d_vals, n_rows, lg, d_out_keys, d_out_vals, d_offsets, (cudaStream_t)stream)
+                   : partition_impl<8>(e, d_keys, d_vals, n_rows, lg, d_out_keys, d_out_vals, d_offsets, (cudaStream_t)stream);
+}
+
+uint32_t dwj_partition_of(uint64_t key, int32_t key_bytes, uint32_t n_parts, uint64_t hash_seed) {
+  uint32_t lg = 0;
+  while ((1u << lg) < n_parts) ++lg;
+  return key_bytes == 4 ? dwj::partition_of((uint32_t)key, lg, hash_seed) : dwj::partition_of((uint64_t)key, lg, hash_seed);
+}
+
+// ---- host-buffer join ---------------------------------------------------------------------------------
+// Build columns go up in one piece; the probe relation is streamed in chunks over two streams so the
+// H2D of chunk i+1 and the D2H of chunk i-1 overlap the probe of chunk i (PCIe is full duplex).
+int dwj_join_host(dwj_engine *e, const void *build_keys, const void *build_vals, uint64_t n_build, const void *probe_keys,
+                  const void *probe_vals, uint64_t n_probe, int out_mode, void *out_key, void *out_build_val,
+                  void *out_probe_val, uint64_t out_capacity, uint64_t *n_out, dwj_timing *timing) {
+  if (int rc = check_engine(e)) return rc;
+  if (out_mode < DWJ_OUT_ALIGNED || out_mode > DWJ_OUT_COUNT) return fail(DWJ_ERR_INVALID, "bad out_mode %d", out_mode);
+  if ((n_build && (!build_keys || !build_vals)) || (n_probe && (!probe_keys || !probe_vals)))
+    return fail(DWJ_ERR_INVALID, "null input column");
+  if (out_mode == DWJ_OUT_ALIGNED && n_probe && (!out_key || !out_build_val || !out_probe_val))
+    return fail(DWJ_ERR_INVALID, "ALIGNED output needs all three columns");
+  if (out_mode == DWJ_OUT_PAIRS && out_capacity && (!out_build_val || !out_probe_val))
+    return fail(DWJ_ERR_INVALID, "PAIRS output needs the two payload columns");
+  if (out_mode != DWJ_OUT_ALIGNED && !n_out) return fail(DWJ_ERR_INVALID, "n_out is required");
+  if (n_build > e->cfg.max_build_rows && (double)n_build > 0.9 * (double)e->slots)
+    return fail(DWJ_ERR_CAPACITY, "%llu build rows exceed the table created for %llu", (unsigned long long)n_build,
+                (unsigned long long)e->cfg.max_build_rows);
+  DeviceGuard g(e->cfg.device);
+  const uint64_t W = (uint64_t)e->W;
+  const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint64_t>(n_probe, 1), HOST_CHUNK_BYTES / W));
+  // staging: build k,v | 2 stages x (probe k,v + out k,b,p) | 2 counters
+  const uint64_t build_b = ((n_build * W + 255) / 256) * 256, chunk_b = ((chunk_rows * W + 255) / 256) * 256;
+  const uint64_t need = 2 * build_b + 2 * 5 * chunk_b + 512;
+  if (need > e->stage_bytes) {
+    if (e->stage) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->stage)); e->stage = nullptr; e->stage_bytes = 0; }
+    CU(cudaMalloc(&e->stage, need));
+    e->stage_bytes = need;
+  }
+  for (int i = 0; i < 2; ++i)
+    if (!e->hs[i]) CU(cudaStreamCreateWithFlags(&e->hs[i], cudaStreamNonBlocking));
+  for (auto &ev : e->hev)
+    if (!ev) CU(cudaEventCreate(&ev));
+  char *base = (char *)e->stage;
+  char *d_bk = base, *d_bv = base + build_b;
+  char *stage_base = base + 2 * build_b;
+  unsigned long long *d_cnt = (unsigned long long *)(stage_base + 10 * chunk_b);
+  cudaStream_t s0 = e->hs[0];
+
+  // hev: 0 start, 1 build h2d done, 2 build done, 3 end
+  CU(cudaEventRecord(e->hev[0], s0));
+  if (n_build) {
+    CU(cudaMemcpyAsync(d_bk, build_keys, n_build * W, cudaMemcpyHostToDevice, s0));
+    CU(cudaMemcpyAsync(d_bv, build_vals, n_build * W, cudaMemcpyHostToDevice, s0));
+  }
+  CU(cudaEventRecord(e->hev[1], s0));
+  if (int rc = dwj_build(e, d_bk, d_bv, n_build, s0)) return rc;
+  CU(cudaEventRecord(e->hev[2], s0));
+  CU(cudaStreamWaitEvent(e->hs[1], e->hev[2], 0));
+
+  uint64_t produced = 0;       // rows written to the host outputs so far (PAIRS) / matches (COUNT)
+  bool overflow = false;
+  const uint64_t n_chunks = (n_probe + chunk_rows - 1) / chunk_rows;
+  struct Pending { bool active = false; uint64_t rows = 0; } pend[2];
+  auto stage_ptr = [&](int st, int col) { return stage_base + (uint64_t)(st * 5 + col) * chunk_b; };
+
+  // Finish stage st (PAIRS / COUNT): wait for its probe, learn its match count, enqueue its D2H.
+  auto drain = [&](int st) -> int {
+    Pending &p = pend[st];
+    if (!p.active) return DWJ_OK;
+    p.active = false;
+    cudaStream_t s = e->hs[st];
+    unsigned long long c = 0;
+    CU(cudaMemcpyAsync(&c, d_cnt + st * 8, sizeof(c), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (out_mode == DWJ_OUT_PAIRS) {
+      if (c > chunk_rows)
+        return fail(DWJ_ERR_OVERFLOW,
+                    "a probe chunk of %llu rows produced %llu matches; dwj_join_host stages at most one match per probe "
+                    "row -- use dwj_probe_pairs with device buffers for higher multiplicities",
+                    (unsigned long long)p.rows, c);
+      const uint64_t room = produced < out_capacity ? out_capacity - produced : 0;
+      const uint64_t take = std::min<uint64_t>(c, room);
+      if (take < c) overflow = true;
+      if (take) {
+        if (out_key) CU(cudaMemcpyAsync((char *)out_key + produced * W, stage_ptr(st, 2), take * W, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync((char *)out_build_val + produced * W, stage_ptr(st, 3), take * W, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync((char *)out_probe_val + produced * W, stage_ptr(st, 4), take * W, cudaMemcpyDeviceToHost, s));
+      }
+    }
+    produced += c;
+    return DWJ_OK;
+  };
+
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    const int st = (int)(c & 1);
+    cudaStream_t s = e->hs[st];
+    // Stage st's previous chunk was drained one iteration ago; its D2H copies sit earlier in this same
+    // stream, so stream order protects the buffers that are overwritten now.
+    const uint64_t row0 = c * chunk_rows, rows = std::min<uint64_t>(chunk_rows, n_probe - row0);
+    CU(cudaMemcpyAsync(stage_ptr(st, 0), (const char *)probe_keys + row0 * W, rows * W, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(stage_ptr(st, 1), (const char *)probe_vals + row0 * W, rows * W, cudaMemcpyHostToDevice, s));
+    int rc;
+    if (out_mode == DWJ_OUT_ALIGNED) {
+      rc = dwj_probe_aligned(e, stage_ptr(st, 0), stage_ptr(st, 1), rows, stage_ptr(st, 2), stage_ptr(st, 3), stage_ptr(st, 4), s);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync((char *)out_key + row0 * W, stage_ptr(st, 2), rows * W, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpyAsync((char *)out_build_val + row0 * W, stage_ptr(st, 3), rows * W, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpyAsync((char *)out_probe_val + row0 * W, stage_ptr(st, 4), rows * W, cudaMemcpyDeviceToHost, s));
+      continue;
+    }
+    if (out_mode == DWJ_OUT_PAIRS)
+      rc = dwj_probe_pairs(e, stage_ptr(st, 0), stage_ptr(st, 1), rows, out_key ? stage_ptr(st, 2) : nullptr, stage_ptr(st, 3),
+                           stage_ptr(st, 4), chunk_rows, (uint64_t *)(d_cnt + st * 8), nullptr, s);
+    else
+      rc = dwj_probe_count(e, stage_ptr(st, 0), rows, (uint64_t *)(d_cnt + st * 8), nullptr, s);
+    if (rc) return rc;
+    pend[st].active = true;
+    pend[st].rows = rows;
+    if (int rc2 = drain(1 - st)) return rc2;    // chunk c-1: overlaps with chunk c's H2D + probe
+  }
+  if (int rc = drain((int)(n_chunks & 1))) return rc;          // the older of the two outstanding chunks first
+  if (int rc = drain((int)((n_chunks + 1) & 1))) return rc;
+  CU(cudaStreamSynchronize(e->hs[0]));
+  CU(cudaStreamSynchronize(e->hs[1]));
+  CU(cudaEventRecord(e->hev[3], s0));
+  CU(cudaEventSynchronize(e->hev[3]));
+
+  dwj_timing t{};
+  CU(cudaEventElapsedTime(&t.h2d_ms, e->hev[0], e->hev[1]));
+  CU(cudaEventElapsedTime(&t.build_ms, e->hev[1], e->hev[2]));
+  CU(cudaEventElapsedTime(&t.total_ms, e->hev[0], e->hev[3]));
+  t.probe_ms = std::max(0.f, t.total_ms - t.h2d_ms - t.build_ms);   // the streamed probe phase, copies overlapped
+  e->last_host = t;
+  if (timing) *timing = t;
+  if (n_out) *n_out = out_mode == DWJ_OUT_ALIGNED ? n_probe : produced;
+  if (overflow) return fail(DWJ_ERR_OVERFLOW, "join produced %llu rows, output capacity is %llu", (unsigned long long)produced, (unsigned long long)out_capacity);
+  return DWJ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// table.cuh -- slot / bucket layout and hash functions of the join table.
+//
+// Layout (HBM): an array of 32-byte BUCKETS, one bucket == one DRAM/L2 sector.
+//   key_bytes 4: bucket = 4 slots of 8 B,  slot = key | payload << 32
+//   key_bytes 8: bucket = 2 slots of 16 B, slot = { key, payload }
+// The bucket count is a power of two; bucket(key) = hash(key) & (buckets - 1); a chain
+// continues in the next bucket (linear probing at sector granularity).  A probe therefore
+// costs exactly one 32 B sector (one LDG.256) unless the home bucket is full.
+// Empty slots are all-ones (the reference's `empty_element`, join/join.cpp:10).
+//
+// This replaces SimpleNonOwningHashTable's three separate arrays (keys[], vals[], bitmask[],
+// common/dpcpp/hashtable.hpp:59-66), which cost three dependent sectors per lookup.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dwj {
+
+#if defined(__CUDACC__)
+#define DWJ_HD __host__ __device__ __forceinline__
+#define DWJ_D __device__ __forceinline__
+#else
+#define DWJ_HD inline
+#define DWJ_D inline
+#endif
+
+// ---- hashing ---------------------------------------------------------------------------
+// Slot hash: the Murmur3 finalisers (fmix32 is the reference's own finaliser,
+// common/dpcpp/hashfunctions.hpp:77-85).  The full MurmurHash3_x86_32 body adds nothing for a
+// single 4-byte block and the hash choice cannot change the match multiset.
+DWJ_HD uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85ebca6bu;
+  h ^= h >> 13;
+  h *= 0xc2b2ae35u;
+  h ^= h >> 16;
+  return h;
+}
+DWJ_HD uint64_t fmix64(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+
+template <int W> struct KeyT;
+template <> struct KeyT<4> { using type = uint32_t; };
+template <> struct KeyT<8> { using type = uint64_t; };
+
+// Bucket hash (low bits are used) and partition hash (top bits are used).  For 4-byte keys the
+// partition hash is a second, differently-keyed mix so that partition id and bucket index are
+// independent; for 8-byte keys one 64-bit mix has enough bits for both ends.
+DWJ_HD uint64_t slot_hash(uint32_t key, uint64_t seed) { return fmix32(key ^ (uint32_t)seed); }
+DWJ_HD uint64_t slot_hash(uint64_t key, uint64_t seed) { return fmix64(key ^ seed); }
+DWJ_HD uint32_t part_hash32(uint32_t key, uint64_t seed) {
+  return fmix32(key * 0x9E3779B1u + (uint32_t)(seed >> 32) + 0x7F4A7C15u);
+}
+DWJ_HD uint32_t partition_of(uint32_t key, uint32_t log2_parts, uint64_t seed) {
+  return log2_parts ? part_hash32(key, seed) >> (32 - log2_parts) : 0u;
+}
+DWJ_HD uint32_t partition_of(uint64_t key, uint32_t log2_parts, uint64_t seed) {
+  return log2_parts ? (uint32_t)(fmix64(key ^ seed) >> (64 - log2_parts)) : 0u;
+}
+
+#if defined(__CUDACC__)
+
+// ---- bucket access -----------------------------------------------------------------------
+template <int W> struct Bucket;
+
+template <> struct Bucket<4> {
+  using key_t = uint32_t;
+  static constexpr int SLOTS = 4;
+  unsigned long long s[4];  // key | payload << 32
+  static DWJ_D unsigned long long pack(uint32_t k, uint32_t v) {
+    return (unsigned long long)k | ((unsigned long long)v << 32);
+  }
+  DWJ_D bool empty(int i) const { return s[i] == ~0ull; }
+  DWJ_D bool match(int i, uint32_t k) const { return (uint32_t)s[i] == k && s[i] != ~0ull; }
+  DWJ_D uint32_t payload(int i) const { return (uint32_t)(s[i] >> 32); }
+  DWJ_D bool any_empty() const { return s[3] == ~0ull || s[2] == ~0ull || s[1] == ~0ull || s[0] == ~0ull; }
+};
+
+template <> struct Bucket<8> {
+  using key_t = uint64_t;
+  static constexpr int SLOTS = 2;
+  unsigned long long s[4];  // k0, v0, k1, v1
+  DWJ_D bool empty(int i) const { return s[2 * i] == ~0ull; }
+  DWJ_D bool match(int i, uint64_t k) const { return s[2 * i] == k && k != ~0ull; }
+  DWJ_D uint64_t payload(int i) const { return s[2 * i + 1]; }
+  DWJ_D bool any_empty() const { return s[2] == ~0ull || s[0] == ~0ull; }
+};
+
+// One 32-byte sector in one instruction (LDG.E.256, sm_100+).  Read-only path for the probe
+// (the table is immutable while a probe kernel runs); L1 is bypassed -- a random sector is
+// never re-used by the same SM -- and the line is marked evict_last in L2 so that the
+// streaming probe columns do not push the table out.
+template <int W> DWJ_D Bucket<W> load_bucket_ro(const void *table, uint64_t b) {
+  Bucket<W> r;
+  const char *p = (const char *)table + (b << 5);
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(r.s[0]), "=l"(r.s[1]), "=l"(r.s[2]), "=l"(r.s[3])
+               : "l"(p));
+  return r;
+}
+// Coherent variant for the build kernel (other CTAs are inserting concurrently): L2 is the
+// point of coherence, so skip L1 (.cg).  A stale view can only show a slot as still empty, and
+// the CAS that follows corrects that.
+template <int W> DWJ_D Bucket<W> load_bucket_cg(const void *table, uint64_t b) {
+  Bucket<W> r;
+  const char *p = (const char *)table + (b << 5);
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(r.s[0]), "=l"(r.s[1]), "=l"(r.s[2]), "=l"(r.s[3])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+
+// ---- streaming column access ---------------------------------------------------------------
+template <class T> DWJ_D T load_stream(const T *p) { return __ldcs(p); }   // ld.global.cs: evict-first
+template <class T> DWJ_D void store_stream(T *p, T v) { __stcs(p, v); }    // st.global.cs
+
+#endif  // __CUDACC__
+
+}  // namespace dwj

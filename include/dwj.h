@@ -1,0 +1,174 @@
+/*
+ * dwj.h -- C ABI of the B200-native hash-join engine (libdwj_b200.so).
+ *
+ * This is the drop-in boundary for dwarf_bench's Join hot path.  Plain C, POD
+ * structs, raw device/host pointers and sizes only: no C++ types, no torch
+ * types, no exceptions across the boundary.  Every call returns 0 on success
+ * or a negative DWJ_ERR_* code; dwj_last_error() holds the message for the
+ * calling thread.  There is NO CPU fallback: when no CUDA device is usable the
+ * calls fail with DWJ_ERR_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to kurapov-peter/dwarf_bench):
+ *   dwj_build            kernel `join_build`  join/join.cpp:60-77
+ *                        = SimpleNonOwningHashTable::insert
+ *                          common/dpcpp/hashtable.hpp:15-21,70-92;
+ *                        kernel `hash_build`  hash/hash_build.cpp:36-50
+ *   dwj_probe_aligned    kernel `join_probe`  join/join.cpp:80-104
+ *                        = SimpleNonOwningHashTable::at  hashtable.hpp:23-40,
+ *                          probe-aligned 0xFFFFFFFF-filled outputs join.cpp:41-43
+ *   dwj_probe_contains   kernel `hash_build_check` hash/hash_build.cpp:61-76
+ *                        = SimpleNonOwningHashTable::has hashtable.hpp:42-58;
+ *                        SlabHashTable::find as used by probe/slab_probe.cpp:69-86
+ *   dwj_probe_pairs      host compaction loop join/join.cpp:119-129, moved on
+ *                        device; row definition = join_helpers::seq_join
+ *                        join/join_helpers/join_helpers.hpp:85-104
+ *   dwj_probe_count      size of that row list (join_helpers.hpp:21-25 get_size)
+ *   dwj_join_host        the whole timed region join/join.cpp:45-113 with the
+ *                        implicit sycl::buffer H2D/D2H copies made explicit
+ *   dwj_timings          HashJoinResult{build_time,probe_time,host_time,
+ *                        kernel_time}  common/result.hpp:11-33
+ *   dwj_partition        new (no reference counterpart): radix partition on
+ *                        the key hash for the multi-GPU exchange
+ */
+#ifndef DWJ_H
+#define DWJ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DWJ_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DWJ_API __attribute__((visibility("default")))
+#else
+#define DWJ_API
+#endif
+
+/* error codes */
+#define DWJ_OK 0
+#define DWJ_ERR_INVALID (-1)   /* bad argument                                        */
+#define DWJ_ERR_CUDA (-2)      /* CUDA runtime error / no device                       */
+#define DWJ_ERR_OOM (-3)       /* device or host allocation failed                     */
+#define DWJ_ERR_OVERFLOW (-4)  /* output capacity too small; *n_matches holds the need */
+#define DWJ_ERR_STATE (-5)     /* call order (probe before build, ...)                 */
+#define DWJ_ERR_CAPACITY (-6)  /* more build rows than the table was created for       */
+
+/* dwj_config.flags */
+#define DWJ_FLAG_UNIQUE_BUILD_KEYS 0x1u /* build keys are distinct: a probe row stops at its
+                                           first hit (SimpleNonOwningHashTable::at semantics).
+                                           Without it every equal build row is matched
+                                           (seq_join semantics).                           */
+#define DWJ_FLAG_L2_PERSIST 0x2u        /* pin the table in L2 with an access-policy window
+                                           when it fits the device's persisting-L2 limit    */
+
+typedef struct dwj_engine dwj_engine; /* opaque; owns the table and all scratch device memory */
+
+typedef struct {
+  int32_t device;          /* CUDA device ordinal                                         */
+  int32_t key_bytes;       /* 4 (uint32 keys, the reference's type) or 8 (uint64)         */
+  int32_t payload_bytes;   /* must equal key_bytes                                        */
+  uint32_t flags;          /* DWJ_FLAG_*                                                  */
+  uint64_t max_build_rows; /* table capacity in rows                                      */
+  double load_factor;      /* (0, 0.9]; slots = next_pow2(max_build_rows / load_factor);
+                              0 selects the reference's 0.5 (join/join.cpp:30: T = 2n)    */
+  uint64_t hash_seed;      /* mixes into the slot hash (reference: MurmurHash3 seed,
+                              join/join.cpp:32); does not affect results                  */
+} dwj_config;
+
+typedef struct {
+  float build_ms;     /* device time of the last dwj_build (table clear + insert)          */
+  float probe_ms;     /* device time of the last dwj_probe_*                               */
+  float partition_ms; /* device time of the last dwj_partition                             */
+  float h2d_ms;       /* dwj_join_host only: host->device copies                           */
+  float d2h_ms;       /* dwj_join_host only: device->host copies                           */
+  float total_ms;     /* dwj_join_host: first copy to last copy; else build_ms + probe_ms  */
+} dwj_timing;
+
+typedef struct {
+  uint64_t slots;            /* table slots (power of two)                                 */
+  uint64_t table_bytes;      /* bytes of the slot array                                    */
+  uint64_t build_rows;       /* rows inserted by the last dwj_build                        */
+  uint32_t slot_bytes;       /* key_bytes + payload_bytes                                  */
+  uint32_t slots_per_bucket; /* slots in one 32-byte sector                                */
+  uint32_t l2_persist;       /* 1 when an access-policy window is active for the table     */
+  uint32_t sm_count;
+  uint64_t l2_bytes;
+  uint32_t launches_build;   /* kernels (incl. memsets) one dwj_build enqueues             */
+  uint32_t launches_probe;   /* kernels (incl. memsets) the last dwj_probe_* enqueued      */
+} dwj_info;
+
+DWJ_API int dwj_abi_version(void);
+DWJ_API const char *dwj_last_error(void);
+
+DWJ_API int dwj_create(const dwj_config *cfg, dwj_engine **out);
+DWJ_API int dwj_destroy(dwj_engine *e);
+DWJ_API int dwj_get_info(const dwj_engine *e, dwj_info *info);
+
+/* Insert n_rows (key, payload) pairs from DEVICE columns into a freshly cleared table.
+ * Duplicate keys each take their own slot (as hashtable.hpp:15-21 does).  `stream` is a
+ * cudaStream_t (NULL = the legacy default stream).  Asynchronous. */
+DWJ_API int dwj_build(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *stream);
+
+/* Reference-shaped probe: for probe row i writes (key, build payload, probe payload) at index i
+ * when the key is present, all-ones sentinels otherwise (join/join.cpp:41-43,93-103).  First hit
+ * wins, as SimpleNonOwningHashTable::at.  Outputs are n_rows long.  Asynchronous. */
+DWJ_API int dwj_probe_aligned(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows,
+                      void *d_out_key, void *d_out_build_val, void *d_out_probe_val, void *stream);
+
+/* d_out_flags[i] (uint32) = 1 when probe key i is in the table, else 0.  Asynchronous. */
+DWJ_API int dwj_probe_contains(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t *d_out_flags,
+                       void *stream);
+
+/* Compacted join output in probe-row order: row r of the result is
+ * (d_out_key[r], d_out_build_val[r], d_out_probe_val[r]); d_out_key may be NULL to skip the key
+ * column.  At most `capacity` rows are written; the total match count is stored to *d_n_matches
+ * (device, uint64) and, when n_matches != NULL, the call synchronises the stream and returns it
+ * on the host too (DWJ_ERR_OVERFLOW when it exceeds capacity).  With n_matches == NULL the call
+ * is asynchronous. */
+DWJ_API int dwj_probe_pairs(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows,
+                    void *d_out_key, void *d_out_build_val, void *d_out_probe_val,
+                    uint64_t capacity, uint64_t *d_n_matches, uint64_t *n_matches, void *stream);
+
+/* Match count only (no materialisation).  Same n_matches convention as dwj_probe_pairs. */
+DWJ_API int dwj_probe_count(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint64_t *d_n_matches,
+                    uint64_t *n_matches, void *stream);
+
+/* Device time of the last build / probe / partition on this engine (cudaEvent pairs on the
+ * caller's stream).  Synchronises on those events. */
+DWJ_API int dwj_timings(dwj_engine *e, dwj_timing *t);
+
+/* output shapes for dwj_join_host */
+#define DWJ_OUT_ALIGNED 0 /* probe-aligned sentinel arrays, n_probe long (reference shape) */
+#define DWJ_OUT_PAIRS 1   /* compacted rows, *n_out of them                                */
+#define DWJ_OUT_COUNT 2   /* only *n_out                                                   */
+
+/* The whole join with HOST columns: H2D of both relations, build, probe, D2H of the result --
+ * what the reference's sycl::buffer scopes do implicitly inside its timed window
+ * (join/join.cpp:45-117).  The probe relation is streamed through in chunks so copies overlap
+ * the kernels.  Host pointers may be pageable; pinned memory makes the copies asynchronous.
+ * out_* must hold n_probe rows (ALIGNED) or out_capacity rows (PAIRS); out_key may be NULL. */
+DWJ_API int dwj_join_host(dwj_engine *e, const void *build_keys, const void *build_vals, uint64_t n_build,
+                  const void *probe_keys, const void *probe_vals, uint64_t n_probe, int out_mode,
+                  void *out_key, void *out_build_val, void *out_probe_val, uint64_t out_capacity,
+                  uint64_t *n_out, dwj_timing *timing);
+
+/* Radix partition of DEVICE columns on the key hash, for the multi-GPU exchange: rows whose
+ * partition id (top hash bits, independent of the slot hash) is p end up contiguous in
+ * d_out_keys/d_out_vals[d_offsets[p] .. d_offsets[p+1]).  n_parts must be a power of two <= 256.
+ * d_offsets: n_parts + 1 uint64 (device).  d_out_vals/d_vals may both be NULL.  Asynchronous. */
+DWJ_API int dwj_partition(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows,
+                  uint32_t n_parts, void *d_out_keys, void *d_out_vals, uint64_t *d_offsets,
+                  void *stream);
+
+/* Partition id of one key on the host (same function the kernels use) -- lets callers and tests
+ * reason about placement without a device. */
+DWJ_API uint32_t dwj_partition_of(uint64_t key, int32_t key_bytes, uint32_t n_parts, uint64_t hash_seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DWJ_H */

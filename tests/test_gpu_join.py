@@ -1,0 +1,344 @@
+"""Parity of the CUDA engine (through the C ABI, include/dwj.h) with the CPU oracle.
+
+Every test here needs a B200 (`-m gpu`).  Inputs are seeded; the same arrays go to the oracle and the
+engine (the reference's own generator is unseeded).  Bar: bit-exact match multiset
+(sorted (key, build payload, probe payload) rows, join_helpers.hpp:106-125), and -- for unique build
+keys -- bit-exact probe-aligned arrays and bit-exact compaction ORDER (join.cpp:119-129).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def dwj():
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+    import dwarf_bench_b200 as d
+    d.load_library()        # hard failure when the extension is missing -- no fallback exists
+    return d
+
+
+def dev(a: np.ndarray):
+    """numpy uint32/uint64 column -> device tensor (same bits, signed torch dtype)."""
+    a = np.ascontiguousarray(a)
+    signed = a.view(np.int32 if a.dtype.itemsize == 4 else np.int64)
+    return torch.from_numpy(signed).cuda()
+
+
+def host(t, dtype):
+    return t.cpu().numpy().view(dtype)
+
+
+def empty_like_dev(n, dtype):
+    return torch.empty(max(n, 1), dtype=torch.int32 if np.dtype(dtype).itemsize == 4 else torch.int64, device="cuda")
+
+
+def gpu_join_pairs(dwj, ak, av, bk, bv, unique=False, capacity=None, load_factor=0.0, with_key=True):
+    dt = ak.dtype
+    flags = dwj.FLAG_UNIQUE_BUILD_KEYS if unique else 0
+    with dwj.Engine(max(len(ak), 1), key_bytes=dt.itemsize, flags=flags, load_factor=load_factor) as e:
+        dak, dav, dbk, dbv = dev(ak), dev(av), dev(bk), dev(bv)
+        e.build(dak, dav, len(ak))
+        if capacity is None:
+            capacity = e.probe_count(dbk, len(bk))
+        ok, oa, ob = (empty_like_dev(capacity, dt) for _ in range(3))
+        m = e.probe_pairs(dbk, dbv, len(bk), ok if with_key else None, oa, ob, capacity)
+        torch.cuda.synchronize()
+        return (host(ok, dt)[:m] if with_key else None), host(oa, dt)[:m], host(ob, dt)[:m]
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden vectors
+# ---------------------------------------------------------------------------------------------------
+
+def test_join_tests_golden_vector(dwj, golden_dir):
+    """tests/join_tests.cpp:7-23: 7x7 with a duplicated key on both sides -> exactly 8 rows."""
+    g = json.load(open(os.path.join(golden_dir, "join_tests_golden.json")))
+    ak, av, bk, bv = (np.array(g[k], np.uint32) for k in ("keys_a", "vals_a", "keys_b", "vals_b"))
+    k, a, b = gpu_join_pairs(dwj, ak, av, bk, bv)
+    assert len(k) == 8
+    got = sorted(zip(k.tolist(), a.tolist(), b.tolist()))
+    assert got == sorted(map(tuple, g["rows_emission_order"]))
+
+
+@pytest.mark.parametrize("case", ["unique128", "unique1024", "unique4096", "dups", "empty_build", "no_match",
+                                  "edge_keys", "u64"])
+def test_reference_seq_join_fixtures(dwj, golden_dir, case):
+    """Rows the reference's own seq_join produced (tests/golden/make_golden.py) == engine rows."""
+    g = np.load(os.path.join(golden_dir, "seq_join_golden.npz"))
+    ak, av, bk, bv = (g[f"{case}.{n}"] for n in ("ak", "av", "bk", "bv"))
+    want = tuple(g[f"{case}.{n}"] for n in ("k", "a", "b"))
+    got = pyoracle.canonical_rows(*gpu_join_pairs(dwj, ak, av, bk, bv))
+    for w, x in zip(want, got):
+        np.testing.assert_array_equal(w, x)
+    if case.startswith("unique"):       # the first-hit fast path must agree when keys really are unique
+        got = pyoracle.canonical_rows(*gpu_join_pairs(dwj, ak, av, bk, bv, unique=True))
+        for w, x in zip(want, got):
+            np.testing.assert_array_equal(w, x)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference Join dwarf's shape (join/join.cpp), sizes of tests/dwarf_tests/dwarf_tests.cpp:44-50
+# ---------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [128, 256, 512, 1024, 2048, 4096, 1 << 20])
+def test_join_dwarf_shape(dwj, oracle, n):
+    ak, av, bk, bv = (oracle.make_unique_random(n, s) for s in (1, 2, 3, 4))
+    (wk, wp, wv), _ = oracle.join_build_probe(ak, av, bk, bv, seed=42)       # Join::_run restated
+    with dwj.Engine(n, key_bytes=4, flags=dwj.FLAG_UNIQUE_BUILD_KEYS) as e:
+        dak, dav, dbk, dbv = dev(ak), dev(av), dev(bk), dev(bv)
+        e.build(dak, dav, n)
+        ok, op, ov = (empty_like_dev(n, np.uint32) for _ in range(3))
+        e.probe_aligned(dbk, dbv, n, ok, op, ov)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(host(ok, np.uint32), wk)               # probe-aligned, sentinel-filled
+        np.testing.assert_array_equal(host(op, np.uint32), wp)
+        np.testing.assert_array_equal(host(ov, np.uint32), wv)
+        # device compaction == the reference's host compaction loop, same ORDER (join.cpp:119-129)
+        ck, cp, cv = oracle.compact(wk, wp, wv)
+        m = e.probe_pairs(dbk, dbv, n, ok, op, ov, n)
+        torch.cuda.synchronize()
+        assert m == len(ck)
+        np.testing.assert_array_equal(host(ok, np.uint32)[:m], ck)
+        np.testing.assert_array_equal(host(op, np.uint32)[:m], cp)
+        np.testing.assert_array_equal(host(ov, np.uint32)[:m], cv)
+        assert e.probe_count(dbk, n) == m
+        t = e.timings()
+        assert t.build_ms > 0 and t.probe_ms > 0
+    want = oracle.sort_join(ak, av, bk, bv)
+    for w, x in zip(want, pyoracle.canonical_rows(ck, cp, cv)):
+        np.testing.assert_array_equal(w, x)
+
+
+@pytest.mark.parametrize("n", [128, 4096, 300000])
+def test_hash_build_dwarf_shape(dwj, oracle, n):
+    """HashBuild (hash/hash_build.cpp): keys in [1,10000] with heavy duplicates, val = key, has() == 1 for all."""
+    src = oracle.make_random(n, seed=n)
+    found, _, _ = oracle.hash_build_check(src, seed=5)
+    assert found == n
+    with dwj.Engine(n, key_bytes=4) as e:
+        d = dev(src)
+        e.build(d, d, n)
+        flags = torch.empty(n + 64, dtype=torch.int32, device="cuda")
+        e.probe_contains(d, n, flags)
+        absent = dev(np.arange(10001, 10065, dtype=np.uint32))
+        e.probe_contains(absent, 64, flags[n:])
+        torch.cuda.synchronize()
+        f = flags.cpu().numpy()
+        assert f[:n].sum() == n and f[n:].sum() == 0
+        # every duplicate took its own slot: matching the source against itself counts sum(c_k^2)
+        _, counts = np.unique(src, return_counts=True)
+        assert e.probe_count(d, n) == int((counts.astype(np.int64) ** 2).sum())
+
+
+# ---------------------------------------------------------------------------------------------------
+# one-to-many (seq_join semantics), skew, 64-bit
+# ---------------------------------------------------------------------------------------------------
+
+def zipf_ranks(rng, n_distinct, size, s=1.0):
+    w = 1.0 / np.arange(1, n_distinct + 1) ** s
+    cdf = np.cumsum(w) / w.sum()
+    return np.searchsorted(cdf, rng.random(size)).clip(0, n_distinct - 1)
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_duplicates_x4_zipf_probe(dwj, oracle, wide):
+    """BASELINE config 3 at test size: every distinct build key 4 times, Zipf(1.0) probe, compacted output."""
+    rng = np.random.default_rng(11)
+    dt = np.uint64 if wide else np.uint32
+    D, S = 1 << 14, 1 << 17
+    distinct = rng.choice(1 << 30, D, replace=False).astype(dt)
+    ak = np.repeat(distinct, 4)
+    rng.shuffle(ak)
+    av = np.arange(len(ak), dtype=dt)
+    bk = distinct[zipf_ranks(rng, D, S)]
+    bv = np.arange(S, dtype=dt)
+    k, a, b = gpu_join_pairs(dwj, ak, av, bk, bv)
+    assert len(k) == 4 * S
+    want = oracle.sort_join(ak, av, bk, bv)
+    for w, x in zip(want, pyoracle.canonical_rows(k, a, b)):
+        np.testing.assert_array_equal(w, x)
+
+
+def test_heavy_multiplicity(dwj, oracle):
+    """One key repeated 1000x on the build side: long chains across many buckets, all emitted."""
+    rng = np.random.default_rng(3)
+    ak = np.concatenate([np.full(1000, 77, np.uint32), rng.choice(100000, 3000, replace=False).astype(np.uint32) + 1000])
+    av = rng.integers(0, 2**32, len(ak), dtype=np.uint64).astype(np.uint32)
+    bk = np.concatenate([np.full(50, 77, np.uint32), ak[1000:1500], rng.integers(200000, 300000, 500).astype(np.uint32)])
+    bv = np.arange(len(bk), dtype=np.uint32)
+    got = pyoracle.canonical_rows(*gpu_join_pairs(dwj, ak, av, bk, bv))
+    want = oracle.sort_join(ak, av, bk, bv)
+    assert len(want[0]) == 50 * 1000 + 500
+    for w, x in zip(want, got):
+        np.testing.assert_array_equal(w, x)
+
+
+@pytest.mark.parametrize("lf", [0.25, 0.5, 0.9])
+def test_u64_random_with_load_factors(dwj, oracle, lf):
+    rng = np.random.default_rng(int(lf * 100))
+    n = 200003                                                  # not a multiple of any tile
+    ak = rng.integers(0, 2**64 - 2, n, dtype=np.uint64)
+    av = rng.integers(0, 2**64 - 1, n, dtype=np.uint64)
+    bk = np.concatenate([ak[rng.integers(0, n, 150000)], rng.integers(0, 2**64 - 2, 50001, dtype=np.uint64)])
+    bv = rng.integers(0, 2**64 - 1, len(bk), dtype=np.uint64)
+    got = pyoracle.canonical_rows(*gpu_join_pairs(dwj, ak, av, bk, bv, load_factor=lf))
+    want = oracle.sort_join(ak, av, bk, bv)
+    for w, x in zip(want, got):
+        np.testing.assert_array_equal(w, x)
+
+
+# ---------------------------------------------------------------------------------------------------
+# edge cases and error behaviour
+# ---------------------------------------------------------------------------------------------------
+
+def test_empty_and_ragged_inputs(dwj):
+    z = np.zeros(0, np.uint32)
+    one = np.array([5], np.uint32)
+    k, a, b = gpu_join_pairs(dwj, z, z, one, one, capacity=4)          # empty build
+    assert len(k) == 0
+    k, a, b = gpu_join_pairs(dwj, one, one, z, z, capacity=4)          # empty probe
+    assert len(k) == 0
+    k, a, b = gpu_join_pairs(dwj, one, np.array([9], np.uint32), np.array([5, 6, 5], np.uint32),
+                             np.array([1, 2, 3], np.uint32), capacity=4)
+    assert (k.tolist(), a.tolist(), b.tolist()) == ([5, 5], [9, 9], [1, 3])
+    # extreme key values; all-ones is the reserved empty marker (join.cpp:10 empty_element)
+    ak = np.array([0, 0xFFFFFFFE, 0x80000000], np.uint32)
+    k, a, b = gpu_join_pairs(dwj, ak, ak + 1, ak[::-1].copy(), ak, capacity=8)
+    assert sorted(zip(k.tolist(), a.tolist())) == sorted(zip(ak.tolist(), (ak + 1).tolist()))
+
+
+def test_key_column_optional(dwj, oracle):
+    ak, av, bk, bv = (oracle.make_unique_random(5000, s) for s in (5, 6, 7, 8))
+    k, a, b = gpu_join_pairs(dwj, ak, av, bk, bv, unique=True)
+    k2, a2, b2 = gpu_join_pairs(dwj, ak, av, bk, bv, unique=True, with_key=False)
+    assert k2 is None
+    np.testing.assert_array_equal(a, a2)
+    np.testing.assert_array_equal(b, b2)
+
+
+def test_error_codes(dwj):
+    with pytest.raises(dwj.DwjError) as ei:
+        dwj.Engine(10, key_bytes=3)
+    assert ei.value.code == -1
+    with pytest.raises(dwj.DwjError) as ei:
+        dwj.Engine(10, load_factor=0.99)
+    assert ei.value.code == -1
+    with pytest.raises(dwj.DwjError) as ei:
+        dwj.Engine(10, device=99)
+    assert ei.value.code == -1
+    k = dev(np.arange(100, dtype=np.uint32))
+    with dwj.Engine(16) as e:
+        with pytest.raises(dwj.DwjError) as ei:                         # probe before build
+            e.probe_count(k, 100)
+        assert ei.value.code == -5
+        with pytest.raises(dwj.DwjError) as ei:                         # more rows than the table holds
+            e.build(k, k, 100)
+        assert ei.value.code == -6
+        e.build(k, k, 16)
+        out = empty_like_dev(4, np.uint32)
+        with pytest.raises(dwj.DwjError) as ei:                         # capacity too small: count still exact
+            e.probe_pairs(k, k, 100, out, out, out, 4)
+        assert ei.value.code == -4 and "16" in str(ei.value)
+        assert e.info()["slots"] == 32 and e.info()["slots_per_bucket"] == 4
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-buffer entry point (the reference's sycl::buffer-style call) and the partition kernels
+# ---------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("wide,n_build,n_probe", [(False, 1 << 16, 1 << 18), (True, 50000, 70001),
+                                                   (False, 1 << 20, (16 << 20) * 2 + 12345)])
+def test_join_host_buffers(dwj, wide, n_build, n_probe):
+    """FK->PK join through dwj_join_host with pageable numpy buffers; the largest case spans three probe
+    chunks so the double-buffered copy/probe pipeline and the running output offset are exercised."""
+    rng = np.random.default_rng(n_probe)
+    dt = np.uint64 if wide else np.uint32
+    ak = rng.permutation(n_build).astype(dt) * dt(2654435761 if not wide else 0x9E3779B97F4A7C15) + dt(1)
+    assert len(np.unique(ak)) == n_build
+    av = np.arange(n_build, dtype=dt)
+    idx = rng.integers(0, n_build, n_probe)
+    hit = rng.random(n_probe) < 0.75
+    bk = np.where(hit, ak[idx], ak[idx] ^ dt(0x55555555))            # ~25% keys that are (almost surely) absent
+    present = np.isin(bk, ak)
+    bv = np.arange(n_probe, dtype=dt)
+    lookup = dict()                                                 # expected payload by key, vectorised via sort
+    order = np.argsort(ak)
+    pos = np.searchsorted(ak[order], bk[present])
+    want_a = av[order][pos]
+    want_k, want_b = bk[present], bv[present]
+    with dwj.Engine(n_build, key_bytes=dt().itemsize, flags=dwj.FLAG_UNIQUE_BUILD_KEYS) as e:
+        ok, oa, ob = (np.empty(n_probe, dt) for _ in range(3))
+        m, t = e.join_host(ak, av, n_build, bk, bv, n_probe, dwj.OUT_PAIRS, ok, oa, ob, n_probe)
+        assert m == int(present.sum()) and t.total_ms > 0
+        np.testing.assert_array_equal(ok[:m], want_k)               # probe order is preserved across chunks
+        np.testing.assert_array_equal(oa[:m], want_a)
+        np.testing.assert_array_equal(ob[:m], want_b)
+        m2, _ = e.join_host(ak, av, n_build, bk, bv, n_probe, dwj.OUT_COUNT, None, None, None, 0)
+        assert m2 == m
+        n_al, _ = e.join_host(ak, av, n_build, bk, bv, n_probe, dwj.OUT_ALIGNED, ok, oa, ob, n_probe)
+        assert n_al == n_probe
+        sent = dt(~dt(0))
+        np.testing.assert_array_equal(ok, np.where(present, bk, sent))
+        np.testing.assert_array_equal(ob, np.where(present, bv, sent))
+        np.testing.assert_array_equal(oa[present], want_a)
+        assert (oa[~present] == sent).all()
+        with pytest.raises(dwj.DwjError) as ei:
+            e.join_host(ak, av, n_build, bk, bv, n_probe, dwj.OUT_PAIRS, ok, oa, ob, m - 1)
+        assert ei.value.code == -4
+    del lookup
+
+
+@pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("parts", [1, 2, 8, 256])
+def test_partition(dwj, wide, parts):
+    from dwarf_bench_b200 import capi
+    rng = np.random.default_rng(parts)
+    dt = np.uint64 if wide else np.uint32
+    n = 1_000_003
+    k = rng.integers(0, 2**31, n).astype(dt)
+    v = np.arange(n, dtype=dt)
+    with dwj.Engine(16, key_bytes=dt().itemsize, hash_seed=42) as e:
+        ok, ov = empty_like_dev(n, dt), empty_like_dev(n, dt)
+        offs = torch.zeros(parts + 1, dtype=torch.int64, device="cuda")
+        e.partition(dev(k), dev(v), n, parts, ok, ov, offs)
+        torch.cuda.synchronize()
+        offs = offs.cpu().numpy()
+        ok, ov = host(ok, dt)[:n], host(ov, dt)[:n]
+    assert offs[0] == 0 and offs[-1] == n and (np.diff(offs) >= 0).all()
+    np.testing.assert_array_equal(k[ov.astype(np.int64)], ok)        # (key, payload) pairs stay together
+    np.testing.assert_array_equal(np.sort(ov), v)                    # a permutation: nothing lost or duplicated
+    sample = rng.integers(0, n, 2000)
+    for i in sample:                                                 # every sampled row sits in its hash partition
+        p = capi.partition_of(int(ok[i]), dt().itemsize, parts, 42)
+        assert offs[p] <= i < offs[p + 1]
+    if parts > 1:
+        sizes = np.diff(offs)
+        assert sizes.max() < 1.2 * n / parts + 1000                  # hash spreads uniformly
+
+
+def test_table_larger_than_l2_int64(dwj):
+    """32M unique 64-bit keys (1 GiB table at load 0.5 -- far beyond the 126 MB L2), 64M FK probes, exact check
+    by gathering the expected payloads with torch (independent of the engine's kernels)."""
+    R, S = 1 << 25, 1 << 26
+    g = torch.Generator(device="cuda").manual_seed(13)
+    ak = torch.randperm(R, device="cuda", generator=g, dtype=torch.int64) * 0x9E3779B1 + 12345
+    av = torch.arange(R, device="cuda", dtype=torch.int64) * 3 + 1
+    idx = torch.randint(0, R, (S,), device="cuda", generator=g)
+    bk = ak[idx]
+    bv = torch.arange(S, device="cuda", dtype=torch.int64)
+    with dwj.Engine(R, key_bytes=8, flags=dwj.FLAG_UNIQUE_BUILD_KEYS) as e:
+        e.build(ak, av, R)
+        oa, ob = torch.empty_like(bk), torch.empty_like(bk)
+        m = e.probe_pairs(bk, bv, S, None, oa, ob, S)
+        assert m == S
+        assert torch.equal(oa, av[idx]) and torch.equal(ob, bv)
