@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 FLAG_UNIQUE_BUILD_KEYS = 0x1
 FLAG_L2_PERSIST = 0x2
+FLAG_UNORDERED_OUTPUT = 0x4
 OUT_ALIGNED, OUT_PAIRS, OUT_COUNT = 0, 1, 2
 
 ERR_NAMES = {0: "DWJ_OK", -1: "DWJ_ERR_INVALID", -2: "DWJ_ERR_CUDA", -3: "DWJ_ERR_OOM", -4: "DWJ_ERR_OVERFLOW",

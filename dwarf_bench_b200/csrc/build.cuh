@@ -24,10 +24,10 @@ template <int W> struct BuildArgs {
 // Slots are never emptied again, so when this returns false the bucket is full.
 DWJ_D bool insert_into_bucket(void *table, uint64_t b, const Bucket<4> &bk, uint32_t k, uint32_t v) {
   unsigned long long *bp = (unsigned long long *)table + (b << 2);
-  const unsigned long long mine = Bucket<4>::pack(k, v);
+  const unsigned long long mine = (unsigned long long)k | ((unsigned long long)v << 32);
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    if (bk.s[i] == ~0ull && atomicCAS(bp + i, ~0ull, mine) == ~0ull) return true;
+    if (bk.empty(i) && atomicCAS(bp + i, ~0ull, mine) == ~0ull) return true;
   return false;
 }
 DWJ_D bool insert_into_bucket(void *table, uint64_t b, const Bucket<8> &bk, uint64_t k, uint64_t v) {
@@ -36,12 +36,13 @@ DWJ_D bool insert_into_bucket(void *table, uint64_t b, const Bucket<8> &bk, uint
   const unsigned __int128 mine = (unsigned __int128)k | ((unsigned __int128)v << 64);
 #pragma unroll
   for (int i = 0; i < 2; ++i)
-    if (bk.s[2 * i] == ~0ull && atomicCAS(bp + i, empty, mine) == empty) return true;
+    if (bk.empty(i) && atomicCAS(bp + i, empty, mine) == empty) return true;
   return false;
 }
 
 template <int W, class K>
 DWJ_D void insert_row(void *table, uint64_t mask, uint64_t b, Bucket<W> bk, K k, K v) {
+  if (k == ~(K)0) return;               // reserved empty marker (table.cuh)
   for (;;) {
     if (insert_into_bucket(table, b, bk, k, v)) return;
     b = (b + 1) & mask;                 // linear probing at sector granularity

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -50,9 +51,14 @@ uint64_t next_pow2(uint64_t v) {
   return p;
 }
 
-constexpr int PROBE_THREADS = 256;
-constexpr int PROBE_ITEMS_4 = 8;    // rows per thread, 4-byte keys
-constexpr int PROBE_ITEMS_8 = 4;    // rows per thread, 8-byte keys
+// Staged PAIRS kernel (unique build keys): warps per CTA, rows per thread per round, rounds, min CTAs per SM.
+// DWJ_STAGED_SHAPE=0..4 picks one at run time for tuning sweeps (tools/probe_sweep.py); the default is what
+// profiles/ shows to be fastest.
+struct StagedShape { int warps, items, sub, minb; };
+constexpr StagedShape STAGED_SHAPES_4[] = {{8, 4, 4, 4}, {8, 4, 8, 2}, {8, 2, 8, 4}, {4, 4, 4, 8}, {8, 8, 2, 2}};
+constexpr StagedShape STAGED_SHAPES_8[] = {{8, 2, 4, 4}, {8, 2, 8, 2}, {8, 4, 2, 4}, {4, 2, 4, 8}, {8, 4, 4, 2}};
+constexpr int DEFAULT_STAGED_SHAPE_4 = 2, DEFAULT_STAGED_SHAPE_8 = 3;   // gpurun sweep, profiles/r1_probe.md
+constexpr int SIMPLE_ITEMS_4 = 4, SIMPLE_ITEMS_8 = 4;   // rows per thread per round, warp-centric kernel
 constexpr uint64_t HOST_CHUNK_BYTES = 64ull << 20;   // per column per pipeline stage in dwj_join_host
 
 }  // namespace
@@ -76,6 +82,7 @@ struct dwj_engine {
   unsigned long long *counter = nullptr;       // device uint64 used when the caller passes no d_n_matches
   unsigned long long *part_scratch = nullptr;  // hist[256] + cursor[256]
   uint32_t launches_build = 0, launches_probe = 0;
+  int staged_shape = -1;   // -1: per-key-width default
   // dwj_join_host staging
   void *stage = nullptr;
   uint64_t stage_bytes = 0;
@@ -137,30 +144,95 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
   return DWJ_OK;
 }
 
+// ALIGNED / CONTAINS / COUNT: warp-centric kernel, no barriers, grid sized to fill the machine.
 template <int W, int MODE, bool UNIQUE>
-int probe_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
-  constexpr int ITEMS = W == 4 ? PROBE_ITEMS_4 : PROBE_ITEMS_8;
-  constexpr uint64_t TILE = (uint64_t)PROBE_THREADS * ITEMS;
-  const uint64_t tiles = (a.n + TILE - 1) / TILE;
-  a.num_tiles = tiles;
+int simple_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
+  constexpr int ITEMS = W == 4 ? SIMPLE_ITEMS_4 : SIMPLE_ITEMS_8;
+  const uint64_t tiles = (a.n + 32ull * ITEMS - 1) / (32ull * ITEMS);
   e->launches_probe = 0;
-  if (MODE == dwj::PROBE_PAIRS) {
-    int rc = ensure_tile_state(e, tiles, s);
-    if (rc) return rc;
-    a.tile_state = e->tile_state;
-    CU(cudaMemsetAsync(e->tile_state, 0, (tiles + 1) * sizeof(unsigned long long), s));
-    e->launches_probe++;
-  }
-  if (MODE == dwj::PROBE_PAIRS || MODE == dwj::PROBE_COUNT) {
+  if (MODE == dwj::PROBE_COUNT) {
     CU(cudaMemsetAsync(a.n_matches, 0, sizeof(unsigned long long), s));
     e->launches_probe++;
   }
   if (tiles) {
-    if (tiles > 0x7fffffffull) return fail(DWJ_ERR_INVALID, "probe of %llu rows needs more than 2^31 tiles", (unsigned long long)a.n);
-    CU(launch(e, dwj::probe_kernel<W, MODE, UNIQUE, PROBE_THREADS, ITEMS>, dim3((unsigned)tiles), dim3(PROBE_THREADS), s, a, true));
+    const uint64_t ctas = (tiles + 7) / 8;
+    const unsigned grid = (unsigned)std::min<uint64_t>(ctas, (uint64_t)e->prop.multiProcessorCount * 16);
+    CU(launch(e, dwj::probe_simple_kernel<W, MODE, UNIQUE, ITEMS>, dim3(grid), dim3(256), s, a, true));
     e->launches_probe++;
   }
   return DWJ_OK;
+}
+
+// PAIRS with non-unique build keys: one look-back descriptor per CTA tile, rows written from registers.
+template <int W>
+int multi_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
+  constexpr int THREADS = 256, ITEMS = 4, MINB = 4;
+  constexpr uint64_t TILE = (uint64_t)THREADS * ITEMS;
+  const uint64_t tiles = (a.n + TILE - 1) / TILE;
+  a.num_tiles = tiles;
+  int rc = ensure_tile_state(e, tiles, s);
+  if (rc) return rc;
+  a.tile_state = e->tile_state;
+  CU(cudaMemsetAsync(e->tile_state, 0, (tiles + 1) * sizeof(unsigned long long), s));
+  CU(cudaMemsetAsync(a.n_matches, 0, sizeof(unsigned long long), s));
+  e->launches_probe = 2;
+  if (tiles) {
+    if (tiles > 0x7fffffffull) return fail(DWJ_ERR_INVALID, "probe of %llu rows needs more than 2^31 tiles", (unsigned long long)a.n);
+    CU(launch(e, dwj::probe_pairs_multi_kernel<W, THREADS, ITEMS, MINB>, dim3((unsigned)tiles), dim3(THREADS), s, a, true));
+    e->launches_probe++;
+  }
+  return DWJ_OK;
+}
+
+template <int W, bool ORDERED, bool WITH_KEY, int SHAPE>
+int staged_launch_shape(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
+  constexpr StagedShape S = W == 4 ? STAGED_SHAPES_4[SHAPE] : STAGED_SHAPES_8[SHAPE];
+  constexpr uint64_t CHUNK = (uint64_t)S.warps * 32 * S.items * S.sub;
+  const uint64_t chunks = (a.n + CHUNK - 1) / CHUNK;
+  a.num_tiles = chunks;
+  e->launches_probe = 0;
+  if (ORDERED) {
+    int rc = ensure_tile_state(e, chunks, s);
+    if (rc) return rc;
+    a.tile_state = e->tile_state;
+    CU(cudaMemsetAsync(e->tile_state, 0, (chunks + 1) * sizeof(unsigned long long), s));
+    e->launches_probe++;
+  }
+  CU(cudaMemsetAsync(a.n_matches, 0, sizeof(unsigned long long), s));
+  e->launches_probe++;
+  if (chunks) {
+    if (chunks > 0x7fffffffull) return fail(DWJ_ERR_INVALID, "probe of %llu rows needs more than 2^31 chunks", (unsigned long long)a.n);
+    auto kern = dwj::probe_pairs_staged_kernel<W, ORDERED, WITH_KEY, S.warps, S.items, S.sub, S.minb>;
+    const size_t smem = CHUNK * W * (WITH_KEY ? 3 : 2);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3((unsigned)chunks);
+    lc.blockDim = dim3(S.warps * 32);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (e->l2_window) {
+      attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+      attr[0].val.accessPolicyWindow = e->window;
+      lc.attrs = attr;
+      lc.numAttrs = 1;
+    }
+    CU(cudaLaunchKernelEx(&lc, kern, a));
+    e->launches_probe++;
+  }
+  return DWJ_OK;
+}
+
+template <int W, bool ORDERED, bool WITH_KEY>
+int staged_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
+  const int shape = e->staged_shape >= 0 ? e->staged_shape : (W == 4 ? DEFAULT_STAGED_SHAPE_4 : DEFAULT_STAGED_SHAPE_8);
+  switch (shape) {
+  case 1: return staged_launch_shape<W, ORDERED, WITH_KEY, 1>(e, a, s);
+  case 2: return staged_launch_shape<W, ORDERED, WITH_KEY, 2>(e, a, s);
+  case 3: return staged_launch_shape<W, ORDERED, WITH_KEY, 3>(e, a, s);
+  case 4: return staged_launch_shape<W, ORDERED, WITH_KEY, 4>(e, a, s);
+  default: return staged_launch_shape<W, ORDERED, WITH_KEY, 0>(e, a, s);
+  }
 }
 
 template <int W>
@@ -185,13 +257,19 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
   CU(cudaEventRecord(e->ev_probe[0], s));
   int rc;
   switch (mode) {
-  case dwj::PROBE_ALIGNED: rc = probe_launch<W, dwj::PROBE_ALIGNED, true>(e, a, s); break;
-  case dwj::PROBE_CONTAINS: rc = probe_launch<W, dwj::PROBE_CONTAINS, true>(e, a, s); break;
+  case dwj::PROBE_ALIGNED: rc = simple_launch<W, dwj::PROBE_ALIGNED, true>(e, a, s); break;
+  case dwj::PROBE_CONTAINS: rc = simple_launch<W, dwj::PROBE_CONTAINS, true>(e, a, s); break;
   case dwj::PROBE_COUNT:
-    rc = unique ? probe_launch<W, dwj::PROBE_COUNT, true>(e, a, s) : probe_launch<W, dwj::PROBE_COUNT, false>(e, a, s);
+    rc = unique ? simple_launch<W, dwj::PROBE_COUNT, true>(e, a, s) : simple_launch<W, dwj::PROBE_COUNT, false>(e, a, s);
     break;
   default:
-    rc = unique ? probe_launch<W, dwj::PROBE_PAIRS, true>(e, a, s) : probe_launch<W, dwj::PROBE_PAIRS, false>(e, a, s);
+    if (unique) {      // one look-back (or one atomic) per chunk, rows staged in shared memory
+      const bool ordered = !(e->cfg.flags & DWJ_FLAG_UNORDERED_OUTPUT);
+      if (ordered) rc = ok ? staged_launch<W, true, true>(e, a, s) : staged_launch<W, true, false>(e, a, s);
+      else rc = ok ? staged_launch<W, false, true>(e, a, s) : staged_launch<W, false, false>(e, a, s);
+    } else {
+      rc = multi_launch<W>(e, a, s);
+    }
   }
   if (rc) return rc;
   CU(cudaEventRecord(e->ev_probe[1], s));
@@ -267,6 +345,7 @@ int dwj_create(const dwj_config *cfg, dwj_engine **out) {
   e->cfg = *cfg;
   e->cfg.load_factor = lf;
   e->W = cfg->key_bytes;
+  if (const char *ps = getenv("DWJ_STAGED_SHAPE")) e->staged_shape = atoi(ps);
   DeviceGuard g(cfg->device);
   auto bail = [&](int rc) { dwj_destroy(e); return rc; };
   if (cudaGetDeviceProperties(&e->prop, cfg->device) != cudaSuccess) return bail(fail(DWJ_ERR_CUDA, "cudaGetDeviceProperties failed"));

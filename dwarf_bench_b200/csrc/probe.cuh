@@ -82,18 +82,36 @@ DWJ_D unsigned long long lookback_exclusive_prefix(unsigned long long *desc, uin
 }
 
 // ---- chain walk ---------------------------------------------------------------------------------
-// First hit (SimpleNonOwningHashTable::at): returns true and the payload.  `bk` is the home
-// bucket, already loaded by the caller so that ITEMS loads are in flight together.
+// The home bucket is tested branch-free (4 compares + selects: straight-line code the compiler keeps in
+// registers); only a FULL home bucket without a hit continues into the next sector, in a cold loop.
 template <int W, class K>
-DWJ_D bool find_first(const void *table, uint64_t mask, uint64_t b, Bucket<W> bk, K key, K &payload) {
+DWJ_D bool find_first_overflow(const void *table, uint64_t mask, uint64_t b, K key, K &payload) {
   for (;;) {
-#pragma unroll
-    for (int i = 0; i < Bucket<W>::SLOTS; ++i)
-      if (bk.match(i, key)) { payload = bk.payload(i); return true; }
-    if (bk.any_empty()) return false;      // chains never skip a bucket with a free slot
     b = (b + 1) & mask;
-    bk = load_bucket_ro<W>(table, b);
+    const Bucket<W> bk = load_bucket_ro<W>(table, b);
+    bool hit = false;
+#pragma unroll
+    for (int i = Bucket<W>::SLOTS - 1; i >= 0; --i) {
+      const bool m = bk.match(i, key);
+      payload = m ? bk.payload(i) : payload;
+      hit |= m;
+    }
+    if (hit || bk.any_empty()) return hit;      // chains never skip a bucket with a free slot
   }
+}
+
+// First hit (SimpleNonOwningHashTable::at): returns true and the payload of the lowest matching slot.
+template <int W, class K>
+DWJ_D bool find_first(const void *table, uint64_t mask, uint64_t b, const Bucket<W> &bk, K key, K &payload) {
+  bool hit = false;
+#pragma unroll
+  for (int i = Bucket<W>::SLOTS - 1; i >= 0; --i) {     // descending, so the lowest slot wins
+    const bool m = bk.match(i, key);
+    payload = m ? bk.payload(i) : payload;
+    hit |= m;
+  }
+  if (hit || bk.any_empty()) return hit;
+  return find_first_overflow<W, K>(table, mask, b, key, payload);
 }
 
 // All hits (seq_join semantics): calls emit(payload) for every equal build row, returns the count.
@@ -109,10 +127,86 @@ DWJ_D uint32_t for_each_match(const void *table, uint64_t mask, uint64_t b, Buck
     bk = load_bucket_ro<W>(table, b);
   }
 }
+template <int W, class K>
+DWJ_D uint32_t count_matches(const void *table, uint64_t mask, uint64_t b, Bucket<W> bk, K key, K &first_payload) {
+  uint32_t c = 0;
+  for (;;) {
+#pragma unroll
+    for (int i = 0; i < Bucket<W>::SLOTS; ++i) {
+      const bool m = bk.match(i, key);
+      if (m && c == 0) first_payload = bk.payload(i);
+      c += m ? 1u : 0u;
+    }
+    if (bk.any_empty()) return c;
+    b = (b + 1) & mask;
+    bk = load_bucket_ro<W>(table, b);
+  }
+}
 
-// ---- the probe kernel -------------------------------------------------------------------------------
-template <int W, int MODE, bool UNIQUE, int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS) probe_kernel(ProbeArgs<W> a) {
+// ---- warp-centric kernel: ALIGNED / CONTAINS / COUNT ---------------------------------------------------
+// No inter-warp communication is needed for these shapes, so there are no CTA barriers at all: a warp takes
+// tiles of 32*ITEMS consecutive rows (every column access is one contiguous 128 B / 256 B request) and the
+// grid strides over tiles in order.  COUNT accumulates in registers and issues one atomic per warp.
+template <int W, int MODE, bool UNIQUE, int ITEMS>
+__global__ void __launch_bounds__(256) probe_simple_kernel(ProbeArgs<W> a) {
+  using K = typename KeyT<W>::type;
+  constexpr K SENTINEL = ~(K)0;
+  constexpr uint64_t WTILE = 32ull * ITEMS;
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  const uint64_t tiles = (a.n + WTILE - 1) / WTILE;
+  unsigned long long local_count = 0;
+  for (uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < tiles; tile += warps_total) {
+    const uint64_t base = tile * WTILE;
+    const bool full = base + WTILE <= a.n;
+    K key[ITEMS], pval[ITEMS];
+    Bucket<W> bk[ITEMS];
+    uint64_t hb[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const uint64_t row = base + (uint64_t)j * 32 + lane;
+      const bool live = full || row < a.n;
+      key[j] = live ? load_stream(a.keys + row) : SENTINEL;
+      if constexpr (MODE == PROBE_ALIGNED) pval[j] = live ? load_stream(a.vals + row) : SENTINEL;
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      hb[j] = slot_hash(key[j], a.seed) & a.bucket_mask;
+      bk[j] = load_bucket_ro<W>(a.table, hb[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const uint64_t row = base + (uint64_t)j * 32 + lane;
+      K payload = SENTINEL;
+      if constexpr (MODE == PROBE_COUNT) {
+        if (key[j] != SENTINEL)
+          local_count += UNIQUE ? (find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload) ? 1u : 0u)
+                                : count_matches<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload);
+      } else {
+        const bool hit = key[j] != SENTINEL && find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload);
+        if (!(full || row < a.n)) continue;
+        if constexpr (MODE == PROBE_CONTAINS) {
+          store_stream(a.out_flags + row, hit ? 1u : 0u);
+        } else {                                    // join/join.cpp:97-101, sentinel elsewhere (:41-43)
+          store_stream(a.out_key + row, hit ? key[j] : SENTINEL);
+          store_stream(a.out_build_val + row, hit ? payload : SENTINEL);
+          store_stream(a.out_probe_val + row, hit ? pval[j] : SENTINEL);
+        }
+      }
+    }
+  }
+  if constexpr (MODE == PROBE_COUNT) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local_count += __shfl_xor_sync(0xffffffffu, local_count, o);
+    if (lane == 0 && local_count) atomicAdd(a.n_matches, local_count);
+  }
+}
+
+// ---- CTA-tile PAIRS kernel for NON-unique build keys (every equal build row is emitted) -----------------
+// One look-back descriptor per tile; rows are written straight from registers (a probe row may have any
+// number of matches, so they cannot be staged in a fixed amount of shared memory).
+template <int W, int THREADS, int ITEMS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeArgs<W> a) {
   using K = typename KeyT<W>::type;
   constexpr int TILE = THREADS * ITEMS;
   constexpr int WARPS = THREADS / 32;
@@ -120,112 +214,52 @@ __global__ void __launch_bounds__(THREADS) probe_kernel(ProbeArgs<W> a) {
   __shared__ unsigned long long s_tile;
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_warp_sums[ITEMS][WARPS];
-
   const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
-
-  // Tile id: scheduling order for PAIRS (look-back needs every predecessor to be running),
-  // plain block index otherwise.
-  uint64_t tile;
-  if constexpr (MODE == PROBE_PAIRS) {
-    if (t == 0) s_tile = atomicAdd(a.tile_state, 1ull);
-    __syncthreads();
-    tile = s_tile;
-  } else {
-    tile = blockIdx.x;
-  }
+  if (t == 0) s_tile = atomicAdd(a.tile_state, 1ull);     // scheduling order: look-back needs predecessors running
+  __syncthreads();
+  const uint64_t tile = s_tile;
   const uint64_t base = tile * TILE;
+  const bool full = base + TILE <= a.n;
 
-  K key[ITEMS];
+  K key[ITEMS], pval[ITEMS], first_payload[ITEMS];
   Bucket<W> bk[ITEMS];
   uint64_t hb[ITEMS];
-  bool live[ITEMS];
+  uint32_t cnt[ITEMS], off[ITEMS];
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const uint64_t row = base + (uint64_t)j * THREADS + t;
-    live[j] = row < a.n;
-    key[j] = live[j] ? load_stream(a.keys + row) : SENTINEL;
+    const bool live = full || row < a.n;
+    key[j] = live ? load_stream(a.keys + row) : SENTINEL;
+    pval[j] = live ? load_stream(a.vals + row) : SENTINEL;
   }
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     hb[j] = slot_hash(key[j], a.seed) & a.bucket_mask;
-    if (live[j]) bk[j] = load_bucket_ro<W>(a.table, hb[j]);
+    bk[j] = load_bucket_ro<W>(a.table, hb[j]);
   }
-
-  if constexpr (MODE == PROBE_ALIGNED || MODE == PROBE_CONTAINS) {
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      if (!live[j]) continue;
-      const uint64_t row = base + (uint64_t)j * THREADS + t;
-      K payload = SENTINEL;
-      const bool hit = find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload);
-      if constexpr (MODE == PROBE_CONTAINS) {
-        store_stream(a.out_flags + row, hit ? 1u : 0u);
-      } else {                                    // join/join.cpp:97-101, sentinel elsewhere (:41-43)
-        store_stream(a.out_key + row, hit ? key[j] : SENTINEL);
-        store_stream(a.out_build_val + row, payload);
-        store_stream(a.out_probe_val + row, hit ? load_stream(a.vals + row) : SENTINEL);
-      }
-    }
-  } else {
-  // ---- PAIRS / COUNT: per-item match counts ------------------------------------------------------
-  uint32_t cnt[ITEMS];
-  K first_payload[ITEMS];
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
-    cnt[j] = 0;
     first_payload[j] = SENTINEL;
-    if (!live[j]) continue;
-    if (UNIQUE) {
-      cnt[j] = find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], first_payload[j]) ? 1u : 0u;
-    } else {
-      cnt[j] = for_each_match<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j],
-                                    [&](K p) { if (first_payload[j] == SENTINEL) first_payload[j] = p; });
-    }
-  }
-
-  // Exclusive scan over the tile in row order (j major, t minor).
-  uint32_t off[ITEMS];
+    cnt[j] = key[j] != SENTINEL ? count_matches<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], first_payload[j]) : 0u;
+    uint32_t incl = cnt[j];
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    uint32_t incl;
-    if (UNIQUE) {
-      const unsigned m = __ballot_sync(0xffffffffu, cnt[j] != 0);
-      incl = __popc(m & (0xffffffffu >> (31 - lane)));
-    } else {
-      incl = cnt[j];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += n;
-      }
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
     }
     off[j] = incl - cnt[j];
     if (lane == 31) s_warp_sums[j][warp] = incl;
   }
   __syncthreads();
-  uint32_t running = 0, tile_total;
-  {
-    // Every thread folds the ITEMS*WARPS partial sums it needs (tiny: <= 64 values).
-    uint32_t acc = 0;
+  uint32_t tile_total = 0;
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
+  for (int j = 0; j < ITEMS; ++j) {
 #pragma unroll
-      for (int w = 0; w < WARPS; ++w) {
-        const uint32_t s = s_warp_sums[j][w];
-        if (w == (int)warp) off[j] += acc;       // sums of everything before (j, warp)
-        acc += s;
-      }
+    for (int w = 0; w < WARPS; ++w) {
+      if (w == (int)warp) off[j] += tile_total;      // everything before (j, warp) in row order
+      tile_total += s_warp_sums[j][w];
     }
-    tile_total = acc;
-    (void)running;
   }
-
-  if constexpr (MODE == PROBE_COUNT) {
-    if (t == 0 && tile_total) atomicAdd(a.n_matches, (unsigned long long)tile_total);
-    return;
-  }
-
-  // ---- look-back: where does this tile's output start? --------------------------------------------
   if (warp == 0) {
     const unsigned long long excl = lookback_exclusive_prefix(a.tile_state + 1, tile, tile_total);
     if (lane == 0) {
@@ -235,33 +269,129 @@ __global__ void __launch_bounds__(THREADS) probe_kernel(ProbeArgs<W> a) {
   }
   __syncthreads();
   const unsigned long long out_base = s_base;
-
-  // ---- compacted writes, probe-row order ---------------------------------------------------------------
+  const bool fits = out_base + tile_total <= a.capacity;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     if (cnt[j] == 0) continue;
-    const uint64_t row = base + (uint64_t)j * THREADS + t;
-    const K pv = load_stream(a.vals + row);
     unsigned long long o = out_base + off[j];
-    if (UNIQUE || cnt[j] == 1) {
-      if (o < a.capacity) {
+    if (cnt[j] == 1) {
+      if (fits || o < a.capacity) {
         if (a.out_key) store_stream(a.out_key + o, key[j]);
         store_stream(a.out_build_val + o, first_payload[j]);
-        store_stream(a.out_probe_val + o, pv);
+        store_stream(a.out_probe_val + o, pval[j]);
       }
-    } else {
-      // Re-walk the (now cache-warm) chain and emit every equal build row.
+    } else {                                          // re-walk the (cache-warm) chain, emit every equal build row
       for_each_match<W, K>(a.table, a.bucket_mask, hb[j], load_bucket_ro<W>(a.table, hb[j]), key[j], [&](K p) {
-        if (o < a.capacity) {
+        if (fits || o < a.capacity) {
           if (a.out_key) store_stream(a.out_key + o, key[j]);
           store_stream(a.out_build_val + o, p);
-          store_stream(a.out_probe_val + o, pv);
+          store_stream(a.out_probe_val + o, pval[j]);
         }
         ++o;
       });
     }
   }
-  }  // PAIRS / COUNT
+}
+
+// ---- staged PAIRS kernel (unique build keys) -------------------------------------------------------------
+// At B200 probe rates (> 100 rows/ns) one look-back descriptor per 1-2 K rows means > 100 descriptors per
+// microsecond -- more than one 32-wide look-back window per L2 round trip, so the look-back distance grows until
+// it throttles the kernel (profiles/r1_probe.md: the first PAIRS kernel ran 2.5x slower than ALIGNED, which does
+// the same loads and stores without a scan).  Here a CTA owns a CHUNK of WARPS*SUB*ITEMS*32 consecutive rows and
+// publishes ONE descriptor for it.  Inside the chunk the warps are fully decoupled: warp w probes its own
+// contiguous slice in SUB rounds of ITEMS*32 rows and compacts its hits into its own slice of shared memory
+// (ballot + popc, no barrier).  Two barriers per chunk frame the look-back; then every warp streams its staged
+// rows out with contiguous 128 B stores.  At most one match per probe row (UNIQUE), so the staging never
+// overflows.
+//   ORDERED = true : chunk base from the decoupled look-back -> output in probe-row order (reference order)
+//   ORDERED = false: chunk base from one atomicAdd on the match counter -> same multiset, chunk order arbitrary
+template <int W, bool ORDERED, bool WITH_KEY, int WARPS, int ITEMS, int SUB, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) probe_pairs_staged_kernel(ProbeArgs<W> a) {
+  using K = typename KeyT<W>::type;
+  constexpr int WROWS = 32 * ITEMS * SUB;           // rows per warp
+  constexpr int CHUNK = WARPS * WROWS;
+  constexpr K SENTINEL = ~(K)0;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  K *s_build = reinterpret_cast<K *>(s_raw);
+  K *s_probe = s_build + CHUNK;
+  K *s_key = s_probe + CHUNK;                       // only touched when WITH_KEY
+  __shared__ unsigned long long s_chunk;
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_wtot[WARPS];
+
+  const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) s_chunk = ORDERED ? atomicAdd(a.tile_state, 1ull) : (unsigned long long)blockIdx.x;
+  __syncthreads();
+  const uint64_t chunk = s_chunk;
+  const uint64_t warp_base = chunk * CHUNK + (uint64_t)warp * WROWS;
+  const bool full = warp_base + WROWS <= a.n;       // warp-uniform
+  K *wb = s_build + warp * WROWS, *wp = s_probe + warp * WROWS, *wk = s_key + warp * WROWS;
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t staged = 0;                              // warp-uniform running count
+
+#pragma unroll 1
+  for (int sub = 0; sub < SUB; ++sub) {
+    const uint64_t base = warp_base + (uint64_t)sub * (32 * ITEMS);
+    if (!full && base >= a.n) break;                // warp-uniform
+    K key[ITEMS], pval[ITEMS];
+    Bucket<W> bk[ITEMS];
+    uint64_t hb[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const uint64_t row = base + (uint64_t)j * 32 + lane;
+      const bool live = full || row < a.n;
+      key[j] = live ? load_stream(a.keys + row) : SENTINEL;
+      pval[j] = live ? load_stream(a.vals + row) : SENTINEL;
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      hb[j] = slot_hash(key[j], a.seed) & a.bucket_mask;
+      bk[j] = load_bucket_ro<W>(a.table, hb[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      K payload = SENTINEL;
+      const bool hit = key[j] != SENTINEL && find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const uint32_t o = staged + __popc(m & lt);
+        wb[o] = payload;
+        wp[o] = pval[j];
+        if constexpr (WITH_KEY) wk[o] = key[j];
+      }
+      staged += __popc(m);
+    }
+  }
+  if (lane == 0) s_wtot[warp] = staged;
+  __syncthreads();
+
+  // One descriptor (or one atomic) per chunk.
+  if (warp == 0) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) total += s_wtot[w];
+    unsigned long long excl = 0;
+    if constexpr (ORDERED) {
+      excl = lookback_exclusive_prefix(a.tile_state + 1, chunk, total);
+      if (lane == 0 && chunk == a.num_tiles - 1) *a.n_matches = excl + total;
+    } else {
+      if (lane == 0 && total) excl = atomicAdd(a.n_matches, (unsigned long long)total);
+    }
+    if (lane == 0) s_base = excl;
+  }
+  __syncthreads();
+  unsigned long long out_base = s_base;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) out_base += w < (int)warp ? s_wtot[w] : 0u;
+  const bool fits = out_base + staged <= a.capacity;
+  for (uint32_t i = lane; i < staged; i += 32) {
+    const unsigned long long o = out_base + i;
+    if (fits || o < a.capacity) {
+      store_stream(a.out_build_val + o, wb[i]);
+      store_stream(a.out_probe_val + o, wp[i]);
+      if constexpr (WITH_KEY) store_stream(a.out_key + o, wk[i]);
+    }
+  }
 }
 
 }  // namespace dwj

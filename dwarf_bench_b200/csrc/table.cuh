@@ -67,54 +67,81 @@ DWJ_HD uint32_t partition_of(uint64_t key, uint32_t log2_parts, uint64_t seed) {
 #if defined(__CUDACC__)
 
 // ---- bucket access -----------------------------------------------------------------------
+// A bucket in registers: `K f[..]` alternating key, payload (k0 v0 k1 v1 ...), exactly the 32 bytes of
+// the sector.  A slot is empty when its KEY field is all-ones; the all-ones key is therefore reserved
+// (it is the reference's `empty_element`, join/join.cpp:10, which the reference cannot join either:
+// its compaction loop drops such rows, join.cpp:123-129).  Rows carrying it are ignored by the build
+// and never match in a probe.
 template <int W> struct Bucket;
 
 template <> struct Bucket<4> {
   using key_t = uint32_t;
   static constexpr int SLOTS = 4;
-  unsigned long long s[4];  // key | payload << 32
-  static DWJ_D unsigned long long pack(uint32_t k, uint32_t v) {
-    return (unsigned long long)k | ((unsigned long long)v << 32);
-  }
-  DWJ_D bool empty(int i) const { return s[i] == ~0ull; }
-  DWJ_D bool match(int i, uint32_t k) const { return (uint32_t)s[i] == k && s[i] != ~0ull; }
-  DWJ_D uint32_t payload(int i) const { return (uint32_t)(s[i] >> 32); }
-  DWJ_D bool any_empty() const { return s[3] == ~0ull || s[2] == ~0ull || s[1] == ~0ull || s[0] == ~0ull; }
+  uint32_t f[8];
+  DWJ_D bool empty(int i) const { return f[2 * i] == 0xFFFFFFFFu; }
+  DWJ_D bool match(int i, uint32_t k) const { return f[2 * i] == k; }
+  DWJ_D uint32_t payload(int i) const { return f[2 * i + 1]; }
+  // Slots fill in order and are never freed, so the occupied slots of a bucket form a prefix.
+  DWJ_D bool any_empty() const { return f[6] == 0xFFFFFFFFu; }
 };
 
 template <> struct Bucket<8> {
   using key_t = uint64_t;
   static constexpr int SLOTS = 2;
-  unsigned long long s[4];  // k0, v0, k1, v1
-  DWJ_D bool empty(int i) const { return s[2 * i] == ~0ull; }
-  DWJ_D bool match(int i, uint64_t k) const { return s[2 * i] == k && k != ~0ull; }
-  DWJ_D uint64_t payload(int i) const { return s[2 * i + 1]; }
-  DWJ_D bool any_empty() const { return s[2] == ~0ull || s[0] == ~0ull; }
+  unsigned long long f[4];
+  DWJ_D bool empty(int i) const { return f[2 * i] == ~0ull; }
+  DWJ_D bool match(int i, uint64_t k) const { return f[2 * i] == k; }
+  DWJ_D uint64_t payload(int i) const { return f[2 * i + 1]; }
+  DWJ_D bool any_empty() const { return f[2] == ~0ull; }
 };
 
-// One 32-byte sector in one instruction (LDG.E.256, sm_100+).  Read-only path for the probe
-// (the table is immutable while a probe kernel runs); L1 is bypassed -- a random sector is
-// never re-used by the same SM -- and the line is marked evict_last in L2 so that the
-// streaming probe columns do not push the table out.
-template <int W> DWJ_D Bucket<W> load_bucket_ro(const void *table, uint64_t b) {
-  Bucket<W> r;
+// One 32-byte sector in ONE instruction (LDG.E.256, sm_100+): measured on B200, a random-sector gather
+// costs one L1TEX wavefront per instruction, so two 128-bit loads would halve the probe rate
+// (tools/gather_bench.cu: 285 vs 143 G gathers/s on an L2-resident table).  Read-only path for the probe
+// (the table is immutable while a probe kernel runs); L1 is bypassed -- a random sector is never re-used
+// by the same SM.
+DWJ_D Bucket<4> load_bucket_ro(const void *table, uint64_t b, Bucket<4> *) {
+  Bucket<4> r;
   const char *p = (const char *)table + (b << 5);
-  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];"
-               : "=l"(r.s[0]), "=l"(r.s[1]), "=l"(r.s[2]), "=l"(r.s[3])
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.f[0]), "=r"(r.f[1]), "=r"(r.f[2]), "=r"(r.f[3]), "=r"(r.f[4]), "=r"(r.f[5]), "=r"(r.f[6]), "=r"(r.f[7])
                : "l"(p));
   return r;
 }
-// Coherent variant for the build kernel (other CTAs are inserting concurrently): L2 is the
-// point of coherence, so skip L1 (.cg).  A stale view can only show a slot as still empty, and
-// the CAS that follows corrects that.
-template <int W> DWJ_D Bucket<W> load_bucket_cg(const void *table, uint64_t b) {
-  Bucket<W> r;
+DWJ_D Bucket<8> load_bucket_ro(const void *table, uint64_t b, Bucket<8> *) {
+  Bucket<8> r;
   const char *p = (const char *)table + (b << 5);
-  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
-               : "=l"(r.s[0]), "=l"(r.s[1]), "=l"(r.s[2]), "=l"(r.s[3])
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(r.f[0]), "=l"(r.f[1]), "=l"(r.f[2]), "=l"(r.f[3])
+               : "l"(p));
+  return r;
+}
+template <int W> DWJ_D Bucket<W> load_bucket_ro(const void *table, uint64_t b) {
+  return load_bucket_ro(table, b, (Bucket<W> *)nullptr);
+}
+// Coherent variant for the build kernel (other CTAs are inserting concurrently): L2 is the point of
+// coherence, so skip L1 (.cg).  A stale view can only show a slot as still empty, and the CAS that
+// follows corrects that.
+DWJ_D Bucket<4> load_bucket_cg(const void *table, uint64_t b, Bucket<4> *) {
+  Bucket<4> r;
+  const char *p = (const char *)table + (b << 5);
+  asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.f[0]), "=r"(r.f[1]), "=r"(r.f[2]), "=r"(r.f[3]), "=r"(r.f[4]), "=r"(r.f[5]), "=r"(r.f[6]), "=r"(r.f[7])
                : "l"(p)
                : "memory");
   return r;
+}
+DWJ_D Bucket<8> load_bucket_cg(const void *table, uint64_t b, Bucket<8> *) {
+  Bucket<8> r;
+  const char *p = (const char *)table + (b << 5);
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(r.f[0]), "=l"(r.f[1]), "=l"(r.f[2]), "=l"(r.f[3])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+template <int W> DWJ_D Bucket<W> load_bucket_cg(const void *table, uint64_t b) {
+  return load_bucket_cg(table, b, (Bucket<W> *)nullptr);
 }
 
 // ---- streaming column access ---------------------------------------------------------------

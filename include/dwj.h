@@ -64,6 +64,10 @@ extern "C" {
                                            (seq_join semantics).                           */
 #define DWJ_FLAG_L2_PERSIST 0x2u        /* pin the table in L2 with an access-policy window
                                            when it fits the device's persisting-L2 limit    */
+#define DWJ_FLAG_UNORDERED_OUTPUT 0x4u  /* dwj_probe_pairs may emit rows in any order (same
+                                           multiset): output ranges are handed out with one
+                                           atomicAdd per chunk instead of the order-preserving
+                                           decoupled look-back scan                           */
 
 typedef struct dwj_engine dwj_engine; /* opaque; owns the table and all scratch device memory */
 

@@ -217,6 +217,26 @@ def test_empty_and_ragged_inputs(dwj):
     assert sorted(zip(k.tolist(), a.tolist())) == sorted(zip(ak.tolist(), (ak + 1).tolist()))
 
 
+def test_unordered_output_same_multiset(dwj, oracle):
+    """DWJ_FLAG_UNORDERED_OUTPUT trades the probe-order guarantee for one atomic per chunk: same rows, any order."""
+    n = 300_001
+    ak, av, bk, bv = (oracle.make_unique_random(n, s) for s in (21, 22, 23, 24))
+    want = oracle.sort_join(ak, av, bk, bv)
+    for wide in (False, True):
+        dt = np.uint64 if wide else np.uint32
+        cols = [c.astype(dt) for c in (ak, av, bk, bv)]
+        with dwj.Engine(n, key_bytes=dt().itemsize, flags=dwj.FLAG_UNIQUE_BUILD_KEYS | dwj.FLAG_UNORDERED_OUTPUT) as e:
+            dak, dav, dbk, dbv = (dev(c) for c in cols)
+            e.build(dak, dav, n)
+            ok, oa, ob = (empty_like_dev(n, dt) for _ in range(3))
+            m = e.probe_pairs(dbk, dbv, n, ok, oa, ob, n)
+            torch.cuda.synchronize()
+            got = pyoracle.canonical_rows(*(host(t, dt)[:m] for t in (ok, oa, ob)))
+            assert m == len(want[0])
+            for w, x in zip(want, got):
+                np.testing.assert_array_equal(w.astype(dt), x)
+
+
 def test_key_column_optional(dwj, oracle):
     ak, av, bk, bv = (oracle.make_unique_random(5000, s) for s in (5, 6, 7, 8))
     k, a, b = gpu_join_pairs(dwj, ak, av, bk, bv, unique=True)
