@@ -1,0 +1,3 @@
+// Forwarder: the reference keeps this part of the framework in common/result.hpp; here it lives in one file.
+#pragma once
+#include "dwarf_framework.hpp"

@@ -1,0 +1,2 @@
+#pragma once
+#include "join/b200_dwarfs.hpp"
