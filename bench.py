@@ -51,7 +51,9 @@ def parse_args():
     ap.add_argument("--build-rows", type=int, default=0, help="override (development only; the line says so)")
     ap.add_argument("--probe-rows", type=int, default=0)
     ap.add_argument("--load-factor", type=float, default=0.5)
-    ap.add_argument("--no-l2-persist", action="store_true")
+    ap.add_argument("--l2-persist", action="store_true", help="access-policy window on the table (measured slower; off)")
+    ap.add_argument("--no-partition", action="store_true", help="probe the table directly (probe-row output order)")
+    ap.add_argument("--unordered", action="store_true", help="DWJ_FLAG_UNORDERED_OUTPUT")
     ap.add_argument("--emit-key", action="store_true", help="also materialise the key column (reference row shape)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -261,7 +263,8 @@ def main():
         inp = make_input(kind, n_build, n_probe, key_bytes, device, seed=7 + rank, key_base=rank * n_build,
                          key_space=world * n_build, keep_map=False)
     matches = inp.expected_matches
-    flags = (dwj.FLAG_UNIQUE_BUILD_KEYS if inp.unique_build else 0) | (0 if args.no_l2_persist else dwj.FLAG_L2_PERSIST)
+    flags = ((dwj.FLAG_UNIQUE_BUILD_KEYS if inp.unique_build else 0) | (dwj.FLAG_L2_PERSIST if args.l2_persist else 0)
+             | (dwj.FLAG_NO_PARTITION if args.no_partition else 0) | (dwj.FLAG_UNORDERED_OUTPUT if args.unordered else 0))
     cap_rows = n_build if world == 1 else int(n_build * 1.25) + 1024
     eng = dwj.Engine(cap_rows, key_bytes=key_bytes, device=local_rank, load_factor=args.load_factor, flags=flags)
     info = eng.info()
@@ -299,8 +302,13 @@ def main():
     if total != want_total:
         sys.exit(f"join produced {total} rows, expected {want_total}")
     if world == 1 and inp.probe_build_row is not None:
-        if not (torch.equal(out_b[:got], inp.build_vals[inp.probe_build_row]) and torch.equal(out_p[:got], inp.probe_vals)):
+        # Order-independent exact check (the engine may emit rows region by region): the probe payload is the probe
+        # row id, so every output row names the probe row it came from.
+        rows = out_p[:got].long()
+        if not (torch.equal(out_b[:got], inp.build_vals[inp.probe_build_row[rows]])
+                and torch.equal(torch.sort(out_p[:got]).values, inp.probe_vals)):
             sys.exit("join output differs from the expected (build payload, probe payload) rows")
+        del rows
     info = eng.info()
     launches_per_step = info["launches_build"] + info["launches_probe"] + (0 if world == 1 else 2 * 4)   # + 2 x dwj_partition
 
@@ -347,7 +355,8 @@ def main():
                    "key_bytes": key_bytes, "payload_bytes": key_bytes, "unique_build_keys": inp.unique_build,
                    "output": "compacted (build payload, probe payload" + (", key)" if args.emit_key else ")"),
                    "table_slots": info["slots"], "table_bytes": info["table_bytes"], "load_factor": args.load_factor,
-                   "l2_persist_window": bool(info["l2_persist"]),
+                   "l2_persist_window": bool(info["l2_persist"]), "table_regions": info["radix_parts"],
+                   "output_order": "probe-row order" if info["radix_parts"] == 1 and not args.unordered else "region-major / unordered",
                    "l2_between_iterations": "inputs and outputs (%.1f GB per step) far exceed the 126 MB L2; no explicit flush"
                                             % (((n_build + n_probe) * 2 + matches * 2) * key_bytes / 1e9),
                    "parallelism": "single GPU" if world == 1 else f"hash-partitioned x{world}, NCCL all-to-all-v"},
@@ -361,6 +370,7 @@ def main():
         build_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
         probe_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
         peak, peak_src = measured_peak_hbm()
+        # whichever algorithm runs, report against the NON-partitioned sector-granular model of this table
         l2_res = info["table_bytes"] <= 100e6
         probe_bytes, step_bytes = algorithmic_bytes(n_build, n_probe, matches, key_bytes, info["slots"], args.emit_key, l2_res)
         achieved = probe_bytes / (probe_ms * 1e-3) / 1e9

@@ -7,7 +7,7 @@ ctypes binding used by tests and bench.py, plus the torch.distributed plumbing o
 There is no CPU fallback: importing works anywhere, creating an engine needs a B200.
 """
 from .capi import (DwjError, Engine, JoinTiming, lib_path, load_library,  # noqa: F401
-                   FLAG_L2_PERSIST, FLAG_UNIQUE_BUILD_KEYS, FLAG_UNORDERED_OUTPUT, OUT_ALIGNED, OUT_COUNT, OUT_PAIRS)
+                   FLAG_L2_PERSIST, FLAG_NO_PARTITION, FLAG_UNIQUE_BUILD_KEYS, FLAG_UNORDERED_OUTPUT, OUT_ALIGNED, OUT_COUNT, OUT_PAIRS)
 
 __all__ = ["DwjError", "Engine", "JoinTiming", "lib_path", "load_library", "FLAG_L2_PERSIST",
-           "FLAG_UNIQUE_BUILD_KEYS", "FLAG_UNORDERED_OUTPUT", "OUT_ALIGNED", "OUT_COUNT", "OUT_PAIRS"]
+           "FLAG_NO_PARTITION", "FLAG_UNIQUE_BUILD_KEYS", "FLAG_UNORDERED_OUTPUT", "OUT_ALIGNED", "OUT_COUNT", "OUT_PAIRS"]

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 FLAG_UNIQUE_BUILD_KEYS = 0x1
 FLAG_L2_PERSIST = 0x2
 FLAG_UNORDERED_OUTPUT = 0x4
+FLAG_NO_PARTITION = 0x8
 OUT_ALIGNED, OUT_PAIRS, OUT_COUNT = 0, 1, 2
 
 ERR_NAMES = {0: "DWJ_OK", -1: "DWJ_ERR_INVALID", -2: "DWJ_ERR_CUDA", -3: "DWJ_ERR_OOM", -4: "DWJ_ERR_OVERFLOW",
@@ -45,7 +46,8 @@ class Timing(C.Structure):
 class Info(C.Structure):
     _fields_ = [("slots", C.c_uint64), ("table_bytes", C.c_uint64), ("build_rows", C.c_uint64), ("slot_bytes", C.c_uint32),
                 ("slots_per_bucket", C.c_uint32), ("l2_persist", C.c_uint32), ("sm_count", C.c_uint32),
-                ("l2_bytes", C.c_uint64), ("launches_build", C.c_uint32), ("launches_probe", C.c_uint32)]
+                ("l2_bytes", C.c_uint64), ("launches_build", C.c_uint32), ("launches_probe", C.c_uint32),
+                ("radix_parts", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 @dataclass

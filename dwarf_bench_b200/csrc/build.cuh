@@ -50,21 +50,27 @@ DWJ_D void insert_row(void *table, uint64_t mask, uint64_t b, Bucket<W> bk, K k,
   }
 }
 
-// Grid-stride; ROWS independent rows per thread: all home-bucket sectors are requested first,
-// then the CAS phase runs, so ROWS random-sector latencies overlap per thread.
+// A CTA takes tiles of 256*ROWS CONSECUTIVE rows (tile = blockIdx, grid-stride over tiles), so the rows in
+// flight across the GPU form one contiguous window of the input: when the engine has pre-partitioned the input by
+// table region (dwj_api.cu) that window touches one L2-resident slice of the table.  ROWS independent rows per
+// thread: all home-bucket sectors are requested first, then the CAS phase runs, so ROWS random-sector latencies
+// overlap per thread.
 template <int W, int ROWS>
 __global__ void __launch_bounds__(256) build_kernel(BuildArgs<W> a) {
   using K = typename KeyT<W>::type;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + (ROWS - 1) * stride < a.n; i += ROWS * stride) {
+  constexpr uint64_t TILE = 256ull * ROWS;
+  const uint64_t tiles = (a.n + TILE - 1) / TILE;
+  for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const uint64_t base = tile * TILE + threadIdx.x;
     K k[ROWS], v[ROWS];
     uint64_t b[ROWS];
     Bucket<W> bk[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      k[r] = load_stream(a.keys + i + r * stride);
-      v[r] = load_stream(a.vals + i + r * stride);
+      const uint64_t i = base + (uint64_t)r * 256;
+      const bool live = i < a.n;
+      k[r] = live ? load_stream(a.keys + i) : ~(K)0;       // the reserved key is skipped by insert_row
+      v[r] = live ? load_stream(a.vals + i) : ~(K)0;
     }
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
@@ -73,11 +79,6 @@ __global__ void __launch_bounds__(256) build_kernel(BuildArgs<W> a) {
     }
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) insert_row<W, K>(a.table, a.bucket_mask, b[r], bk[r], k[r], v[r]);
-  }
-  for (; i < a.n; i += stride) {
-    K k = load_stream(a.keys + i), v = load_stream(a.vals + i);
-    uint64_t b = slot_hash(k, a.seed) & a.bucket_mask;
-    insert_row<W, K>(a.table, a.bucket_mask, b, load_bucket_cg<W>(a.table, b), k, v);
   }
 }
 

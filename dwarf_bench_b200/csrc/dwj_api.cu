@@ -80,7 +80,11 @@ struct dwj_engine {
   unsigned long long *tile_state = nullptr;
   uint64_t tile_state_cap = 0;                 // in descriptors
   unsigned long long *counter = nullptr;       // device uint64 used when the caller passes no d_n_matches
-  unsigned long long *part_scratch = nullptr;  // hist[256] + cursor[256]
+  unsigned long long *part_scratch = nullptr;  // hist[PART_MAX] + cursor[PART_MAX] + region offsets[PART_MAX + 1]
+  // L2-locality regions: inputs are radix-partitioned on the top `region_bits` bits of the bucket index first
+  uint32_t region_bits = 0;
+  void *region_build = nullptr, *region_probe = nullptr;   // partitioned copies (keys then payloads)
+  uint64_t region_build_rows = 0, region_probe_rows = 0;   // capacities in rows
   uint32_t launches_build = 0, launches_probe = 0;
   int staged_shape = -1;   // -1: per-key-width default
   // dwj_join_host staging
@@ -124,18 +128,94 @@ int ensure_tile_state(dwj_engine *e, uint64_t tiles, cudaStream_t s) {
   return DWJ_OK;
 }
 
+// by_bucket = false: partition id from the independent partition hash (multi-GPU exchange, dwj_partition)
+// by_bucket = true : partition id = top log2_parts bits of the bucket index (engine regions)
+template <int W>
+int partition_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, uint32_t log2_parts, bool by_bucket, void *ok,
+                   void *ov, uint64_t *d_offsets, cudaStream_t s) {
+  using K = typename dwj::KeyT<W>::type;
+  dwj::PartitionArgs<W> a{};
+  a.keys = (const K *)keys;
+  a.vals = (const K *)vals;
+  a.n = n;
+  a.log2_parts = log2_parts;
+  a.seed = e->cfg.hash_seed;
+  a.by_bucket = by_bucket ? 1u : 0u;
+  a.bucket_mask = e->buckets - 1;
+  uint32_t lgb = 0;
+  while ((1ull << lgb) < e->buckets) ++lgb;
+  a.bucket_shift = lgb >= log2_parts ? lgb - log2_parts : 0;
+  a.out_keys = (K *)ok;
+  a.out_vals = (K *)ov;
+  a.hist = e->part_scratch;
+  a.cursor = e->part_scratch + dwj::PART_MAX;
+  a.offsets = (unsigned long long *)d_offsets;
+  CU(cudaMemsetAsync(e->part_scratch, 0, 2 * dwj::PART_MAX * sizeof(unsigned long long), s));
+  const unsigned sms = (unsigned)e->prop.multiProcessorCount;
+  constexpr int HROWS = 8, ITEMS = 8;
+  const uint64_t htiles = (n + 256ull * HROWS - 1) / (256ull * HROWS);
+  const uint64_t tiles = (n + 256ull * ITEMS - 1) / (256ull * ITEMS);
+  constexpr int ITEMS8 = W == 4 ? 16 : 8;      // <= 8 partitions: bigger tiles, fewer global reservations
+  const uint64_t tiles8 = (n + 256ull * ITEMS8 - 1) / (256ull * ITEMS8);
+  const dim3 hgrid((unsigned)std::min<uint64_t>(htiles, sms * 8ull)), sgrid((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull));
+  const dim3 sgrid8((unsigned)std::min<uint64_t>(tiles8, 0x7fffffffull));
+  const bool small = log2_parts <= 3;     // <= 8 partitions: packed-register counters, no shared-memory atomics
+  if (n) {
+    if (small) {
+      if (by_bucket) CU(launch(e, dwj::partition_hist8_kernel<W, true, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
+      else CU(launch(e, dwj::partition_hist8_kernel<W, false, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
+    } else {
+      if (by_bucket) CU(launch(e, dwj::partition_hist_kernel<W, true, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
+      else CU(launch(e, dwj::partition_hist_kernel<W, false, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
+    }
+  }
+  CU(launch(e, dwj::partition_offsets_kernel<W>, dim3(1), dim3(32), s, a, false));
+  if (n) {
+    if (small) {
+      if (by_bucket) CU(launch(e, dwj::partition_scatter8_kernel<W, true, ITEMS8>, sgrid8, dim3(dwj::PART_THREADS), s, a, false));
+      else CU(launch(e, dwj::partition_scatter8_kernel<W, false, ITEMS8>, sgrid8, dim3(dwj::PART_THREADS), s, a, false));
+    } else {
+      if (by_bucket) CU(launch(e, dwj::partition_scatter_kernel<W, true, ITEMS>, sgrid, dim3(dwj::PART_THREADS), s, a, false));
+      else CU(launch(e, dwj::partition_scatter_kernel<W, false, ITEMS>, sgrid, dim3(dwj::PART_THREADS), s, a, false));
+    }
+  }
+  return DWJ_OK;
+}
+
+// Grow-only scratch for the region-partitioned copy of a relation: [keys | payloads], rows each.
+int ensure_region_buffer(void **buf, uint64_t *cap_rows, uint64_t rows, int W, cudaStream_t s) {
+  if (rows <= *cap_rows) return DWJ_OK;
+  if (*buf) {
+    CU(cudaStreamSynchronize(s));
+    CU(cudaFree(*buf));
+    *buf = nullptr;
+    *cap_rows = 0;
+  }
+  CU(cudaMalloc(buf, 2 * rows * (uint64_t)W));
+  *cap_rows = rows;
+  return DWJ_OK;
+}
+
 template <int W> int build_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, cudaStream_t s) {
   using K = typename dwj::KeyT<W>::type;
   CU(cudaEventRecord(e->ev_build[0], s));
+  e->launches_build = 0;
+  if (e->region_bits && n) {      // group the rows by table region first: the inserts then hit an L2-resident slice
+    if (int rc = ensure_region_buffer(&e->region_build, &e->region_build_rows, std::max<uint64_t>(n, e->cfg.max_build_rows), W, s)) return rc;
+    K *pk = (K *)e->region_build, *pv = pk + e->region_build_rows;
+    if (int rc = partition_impl<W>(e, keys, vals, n, e->region_bits, true, pk, pv, (uint64_t *)(e->part_scratch + 2 * dwj::PART_MAX), s)) return rc;
+    keys = pk;
+    vals = pv;
+    e->launches_build += 4;
+  }
   CU(cudaMemsetAsync(e->table, 0xFF, e->table_bytes, s));
-  e->launches_build = 1;
+  e->launches_build++;
   if (n) {
     dwj::BuildArgs<W> a{(const K *)keys, (const K *)vals, n, e->table, e->buckets - 1, e->cfg.hash_seed};
     constexpr int ROWS = 4;
-    const uint64_t want = (n + 256ull * ROWS - 1) / (256ull * ROWS);
-    const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)e->prop.multiProcessorCount * 32);
-    CU(launch(e, dwj::build_kernel<W, ROWS>, dim3(grid), dim3(256), s, a, true));
-    e->launches_build = 2;
+    const uint64_t tiles = (n + 256ull * ROWS - 1) / (256ull * ROWS);
+    CU(launch(e, dwj::build_kernel<W, ROWS>, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(256), s, a, true));
+    e->launches_build++;
   }
   CU(cudaEventRecord(e->ev_build[1], s));
   e->have_build = true;
@@ -256,6 +336,20 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
   const bool unique = (e->cfg.flags & DWJ_FLAG_UNIQUE_BUILD_KEYS) != 0;
   CU(cudaEventRecord(e->ev_probe[0], s));
   int rc;
+  uint32_t extra_launches = 0;
+  if (e->region_bits && n && (mode == dwj::PROBE_PAIRS || mode == dwj::PROBE_COUNT)) {
+    // Same grouping for the probe relation: its rows then walk the table slice by slice (output order becomes
+    // region-major; the row multiset is unchanged).
+    if ((rc = ensure_region_buffer(&e->region_probe, &e->region_probe_rows, n, W, s))) return rc;
+    K *pk = (K *)e->region_probe, *pv = pk + e->region_probe_rows;
+    const bool with_vals = mode == dwj::PROBE_PAIRS;
+    if ((rc = partition_impl<W>(e, keys, with_vals ? vals : nullptr, n, e->region_bits, true, pk, with_vals ? pv : nullptr,
+                                (uint64_t *)(e->part_scratch + 2 * dwj::PART_MAX), s)))
+      return rc;
+    a.keys = pk;
+    a.vals = pv;
+    extra_launches = 4;
+  }
   switch (mode) {
   case dwj::PROBE_ALIGNED: rc = simple_launch<W, dwj::PROBE_ALIGNED, true>(e, a, s); break;
   case dwj::PROBE_CONTAINS: rc = simple_launch<W, dwj::PROBE_CONTAINS, true>(e, a, s); break;
@@ -272,6 +366,7 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
     }
   }
   if (rc) return rc;
+  e->launches_probe += extra_launches;
   CU(cudaEventRecord(e->ev_probe[1], s));
   e->have_probe = true;
   if (h_n) {
@@ -282,39 +377,6 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
     if (mode == dwj::PROBE_PAIRS && total > capacity)
       return fail(DWJ_ERR_OVERFLOW, "join produced %llu rows, output capacity is %llu", total, (unsigned long long)capacity);
   }
-  return DWJ_OK;
-}
-
-template <int W>
-int partition_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, uint32_t log2_parts, void *ok, void *ov,
-                   uint64_t *d_offsets, cudaStream_t s) {
-  using K = typename dwj::KeyT<W>::type;
-  dwj::PartitionArgs<W> a{};
-  a.keys = (const K *)keys;
-  a.vals = (const K *)vals;
-  a.n = n;
-  a.log2_parts = log2_parts;
-  a.seed = e->cfg.hash_seed;
-  a.out_keys = (K *)ok;
-  a.out_vals = (K *)ov;
-  a.hist = e->part_scratch;
-  a.cursor = e->part_scratch + dwj::PART_MAX;
-  a.offsets = (unsigned long long *)d_offsets;
-  CU(cudaEventRecord(e->ev_part[0], s));
-  CU(cudaMemsetAsync(e->part_scratch, 0, 2 * dwj::PART_MAX * sizeof(unsigned long long), s));
-  const unsigned sms = (unsigned)e->prop.multiProcessorCount;
-  if (n) {
-    const uint64_t want = (n + 256ull * 8 - 1) / (256ull * 8);
-    CU(launch(e, dwj::partition_hist_kernel<W>, dim3((unsigned)std::min<uint64_t>(want, sms * 8ull)), dim3(dwj::PART_THREADS), s, a, false));
-  }
-  CU(launch(e, dwj::partition_offsets_kernel<W>, dim3(1), dim3(32), s, a, false));
-  if (n) {
-    constexpr int ITEMS = W == 4 ? 16 : 8;
-    const uint64_t tiles = (n + (uint64_t)dwj::PART_THREADS * ITEMS - 1) / ((uint64_t)dwj::PART_THREADS * ITEMS);
-    CU(launch(e, dwj::partition_scatter_kernel<W, ITEMS>, dim3((unsigned)std::min<uint64_t>(tiles, sms * 4ull)), dim3(dwj::PART_THREADS), s, a, false));
-  }
-  CU(cudaEventRecord(e->ev_part[1], s));
-  e->have_part = true;
   return DWJ_OK;
 }
 
@@ -358,12 +420,26 @@ int dwj_create(const dwj_config *cfg, dwj_engine **out) {
   e->table_bytes = e->buckets * 32ull;
   cudaError_t me = cudaMalloc(&e->table, e->table_bytes);
   if (me != cudaSuccess) return bail(fail(DWJ_ERR_OOM, "cudaMalloc of a %llu-byte table failed: %s", (unsigned long long)e->table_bytes, cudaGetErrorString(me)));
-  if (cudaMalloc(&e->counter, 64) != cudaSuccess || cudaMalloc(&e->part_scratch, 2 * dwj::PART_MAX * sizeof(unsigned long long)) != cudaSuccess)
+  if (cudaMalloc(&e->counter, 64) != cudaSuccess || cudaMalloc(&e->part_scratch, (3 * dwj::PART_MAX + 1) * sizeof(unsigned long long)) != cudaSuccess)
     return bail(fail(DWJ_ERR_OOM, "scratch allocation failed"));
   for (int i = 0; i < 2; ++i)
     if (cudaEventCreate(&e->ev_build[i]) != cudaSuccess || cudaEventCreate(&e->ev_probe[i]) != cudaSuccess ||
         cudaEventCreate(&e->ev_part[i]) != cudaSuccess)
       return bail(fail(DWJ_ERR_CUDA, "cudaEventCreate failed"));
+
+  {   // L2-locality regions (see partition.cuh).  DWJ_REGION_MB / DWJ_PARTITION_MIN_MB are tuning overrides.
+    double region_mb = 32.0, min_mb = 192.0;
+    if (const char *v = getenv("DWJ_REGION_MB")) region_mb = atof(v);
+    if (const char *v = getenv("DWJ_PARTITION_MIN_MB")) min_mb = atof(v);
+    if (!(cfg->flags & DWJ_FLAG_NO_PARTITION) && region_mb > 0 && (double)e->table_bytes >= min_mb * 1048576.0) {
+      uint32_t bits = 0, lgb = 0;
+      while ((double)(e->table_bytes >> bits) > region_mb * 1048576.0) ++bits;
+      while ((1ull << lgb) < e->buckets) ++lgb;
+      uint32_t max_bits = 0;
+      while ((1u << (max_bits + 1)) <= (uint32_t)dwj::PART_MAX) ++max_bits;
+      e->region_bits = std::min(std::min(bits, max_bits), lgb);
+    }
+  }
 
   if ((cfg->flags & DWJ_FLAG_L2_PERSIST) && e->prop.persistingL2CacheMaxSize > 0 && e->prop.accessPolicyMaxWindowSize > 0) {
     const size_t carve = std::min<size_t>((size_t)e->prop.persistingL2CacheMaxSize, (size_t)e->table_bytes);
@@ -391,6 +467,8 @@ int dwj_destroy(dwj_engine *e) {
   cudaFree(e->tile_state);
   cudaFree(e->counter);
   cudaFree(e->part_scratch);
+  cudaFree(e->region_build);
+  cudaFree(e->region_probe);
   cudaFree(e->stage);
   for (int i = 0; i < 2; ++i) {
     if (e->ev_build[i]) cudaEventDestroy(e->ev_build[i]);
@@ -417,6 +495,7 @@ int dwj_get_info(const dwj_engine *e, dwj_info *info) {
   info->l2_bytes = (uint64_t)e->prop.l2CacheSize;
   info->launches_build = e->launches_build;
   info->launches_probe = e->launches_probe;
+  info->radix_parts = 1u << e->region_bits;
   return DWJ_OK;
 }
 
@@ -499,8 +578,14 @@ int dwj_partition(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_
   uint32_t lg = 0;
   while ((1u << lg) < n_parts) ++lg;
   DeviceGuard g(e->cfg.device);
-  return e->W == 4 ? partition_impl<4>(e, d_keys, d_vals, n_rows, lg, d_out_keys, d_out_vals, d_offsets, (cudaStream_t)stream)
-                   : partition_impl<8>(e, d_keys, d_vals, n_rows, lg, d_out_keys, d_out_vals, d_offsets, (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaEventRecord(e->ev_part[0], s));
+  const int rc = e->W == 4 ? partition_impl<4>(e, d_keys, d_vals, n_rows, lg, false, d_out_keys, d_out_vals, d_offsets, s)
+                           : partition_impl<8>(e, d_keys, d_vals, n_rows, lg, false, d_out_keys, d_out_vals, d_offsets, s);
+  if (rc) return rc;
+  CU(cudaEventRecord(e->ev_part[1], s));
+  e->have_part = true;
+  return DWJ_OK;
 }
 
 uint32_t dwj_partition_of(uint64_t key, int32_t key_bytes, uint32_t n_parts, uint64_t hash_seed) {

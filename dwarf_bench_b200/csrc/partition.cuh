@@ -1,19 +1,25 @@
-// partition.cuh -- radix partition of (key, payload) columns on the key hash.
+// partition.cuh -- radix partition of (key, payload) columns on bits of the key hash.
 //
-// No reference counterpart (the reference is single-device).  Used for the multi-GPU
-// exchange: rows with equal keys land in the same partition, partitions are contiguous, and the
-// per-partition offsets drive an all-to-all-v.
+// No reference counterpart (the reference is single-device and never partitions).  Two users:
+//   * the multi-GPU exchange (dwj_partition): partition id = top bits of an INDEPENDENT hash, so rows with equal
+//     keys meet on one GPU and the local bucket index stays uniformly distributed;
+//   * the engine's own L2-locality pass (csrc/dwj_api.cu, "regions"): partition id = top bits of the BUCKET INDEX
+//     itself, so a partition's rows touch one contiguous slice of the table that fits in L2.  On B200 an L2 miss
+//     fills a 128-byte line (profiles/r1_gather_microbench.md), so a random probe of an HBM-resident table costs
+//     ~100 B of DRAM traffic per row; partitioning first costs 4 + 16 B per row of pure streaming instead.
 //
-// Three launches: histogram -> offsets (one block) -> scatter.  The scatter stages each tile in
-// shared memory grouped by partition and reserves one contiguous output range per (tile,
-// partition) with a single atomicAdd, so global writes are contiguous runs instead of a
-// row-by-row scatter.
+// Three launches: histogram -> offsets (one block) -> scatter.  Ranks are computed warp-cooperatively: the lanes
+// of a warp that go to the same partition are found with log2(parts) ballots, one lane adds their count to the
+// shared-memory counter and the others derive their rank from the ballot -- ~4x fewer shared-memory atomics than
+// one per row at 8 partitions.  The scatter stages each tile in shared memory grouped by partition and reserves
+// one contiguous output range per (tile, partition) with a single global atomicAdd, so global writes are
+// contiguous runs (2 KB on average at 8 partitions), not a row-by-row scatter.
 #pragma once
 #include "table.cuh"
 
 namespace dwj {
 
-constexpr int PART_MAX = 256;
+constexpr int PART_MAX = 512;
 constexpr int PART_THREADS = 256;
 
 template <int W> struct PartitionArgs {
@@ -23,6 +29,11 @@ template <int W> struct PartitionArgs {
   uint64_t n;
   uint32_t log2_parts;
   uint64_t seed;
+  // by_bucket: partition id = (slot_hash(key) & bucket_mask) >> bucket_shift   (engine regions)
+  // else     : partition id = partition_of(key, log2_parts, seed)              (multi-GPU exchange)
+  uint32_t by_bucket;
+  uint32_t bucket_shift;
+  uint64_t bucket_mask;
   K *out_keys;
   K *out_vals;         // may be null
   unsigned long long *hist;     // [PART_MAX] zeroed before the histogram kernel
@@ -30,15 +41,42 @@ template <int W> struct PartitionArgs {
   unsigned long long *offsets;  // [parts + 1] result
 };
 
-template <int W>
+template <int W, bool BY_BUCKET> DWJ_D uint32_t part_id(const PartitionArgs<W> &a, typename KeyT<W>::type key) {
+  if constexpr (BY_BUCKET) return (uint32_t)((slot_hash(key, a.seed) & a.bucket_mask) >> a.bucket_shift);
+  else return partition_of(key, a.log2_parts, a.seed);
+}
+
+constexpr uint32_t PART_DEAD = 0xFFFFFFFFu;   // partition id of a lane past the end of the input
+
+// Histogram: HROWS coalesced key loads in flight per thread; the lanes of a warp that share a partition are found
+// with one MATCH.ANY, and one of them adds the group's size to the shared-memory counter.
+template <int W, bool BY_BUCKET, int HROWS>
 __global__ void __launch_bounds__(PART_THREADS) partition_hist_kernel(PartitionArgs<W> a) {
+  using K = typename KeyT<W>::type;
   __shared__ unsigned int s_hist[PART_MAX];
   const uint32_t parts = 1u << a.log2_parts;
+  const unsigned lane = threadIdx.x & 31;
   for (uint32_t p = threadIdx.x; p < parts; p += blockDim.x) s_hist[p] = 0;
   __syncthreads();
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
-    atomicAdd(&s_hist[partition_of(load_stream(a.keys + i), a.log2_parts, a.seed)], 1u);
+  constexpr uint64_t TILE = (uint64_t)PART_THREADS * HROWS;
+  const uint64_t tiles = (a.n + TILE - 1) / TILE;
+  for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const uint64_t base = tile * TILE + threadIdx.x;
+    K k[HROWS];
+    bool live[HROWS];
+#pragma unroll
+    for (int j = 0; j < HROWS; ++j) {
+      const uint64_t i = base + (uint64_t)j * PART_THREADS;
+      live[j] = i < a.n;
+      k[j] = live[j] ? load_stream(a.keys + i) : (K)0;
+    }
+#pragma unroll
+    for (int j = 0; j < HROWS; ++j) {
+      const uint32_t p = live[j] ? part_id<W, BY_BUCKET>(a, k[j]) : PART_DEAD;
+      const unsigned peers = __match_any_sync(0xffffffffu, p);
+      if (live[j] && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&s_hist[p], (unsigned)__popc(peers));
+    }
+  }
   __syncthreads();
   for (uint32_t p = threadIdx.x; p < parts; p += blockDim.x)
     if (s_hist[p]) atomicAdd(a.hist + p, (unsigned long long)s_hist[p]);
@@ -57,17 +95,26 @@ template <int W> __global__ void partition_offsets_kernel(PartitionArgs<W> a) {
   }
 }
 
-template <int W, int ITEMS>
-__global__ void __launch_bounds__(PART_THREADS) partition_scatter_kernel(PartitionArgs<W> a) {
+// Scatter.  Per tile of 256*ITEMS rows: rank every row inside its partition (MATCH.ANY groups + one shared-memory
+// atomic per group), scan the per-partition counts, reserve one global range per partition, stage (key, payload,
+// partition id) in shared memory grouped by partition, then stream the tile out: consecutive threads write
+// consecutive addresses inside each partition's run.
+template <int W, bool BY_BUCKET, int ITEMS>
+__global__ void __launch_bounds__(PART_THREADS, 3) partition_scatter_kernel(PartitionArgs<W> a) {
   using K = typename KeyT<W>::type;
-  constexpr int TILE = PART_THREADS * ITEMS;
+  constexpr uint32_t TILE = PART_THREADS * ITEMS;
   __shared__ K s_keys[TILE];
   __shared__ K s_vals[TILE];
-  __shared__ unsigned int s_count[PART_MAX];       // rows of this tile per partition
-  __shared__ unsigned int s_start[PART_MAX + 1];   // exclusive scan of s_count (staging offsets)
-  __shared__ unsigned long long s_gbase[PART_MAX]; // reserved global start per partition
+  __shared__ unsigned short s_part[TILE];
+  __shared__ unsigned int s_count[PART_MAX];        // rows of this tile per partition
+  __shared__ unsigned int s_start[PART_MAX];        // exclusive scan of s_count (staging offsets)
+  __shared__ long long s_delta[PART_MAX];           // global start of the partition's run minus its staging offset
+  __shared__ unsigned int s_scan[PART_THREADS / 32];
 
   const uint32_t parts = 1u << a.log2_parts;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const bool with_vals = a.vals != nullptr;
   const uint64_t num_tiles = (a.n + TILE - 1) / TILE;
   for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const uint64_t base = tile * TILE;
@@ -77,43 +124,204 @@ __global__ void __launch_bounds__(PART_THREADS) partition_scatter_kernel(Partiti
 
     K k[ITEMS], v[ITEMS];
     uint32_t part[ITEMS], rank[ITEMS];
+    const K *kp = a.keys + base + threadIdx.x, *vp = a.vals + base + threadIdx.x;
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-      const uint32_t r = j * PART_THREADS + threadIdx.x;
-      if (r < rows) {
-        k[j] = load_stream(a.keys + base + r);
-        v[j] = a.vals ? load_stream(a.vals + base + r) : (K)0;
-        part[j] = partition_of(k[j], a.log2_parts, a.seed);
-        rank[j] = atomicAdd(&s_count[part[j]], 1u);
+      const bool live = j * PART_THREADS + threadIdx.x < rows;
+      k[j] = live ? load_stream(kp + j * PART_THREADS) : (K)0;
+      v[j] = live && with_vals ? load_stream(vp + j * PART_THREADS) : (K)0;
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const bool live = j * PART_THREADS + threadIdx.x < rows;
+      part[j] = live ? part_id<W, BY_BUCKET>(a, k[j]) : PART_DEAD;
+      const unsigned peers = __match_any_sync(0xffffffffu, part[j]);
+      const int leader = __ffs(peers) - 1;
+      unsigned wbase = 0;
+      if (live && (int)lane == leader) wbase = atomicAdd(&s_count[part[j]], (unsigned)__popc(peers));
+      rank[j] = __shfl_sync(0xffffffffu, wbase, leader) + __popc(peers & lt);
+    }
+    __syncthreads();
+    // Exclusive scan of s_count[0..parts) by the whole CTA (parts <= 512 = 2 per thread), global reservation.
+    {
+      unsigned local[PART_MAX / PART_THREADS], sum = 0;
+#pragma unroll
+      for (int q = 0; q < PART_MAX / PART_THREADS; ++q) {
+        const uint32_t p = threadIdx.x * (PART_MAX / PART_THREADS) + q;
+        local[q] = p < parts ? s_count[p] : 0u;
+        sum += local[q];
+      }
+      unsigned incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += n;
+      }
+      if (lane == 31) s_scan[warp] = incl;
+      __syncthreads();
+      unsigned before = 0;
+#pragma unroll
+      for (int w = 0; w < PART_THREADS / 32; ++w) before += w < (int)warp ? s_scan[w] : 0u;
+      unsigned run = before + incl - sum;
+#pragma unroll
+      for (int q = 0; q < PART_MAX / PART_THREADS; ++q) {
+        const uint32_t p = threadIdx.x * (PART_MAX / PART_THREADS) + q;
+        if (p < parts) {
+          s_start[p] = run;
+          const unsigned long long g = local[q] ? atomicAdd(a.cursor + p, (unsigned long long)local[q]) : 0ull;
+          s_delta[p] = (long long)g - (long long)run;
+        }
+        run += local[q];
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {                         // parts <= 256: a serial scan is negligible
-      unsigned int run = 0;
-      for (uint32_t p = 0; p < parts; ++p) { s_start[p] = run; run += s_count[p]; }
-      s_start[parts] = run;
-    }
-    for (uint32_t p = threadIdx.x; p < parts; p += PART_THREADS)
-      s_gbase[p] = s_count[p] ? atomicAdd(a.cursor + p, (unsigned long long)s_count[p]) : 0ull;
-    __syncthreads();
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-      const uint32_t r = j * PART_THREADS + threadIdx.x;
-      if (r < rows) {
+      if (part[j] != PART_DEAD) {
         const uint32_t s = s_start[part[j]] + rank[j];
         s_keys[s] = k[j];
         s_vals[s] = v[j];
+        s_part[s] = (unsigned short)part[j];
       }
     }
     __syncthreads();
     for (uint32_t s = threadIdx.x; s < rows; s += PART_THREADS) {
-      const K key = s_keys[s];
-      const uint32_t p = partition_of(key, a.log2_parts, a.seed);
-      const unsigned long long dst = s_gbase[p] + (s - s_start[p]);
-      store_stream(a.out_keys + dst, key);
-      if (a.out_vals) store_stream(a.out_vals + dst, s_vals[s]);
+      const long long dst = (long long)s + s_delta[s_part[s]];
+      store_stream(a.out_keys + dst, s_keys[s]);
+      if (with_vals) store_stream(a.out_vals + dst, s_vals[s]);
     }
     __syncthreads();
+  }
+}
+
+// ---- fast path: at most 8 partitions ---------------------------------------------------------------------
+// No shared-memory atomics and no MATCH: per-partition counters are PACKED into 64-bit registers.
+//   histogram: 8 fields x 8 bits per thread, flushed to shared memory before a field can overflow;
+//   scatter  : ballots + warp-distributed counters (see scatter8_tile); no atomics decide the order inside a
+//              tile, so the output is deterministic up to the order of the tiles' global reservations.
+// Interior tiles run a FULL = true instantiation of the tile body without any bounds predicate (the 64-bit
+// compares and the per-row branches they cause were most of the instruction stream in the first version).
+template <int W, bool BY_BUCKET, int HROWS, bool FULL>
+DWJ_D void hist8_tile(const PartitionArgs<W> &a, uint64_t tile_base, unsigned long long &acc) {
+  using K = typename KeyT<W>::type;
+  const K *kp = a.keys + tile_base + threadIdx.x;
+  const uint32_t rows = FULL ? 0u : (uint32_t)(a.n - tile_base);
+  K k[HROWS];
+#pragma unroll
+  for (int j = 0; j < HROWS; ++j) k[j] = (FULL || j * PART_THREADS + threadIdx.x < rows) ? load_stream(kp + j * PART_THREADS) : (K)0;
+#pragma unroll
+  for (int j = 0; j < HROWS; ++j) {
+    const unsigned long long one = 1ull << (8 * part_id<W, BY_BUCKET>(a, k[j]));
+    acc += (FULL || j * PART_THREADS + threadIdx.x < rows) ? one : 0ull;
+  }
+}
+
+template <int W, bool BY_BUCKET, int HROWS>
+__global__ void __launch_bounds__(PART_THREADS) partition_hist8_kernel(PartitionArgs<W> a) {
+  __shared__ unsigned int s_hist[8];
+  if (threadIdx.x < 8) s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  constexpr uint64_t TILE = (uint64_t)PART_THREADS * HROWS;
+  const uint64_t tiles = (a.n + TILE - 1) / TILE;
+  unsigned long long acc = 0;      // 8 x 8-bit counters
+  uint32_t pending = 0;
+  auto flush = [&]() {
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const unsigned c = (unsigned)(acc >> (8 * p)) & 0xFFu;
+      if (c) atomicAdd(&s_hist[p], c);
+    }
+    acc = 0;
+    pending = 0;
+  };
+  for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    if (tile * TILE + TILE <= a.n) hist8_tile<W, BY_BUCKET, HROWS, true>(a, tile * TILE, acc);
+    else hist8_tile<W, BY_BUCKET, HROWS, false>(a, tile * TILE, acc);
+    pending += HROWS;
+    if (pending > 255 - HROWS) flush();
+  }
+  flush();
+  __syncthreads();
+  if (threadIdx.x < 8 && s_hist[threadIdx.x]) atomicAdd(a.hist + threadIdx.x, (unsigned long long)s_hist[threadIdx.x]);
+}
+
+// Scatter for <= 8 partitions, straight from registers (no staging): a warp ranks its rows with three ballots per
+// 32 rows and warp-distributed counters (lane q keeps the warp's running count of partition q), the CTA combines
+// the per-warp totals once (one barrier pair), reserves one global range per partition, and every row is stored at
+// range + rank.  A warp's store instruction then covers <= 8 contiguous pieces instead of one -- more sectors per
+// request than a staged copy-out, but half the instructions and no shared-memory traffic; L2 merges the pieces
+// before they reach HBM.
+template <int W, bool BY_BUCKET, int ITEMS, bool FULL, bool WITH_VALS>
+DWJ_D void scatter8_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t rows, unsigned int (*s_wcnt)[8],
+                         unsigned long long (*s_wbase)[8]) {
+  using K = typename KeyT<W>::type;
+  constexpr int WARPS = PART_THREADS / 32;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  // lane-constant selectors for "my own partition q = lane & 7" (used by the counter lanes)
+  const unsigned q0 = (lane & 1) ? 0xffffffffu : 0u, q1 = (lane & 2) ? 0xffffffffu : 0u, q2 = (lane & 4) ? 0xffffffffu : 0u;
+  K k[ITEMS], v[ITEMS];
+  uint32_t pr[ITEMS];                              // rank << 4 | partition (partition 8 = dead row)
+  const K *kp = a.keys + base + threadIdx.x, *vp = a.vals + base + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const bool live = FULL || j * PART_THREADS + threadIdx.x < rows;
+    k[j] = live ? load_stream(kp + j * PART_THREADS) : (K)0;
+    if constexpr (WITH_VALS) v[j] = live ? load_stream(vp + j * PART_THREADS) : (K)0;
+  }
+  uint32_t run = 0;                                // lanes 0..7: rows of partition `lane` seen so far by this warp
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const bool live = FULL || j * PART_THREADS + threadIdx.x < rows;
+    const uint32_t p = part_id<W, BY_BUCKET>(a, k[j]);
+    const unsigned alive = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, live);
+    const unsigned b0 = __ballot_sync(0xffffffffu, p & 1u), b1 = __ballot_sync(0xffffffffu, p & 2u), b2 = __ballot_sync(0xffffffffu, p & 4u);
+    const unsigned m0 = (p & 1u) ? b0 : ~b0, m1 = (p & 2u) ? b1 : ~b1, m2 = (p & 4u) ? b2 : ~b2;
+    const unsigned peers = m0 & m1 & m2 & alive;                       // live lanes with my partition
+    const uint32_t before = __shfl_sync(0xffffffffu, run, p);         // the warp's count of my partition so far
+    pr[j] = live ? ((before + __popc(peers & lt)) << 4 | p) : 8u;
+    run += __popc(~(b0 ^ q0) & ~(b1 ^ q1) & ~(b2 ^ q2) & alive);       // counter lanes: rows of partition (lane & 7)
+  }
+  if (lane < 8) s_wcnt[warp][lane] = run;
+  __syncthreads();
+  if (threadIdx.x < 8) {                           // partition q: prefix over the warps, one global reservation
+    const unsigned q = threadIdx.x;
+    unsigned total = 0, pre[WARPS];
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) { pre[w] = total; total += s_wcnt[w][q]; }
+    const unsigned long long g = total ? atomicAdd(a.cursor + q, (unsigned long long)total) : 0ull;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) s_wbase[w][q] = g + pre[w];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    if (FULL || pr[j] != 8u) {
+      const unsigned long long dst = s_wbase[warp][pr[j] & 15u] + (pr[j] >> 4);
+      store_stream(a.out_keys + dst, k[j]);
+      if constexpr (WITH_VALS) store_stream(a.out_vals + dst, v[j]);
+    }
+  }
+}
+
+template <int W, bool BY_BUCKET, int ITEMS>
+__global__ void __launch_bounds__(PART_THREADS, 3) partition_scatter8_kernel(PartitionArgs<W> a) {
+  constexpr uint32_t TILE = PART_THREADS * ITEMS;
+  __shared__ unsigned int s_wcnt[PART_THREADS / 32][8];
+  __shared__ unsigned long long s_wbase[PART_THREADS / 32][8];
+  const bool with_vals = a.vals != nullptr;
+  const uint64_t num_tiles = (a.n + TILE - 1) / TILE;
+  for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint64_t base = tile * TILE;
+    const uint32_t rows = (uint32_t)min((uint64_t)TILE, a.n - base);
+    if (rows == TILE) {
+      if (with_vals) scatter8_tile<W, BY_BUCKET, ITEMS, true, true>(a, base, rows, s_wcnt, s_wbase);
+      else scatter8_tile<W, BY_BUCKET, ITEMS, true, false>(a, base, rows, s_wcnt, s_wbase);
+    } else {
+      if (with_vals) scatter8_tile<W, BY_BUCKET, ITEMS, false, true>(a, base, rows, s_wcnt, s_wbase);
+      else scatter8_tile<W, BY_BUCKET, ITEMS, false, false>(a, base, rows, s_wcnt, s_wbase);
+    }
+    __syncthreads();                               // s_wcnt / s_wbase are reused by the next tile
   }
 }
 

@@ -147,10 +147,50 @@ DWJ_D uint32_t count_matches(const void *table, uint64_t mask, uint64_t b, Bucke
 // No inter-warp communication is needed for these shapes, so there are no CTA barriers at all: a warp takes
 // tiles of 32*ITEMS consecutive rows (every column access is one contiguous 128 B / 256 B request) and the
 // grid strides over tiles in order.  COUNT accumulates in registers and issues one atomic per warp.
-template <int W, int MODE, bool UNIQUE, int ITEMS>
-__global__ void __launch_bounds__(256) probe_simple_kernel(ProbeArgs<W> a) {
+template <int W, int MODE, bool UNIQUE, int ITEMS, bool FULL>
+DWJ_D void simple_round(const ProbeArgs<W> &a, uint64_t base, unsigned lane, unsigned long long &local_count) {
   using K = typename KeyT<W>::type;
   constexpr K SENTINEL = ~(K)0;
+  K key[ITEMS], pval[ITEMS];
+  Bucket<W> bk[ITEMS];
+  uint64_t hb[ITEMS];
+  const uint32_t rows = FULL ? 0u : (uint32_t)min((uint64_t)(32 * ITEMS), a.n - base);
+  const K *kp = a.keys + base + lane, *vp = a.vals + base + lane;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const bool live = FULL || j * 32 + lane < rows;
+    key[j] = live ? load_stream(kp + j * 32) : SENTINEL;
+    if constexpr (MODE == PROBE_ALIGNED) pval[j] = live ? load_stream(vp + j * 32) : SENTINEL;
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    hb[j] = slot_hash(key[j], a.seed) & a.bucket_mask;
+    bk[j] = load_bucket_ro<W>(a.table, hb[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const uint64_t row = base + (uint64_t)j * 32 + lane;
+    K payload = SENTINEL;
+    if constexpr (MODE == PROBE_COUNT) {
+      if (key[j] != SENTINEL)
+        local_count += UNIQUE ? (find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload) ? 1u : 0u)
+                              : count_matches<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload);
+    } else {
+      const bool hit = find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload) && key[j] != SENTINEL;
+      if (!(FULL || j * 32 + lane < rows)) continue;
+      if constexpr (MODE == PROBE_CONTAINS) {
+        store_stream(a.out_flags + row, hit ? 1u : 0u);
+      } else {                                    // join/join.cpp:97-101, sentinel elsewhere (:41-43)
+        store_stream(a.out_key + row, hit ? key[j] : SENTINEL);
+        store_stream(a.out_build_val + row, hit ? payload : SENTINEL);
+        store_stream(a.out_probe_val + row, hit ? pval[j] : SENTINEL);
+      }
+    }
+  }
+}
+
+template <int W, int MODE, bool UNIQUE, int ITEMS>
+__global__ void __launch_bounds__(256) probe_simple_kernel(ProbeArgs<W> a) {
   constexpr uint64_t WTILE = 32ull * ITEMS;
   const unsigned lane = threadIdx.x & 31;
   const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
@@ -158,42 +198,8 @@ __global__ void __launch_bounds__(256) probe_simple_kernel(ProbeArgs<W> a) {
   unsigned long long local_count = 0;
   for (uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < tiles; tile += warps_total) {
     const uint64_t base = tile * WTILE;
-    const bool full = base + WTILE <= a.n;
-    K key[ITEMS], pval[ITEMS];
-    Bucket<W> bk[ITEMS];
-    uint64_t hb[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      const uint64_t row = base + (uint64_t)j * 32 + lane;
-      const bool live = full || row < a.n;
-      key[j] = live ? load_stream(a.keys + row) : SENTINEL;
-      if constexpr (MODE == PROBE_ALIGNED) pval[j] = live ? load_stream(a.vals + row) : SENTINEL;
-    }
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      hb[j] = slot_hash(key[j], a.seed) & a.bucket_mask;
-      bk[j] = load_bucket_ro<W>(a.table, hb[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      const uint64_t row = base + (uint64_t)j * 32 + lane;
-      K payload = SENTINEL;
-      if constexpr (MODE == PROBE_COUNT) {
-        if (key[j] != SENTINEL)
-          local_count += UNIQUE ? (find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload) ? 1u : 0u)
-                                : count_matches<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload);
-      } else {
-        const bool hit = key[j] != SENTINEL && find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload);
-        if (!(full || row < a.n)) continue;
-        if constexpr (MODE == PROBE_CONTAINS) {
-          store_stream(a.out_flags + row, hit ? 1u : 0u);
-        } else {                                    // join/join.cpp:97-101, sentinel elsewhere (:41-43)
-          store_stream(a.out_key + row, hit ? key[j] : SENTINEL);
-          store_stream(a.out_build_val + row, hit ? payload : SENTINEL);
-          store_stream(a.out_probe_val + row, hit ? pval[j] : SENTINEL);
-        }
-      }
-    }
+    if (base + WTILE <= a.n) simple_round<W, MODE, UNIQUE, ITEMS, true>(a, base, lane, local_count);
+    else simple_round<W, MODE, UNIQUE, ITEMS, false>(a, base, lane, local_count);
   }
   if constexpr (MODE == PROBE_COUNT) {
 #pragma unroll
@@ -305,12 +311,50 @@ __global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeA
 // overflows.
 //   ORDERED = true : chunk base from the decoupled look-back -> output in probe-row order (reference order)
 //   ORDERED = false: chunk base from one atomicAdd on the match counter -> same multiset, chunk order arbitrary
+// One round of a warp: 32*ITEMS consecutive rows starting at `base`.  FULL = no row of the round is past the end
+// of the relation: no bounds predicates at all (interior rounds; the 64-bit compares and predicated loads of the
+// guarded version were a third of the instruction stream).
+template <int W, bool WITH_KEY, int ITEMS, bool FULL>
+DWJ_D void staged_round(const ProbeArgs<W> &a, uint64_t base, unsigned lane, unsigned lt, typename KeyT<W>::type *wb,
+                        typename KeyT<W>::type *wp, typename KeyT<W>::type *wk, uint32_t &staged) {
+  using K = typename KeyT<W>::type;
+  constexpr K SENTINEL = ~(K)0;
+  K key[ITEMS], pval[ITEMS];
+  Bucket<W> bk[ITEMS];
+  uint64_t hb[ITEMS];
+  const K *kp = a.keys + base + lane, *vp = a.vals + base + lane;
+  const uint32_t rows = FULL ? 0u : (uint32_t)min((uint64_t)(32 * ITEMS), a.n - base);
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const bool live = FULL || j * 32 + lane < rows;
+    key[j] = live ? load_stream(kp + j * 32) : SENTINEL;       // SENTINEL never matches (reserved key)
+    pval[j] = live ? load_stream(vp + j * 32) : SENTINEL;
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    hb[j] = slot_hash(key[j], a.seed) & a.bucket_mask;
+    bk[j] = load_bucket_ro<W>(a.table, hb[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    K payload = SENTINEL;
+    const bool hit = find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload) && key[j] != SENTINEL;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const uint32_t o = staged + __popc(m & lt);
+      wb[o] = payload;
+      wp[o] = pval[j];
+      if constexpr (WITH_KEY) wk[o] = key[j];
+    }
+    staged += __popc(m);
+  }
+}
+
 template <int W, bool ORDERED, bool WITH_KEY, int WARPS, int ITEMS, int SUB, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) probe_pairs_staged_kernel(ProbeArgs<W> a) {
   using K = typename KeyT<W>::type;
   constexpr int WROWS = 32 * ITEMS * SUB;           // rows per warp
   constexpr int CHUNK = WARPS * WROWS;
-  constexpr K SENTINEL = ~(K)0;
   extern __shared__ __align__(16) unsigned char s_raw[];
   K *s_build = reinterpret_cast<K *>(s_raw);
   K *s_probe = s_build + CHUNK;
@@ -324,42 +368,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) probe_pairs_staged_kernel(Pr
   __syncthreads();
   const uint64_t chunk = s_chunk;
   const uint64_t warp_base = chunk * CHUNK + (uint64_t)warp * WROWS;
-  const bool full = warp_base + WROWS <= a.n;       // warp-uniform
   K *wb = s_build + warp * WROWS, *wp = s_probe + warp * WROWS, *wk = s_key + warp * WROWS;
   const unsigned lt = (1u << lane) - 1u;
   uint32_t staged = 0;                              // warp-uniform running count
 
+  if (warp_base + WROWS <= a.n) {                   // warp-uniform: the whole slice is inside the relation
 #pragma unroll 1
-  for (int sub = 0; sub < SUB; ++sub) {
-    const uint64_t base = warp_base + (uint64_t)sub * (32 * ITEMS);
-    if (!full && base >= a.n) break;                // warp-uniform
-    K key[ITEMS], pval[ITEMS];
-    Bucket<W> bk[ITEMS];
-    uint64_t hb[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      const uint64_t row = base + (uint64_t)j * 32 + lane;
-      const bool live = full || row < a.n;
-      key[j] = live ? load_stream(a.keys + row) : SENTINEL;
-      pval[j] = live ? load_stream(a.vals + row) : SENTINEL;
-    }
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      hb[j] = slot_hash(key[j], a.seed) & a.bucket_mask;
-      bk[j] = load_bucket_ro<W>(a.table, hb[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      K payload = SENTINEL;
-      const bool hit = key[j] != SENTINEL && find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload);
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const uint32_t o = staged + __popc(m & lt);
-        wb[o] = payload;
-        wp[o] = pval[j];
-        if constexpr (WITH_KEY) wk[o] = key[j];
-      }
-      staged += __popc(m);
+    for (int sub = 0; sub < SUB; ++sub)
+      staged_round<W, WITH_KEY, ITEMS, true>(a, warp_base + (uint64_t)sub * (32 * ITEMS), lane, lt, wb, wp, wk, staged);
+  } else {
+#pragma unroll 1
+    for (int sub = 0; sub < SUB; ++sub) {
+      const uint64_t base = warp_base + (uint64_t)sub * (32 * ITEMS);
+      if (base >= a.n) break;
+      staged_round<W, WITH_KEY, ITEMS, false>(a, base, lane, lt, wb, wp, wk, staged);
     }
   }
   if (lane == 0) s_wtot[warp] = staged;
@@ -383,13 +405,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) probe_pairs_staged_kernel(Pr
   unsigned long long out_base = s_base;
 #pragma unroll
   for (int w = 0; w < WARPS; ++w) out_base += w < (int)warp ? s_wtot[w] : 0u;
-  const bool fits = out_base + staged <= a.capacity;
-  for (uint32_t i = lane; i < staged; i += 32) {
-    const unsigned long long o = out_base + i;
-    if (fits || o < a.capacity) {
-      store_stream(a.out_build_val + o, wb[i]);
-      store_stream(a.out_probe_val + o, wp[i]);
-      if constexpr (WITH_KEY) store_stream(a.out_key + o, wk[i]);
+  K *ob = a.out_build_val + out_base, *op = a.out_probe_val + out_base, *ok = a.out_key + out_base;
+  if (out_base + staged <= a.capacity) {            // warp-uniform: no per-row capacity checks
+    for (uint32_t i = lane; i < staged; i += 32) {
+      store_stream(ob + i, wb[i]);
+      store_stream(op + i, wp[i]);
+      if constexpr (WITH_KEY) store_stream(ok + i, wk[i]);
+    }
+  } else {
+    for (uint32_t i = lane; i < staged; i += 32) {
+      if (out_base + i < a.capacity) {
+        store_stream(ob + i, wb[i]);
+        store_stream(op + i, wp[i]);
+        if constexpr (WITH_KEY) store_stream(ok + i, wk[i]);
+      }
     }
   }
 }

@@ -64,6 +64,10 @@ extern "C" {
                                            (seq_join semantics).                           */
 #define DWJ_FLAG_L2_PERSIST 0x2u        /* pin the table in L2 with an access-policy window
                                            when it fits the device's persisting-L2 limit    */
+#define DWJ_FLAG_NO_PARTITION 0x8u      /* never radix-partition inputs by table region (keeps
+                                           dwj_probe_pairs in probe-row order for tables
+                                           larger than L2, at the price of ~100 B of DRAM line
+                                           fills per probe row)                                */
 #define DWJ_FLAG_UNORDERED_OUTPUT 0x4u  /* dwj_probe_pairs may emit rows in any order (same
                                            multiset): output ranges are handed out with one
                                            atomicAdd per chunk instead of the order-preserving
@@ -103,6 +107,10 @@ typedef struct {
   uint64_t l2_bytes;
   uint32_t launches_build;   /* kernels (incl. memsets) one dwj_build enqueues             */
   uint32_t launches_probe;   /* kernels (incl. memsets) the last dwj_probe_* enqueued      */
+  uint32_t radix_parts;      /* > 1: build and probe rows are first radix-partitioned into
+                                this many table regions (L2 locality); dwj_probe_pairs then
+                                emits rows region by region instead of in probe-row order   */
+  uint32_t reserved;
 } dwj_info;
 
 DWJ_API int dwj_abi_version(void);

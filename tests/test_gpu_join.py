@@ -359,6 +359,54 @@ def test_table_larger_than_l2_int64(dwj):
     with dwj.Engine(R, key_bytes=8, flags=dwj.FLAG_UNIQUE_BUILD_KEYS) as e:
         e.build(ak, av, R)
         oa, ob = torch.empty_like(bk), torch.empty_like(bk)
+        assert e.info()["radix_parts"] > 1                       # a table this size is probed region by region
         m = e.probe_pairs(bk, bv, S, None, oa, ob, S)
         assert m == S
-        assert torch.equal(oa, av[idx]) and torch.equal(ob, bv)
+        # rows come out region-major: check them through the probe payload (= probe row id)
+        assert torch.equal(oa, av[idx[ob]])
+        assert torch.equal(torch.sort(ob).values, bv)
+        assert e.probe_count(bk, S) == S
+    with dwj.Engine(R, key_bytes=8, flags=dwj.FLAG_UNIQUE_BUILD_KEYS | dwj.FLAG_NO_PARTITION) as e:
+        assert e.info()["radix_parts"] == 1                      # opt-out keeps probe-row order
+        e.build(ak, av, R)
+        m = e.probe_pairs(bk, bv, S, None, oa, ob, S)
+        assert m == S and torch.equal(oa, av[idx]) and torch.equal(ob, bv)
+
+
+@pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("unique", [True, False])
+def test_region_partitioned_path_small(dwj, oracle, monkeypatch, wide, unique):
+    """Force the L2-region path at test size (1 MB regions) and compare with the oracle: same multiset for unique and
+    duplicate build keys, same counts; region-major output order is allowed."""
+    monkeypatch.setenv("DWJ_PARTITION_MIN_MB", "0")
+    monkeypatch.setenv("DWJ_REGION_MB", "0.25")
+    rng = np.random.default_rng(5 + wide + 2 * unique)
+    dt = np.uint64 if wide else np.uint32
+    n = 150_001
+    if unique:
+        ak = (rng.permutation(n).astype(np.uint64) * 2654435761 % (2**32 - 5)).astype(dt)
+        ak = np.unique(ak)
+    else:
+        ak = rng.integers(0, 40_000, n).astype(dt)
+    av = rng.integers(0, 2**31, len(ak)).astype(dt)
+    bk = np.concatenate([ak[rng.integers(0, len(ak), 200_000)], rng.integers(2**31, 2**32 - 2, 5003).astype(dt)])
+    bv = np.arange(len(bk), dtype=dt)
+    flags = dwj.FLAG_UNIQUE_BUILD_KEYS if unique else 0
+    with dwj.Engine(len(ak), key_bytes=dt().itemsize, flags=flags) as e:
+        parts = e.info()["radix_parts"]
+        assert parts >= 8
+        dak, dav, dbk, dbv = dev(ak), dev(av), dev(bk), dev(bv)
+        e.build(dak, dav, len(ak))
+        cnt = e.probe_count(dbk, len(bk))
+        ok, oa, ob = (empty_like_dev(cnt, dt) for _ in range(3))
+        m = e.probe_pairs(dbk, dbv, len(bk), ok, oa, ob, cnt)
+        torch.cuda.synchronize()
+        got = pyoracle.canonical_rows(*(host(t, dt)[:m] for t in (ok, oa, ob)))
+        # the reference-shaped entry points never partition (they are positional): still exact
+        fl = torch.empty(len(bk), dtype=torch.int32, device="cuda")
+        e.probe_contains(dbk, len(bk), fl)
+        assert int(fl.sum().item()) == 200_000
+    want = oracle.sort_join(ak, av, bk, bv)
+    assert m == cnt == len(want[0])
+    for w, x in zip(want, got):
+        np.testing.assert_array_equal(w, x)

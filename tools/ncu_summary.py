@@ -36,19 +36,28 @@ def main(rep, top=25):
             if h in WANT:
                 print(f"  {h:78s} {units[i]:14s} {vals[i]}")
     src = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv"]))))
-    if len(src) < 3:
-        return
-    h = src[1]
-    idx = {k: i for i, k in enumerate(h)}
-    data = [r for r in src[2:] if len(r) == len(h)]
-    stalls = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
-    tot = sum(int(r[idx["# Samples"]] or 0) for r in data)
-    agg = {s: sum(int(r[idx[s]] or 0) for r in data) for s in stalls}
-    print(f"  SASS instructions: {len(data)}, stall samples: {tot}")
-    print("  stalls: " + ", ".join(f"{k[6:]} {100 * v / max(tot, 1):.1f}%" for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v * 100 > tot))
-    for r in sorted(data, key=lambda r: -int(r[idx["# Samples"]] or 0))[:top]:
-        st = sorted(((s[6:], int(r[idx[s]] or 0)) for s in stalls), key=lambda kv: -kv[1])[:2]
-        print(f"   {r[idx['Address']][-5:]} {int(r[idx['# Samples']] or 0):7d} {r[idx['Instructions Executed']]:>9s}  {r[idx['Source']][:72]:72s} {st}")
+    blocks, cur = [], None
+    for row in src:                                  # one block per kernel: "Kernel Name" line, header line, data
+        if row and row[0] == "Kernel Name":
+            cur = {"name": row[1] if len(row) > 1 else "?", "rows": []}
+            blocks.append(cur)
+        elif cur is not None:
+            cur["rows"].append(row)
+    for blk in blocks:
+        if len(blk["rows"]) < 2:
+            continue
+        h = blk["rows"][0]
+        idx = {k: i for i, k in enumerate(h)}
+        data = [r for r in blk["rows"][1:] if len(r) == len(h)]
+        stalls = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
+        tot = sum(int(r[idx["# Samples"]] or 0) for r in data)
+        agg = {s: sum(int(r[idx[s]] or 0) for r in data) for s in stalls}
+        print(f"## source: {blk['name'][:100]}")
+        print(f"  SASS instructions: {len(data)}, stall samples: {tot}")
+        print("  stalls: " + ", ".join(f"{k[6:]} {100 * v / max(tot, 1):.1f}%" for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v * 100 > tot))
+        for r in sorted(data, key=lambda r: -int(r[idx["# Samples"]] or 0))[:top]:
+            st = sorted(((s[6:], int(r[idx[s]] or 0)) for s in stalls), key=lambda kv: -kv[1])[:2]
+            print(f"   {r[idx['Address']][-5:]} {int(r[idx['# Samples']] or 0):7d} {r[idx['Instructions Executed']]:>9s}  {r[idx['Source']][:72]:72s} {st}")
 
 
 if __name__ == "__main__":

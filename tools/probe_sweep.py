@@ -40,6 +40,7 @@ def main():
         args.flags |= dwj.FLAG_UNORDERED_OUTPUT
     tdt = torch.int32 if args.key_bytes == 4 else torch.int64
     print(f"probe rows {S}, key bytes {args.key_bytes}, load factor {args.load_factor}, flags {args.flags}")
+    print("DWJ_PARTITION_MIN_MB =", os.environ.get("DWJ_PARTITION_MIN_MB"), " DWJ_REGION_MB =", os.environ.get("DWJ_REGION_MB"))
     print(f"{'build':>10} {'table MB':>9} | {'build ms':>9} {'Gins/s':>7} | {'count':>8} {'contains':>8} {'aligned':>8} {'pairs':>8} {'pairs+key':>9}  (ms; G probes/s in brackets)")
     for lg in args.build_log2:
         R = 1 << lg
@@ -57,6 +58,7 @@ def main():
             timed(lambda: e.probe_pairs(inp.probe_keys, inp.probe_vals, S, ok, ob, op, S, d_n_matches=cnt, sync=False)),
         ]
         mb = e.info()["table_bytes"] / 2**20
+        print(f"parts {e.info()['radix_parts']:>4}", end=" ")
         print(f"{R:>10} {mb:>9.0f} | {tb:>9.3f} {R / tb / 1e6:>7.2f} | " + " ".join(f"{t:>5.2f}[{S / t / 1e6:>4.0f}]" for t in res), flush=True)
         e.close()
         del inp, ok, ob, op, fl
