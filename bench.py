@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-partition", action="store_true", help="probe the table directly (probe-row output order)")
     ap.add_argument("--unordered", action="store_true", help="DWJ_FLAG_UNORDERED_OUTPUT")
     ap.add_argument("--emit-key", action="store_true", help="also materialise the key column (reference row shape)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange: fused partition+P2P stores over NVLink (default) or NCCL all-to-all-v")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-probe-rows", type=int, default=1 << 26)
@@ -171,12 +173,13 @@ def run_cpu_baseline(kind, n_build, n_probe_sample, repeats=1):
             "host_ms": best["host_us"] / 1e3}
 
 
-def main_reference(args, kind, n_build, n_probe, key_bytes, workload_name):
+def main_reference(args, kind, n_build, n_probe, key_bytes, workload_name, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     if key_bytes != 4:
-        print(json.dumps({"impl": "reference", "unavailable": "the reference Join path is uint32-only (SURVEY fact 5)"}))
+        out.write(json.dumps({"impl": "reference", "unavailable": "the reference Join path is uint32-only (SURVEY fact 5)"}) + "\n")
+        out.flush()
         return 0
     run, which, threads = cpu_baseline_runner()
     n_sample = min(n_probe, args.cpu_sample_probe_rows)
@@ -188,14 +191,15 @@ def main_reference(args, kind, n_build, n_probe, key_bytes, workload_name):
     value = (len(ak) + len(bk)) / (ms * 1e-3)
     sample = (f"each step joins the full build relation ({len(ak)} rows) with the first {len(bk)} of {n_probe} probe rows "
               f"on {threads} host threads; timed as join.cpp:59-113")
-    print(json.dumps({
+    out.write(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic", "config": {"workload": workload_name, "build_rows": n_build, "probe_rows": n_probe,
                                                         "sampled_probe_rows": len(bk)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": which, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0}) + "\n")
+    out.flush()
     return 0
 
 
@@ -225,13 +229,17 @@ def make_input(kind, n_build, n_probe, key_bytes, device, **kw):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else a library prints to fd 1 (e.g. NCCL's version banner)
+    # is sent to stderr; the JSON is written to the saved descriptor.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     kind, n_build, n_probe, key_bytes = WORKLOADS[args.workload]
     overridden = bool(args.build_rows or args.probe_rows)
     n_build = args.build_rows or n_build
     n_probe = args.probe_rows or n_probe
     if args.impl == "reference":
-        return main_reference(args, kind, n_build, n_probe, key_bytes, args.workload)
+        return main_reference(args, kind, n_build, n_probe, key_bytes, args.workload, real_stdout)
 
     import torch
     import torch.distributed as dist
@@ -266,7 +274,10 @@ def main():
     flags = ((dwj.FLAG_UNIQUE_BUILD_KEYS if inp.unique_build else 0) | (dwj.FLAG_L2_PERSIST if args.l2_persist else 0)
              | (dwj.FLAG_NO_PARTITION if args.no_partition else 0) | (dwj.FLAG_UNORDERED_OUTPUT if args.unordered else 0))
     cap_rows = n_build if world == 1 else int(n_build * 1.25) + 1024
-    eng = dwj.Engine(cap_rows, key_bytes=key_bytes, device=local_rank, load_factor=args.load_factor, flags=flags)
+    # Multi-GPU: a rank receives ~n_build rows +- hash imbalance; 1.25x head-room at load 0.65 keeps the same table
+    # size (2 slots per expected row) as the single-GPU run.
+    load_factor = args.load_factor if world == 1 else min(0.9, args.load_factor * 1.3)
+    eng = dwj.Engine(cap_rows, key_bytes=key_bytes, device=local_rank, load_factor=load_factor, flags=flags)
     info = eng.info()
     out_cap = matches if world == 1 else int(n_probe * 1.25) + 1024
     out_key = torch.empty(out_cap, dtype=tdt, device=device) if args.emit_key else None
@@ -282,8 +293,24 @@ def main():
                             sync=False, stream=stream)
         launches_per_step = None
     else:
-        from dwarf_bench_b200.distributed import CudaJoinOps, ExchangeJoin
-        xj = ExchangeJoin(CudaJoinOps(eng, stream), device, tdt)
+        from dwarf_bench_b200.distributed import CudaJoinOps, ExchangeJoin, P2PExchangeJoin
+        exchange_used = "nccl all-to-all-v"
+        xj = None
+        if args.exchange == "p2p":
+            try:
+                xj = P2PExchangeJoin(eng, device, tdt, cap_rows, out_cap, stream=stream)
+                exchange_used = "fused partition + P2P stores into peer memory (NVLink), counts by all-gather"
+            except Exception as ex:      # peer mapping unavailable on this box: NCCL path (still GPU-only)
+                print(f"[rank {rank}] symmetric memory unavailable ({ex!r}); using NCCL all-to-all-v", file=sys.stderr)
+                xj = None
+            # all ranks must take the same path
+            ok = torch.tensor([1 if xj is not None else 0], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                xj = None
+                exchange_used = "nccl all-to-all-v"
+        if xj is None:
+            xj = ExchangeJoin(CudaJoinOps(eng, stream), device, tdt)
 
         def step():
             xj.join(inp.build_keys, inp.build_vals, n_build, inp.probe_keys, inp.probe_vals, n_probe, out_key, out_b, out_p,
@@ -359,7 +386,7 @@ def main():
                    "output_order": "probe-row order" if info["radix_parts"] == 1 and not args.unordered else "region-major / unordered",
                    "l2_between_iterations": "inputs and outputs (%.1f GB per step) far exceed the 126 MB L2; no explicit flush"
                                             % (((n_build + n_probe) * 2 + matches * 2) * key_bytes / 1e9),
-                   "parallelism": "single GPU" if world == 1 else f"hash-partitioned x{world}, NCCL all-to-all-v"},
+                   "parallelism": "single GPU" if world == 1 else f"hash-partitioned x{world}, {exchange_used}"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks.summary(),
         "wall_ms_per_step": wall_ms / args.steps,
@@ -373,11 +400,24 @@ def main():
         # whichever algorithm runs, report against the NON-partitioned sector-granular model of this table
         l2_res = info["table_bytes"] <= 100e6
         probe_bytes, step_bytes = algorithmic_bytes(n_build, n_probe, matches, key_bytes, info["slots"], args.emit_key, l2_res)
-        achieved = probe_bytes / (probe_ms * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "probe_kernel (PAIRS)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                            "algorithmic_bytes_per_launch": probe_bytes, "kernel_ms": probe_ms,
+        # The dominant kernel is the probe kernel proper; its duration comes from the engine's own CUDA-event pair
+        # around that launch (last timed step), the phase times from the events recorded above.
+        tm = eng.timings()
+        kernel_ms = tm.probe_kernel_ms if tm.probe_kernel_ms > 0 else probe_ms
+        achieved = probe_bytes / (kernel_ms * 1e-3) / 1e9
+        kname = "probe_pairs_staged_kernel" if inp.unique_build else "probe_pairs_multi_kernel"
+        traffic = None
+        try:        # dram__bytes_read+write of that kernel from the committed ncu --set full capture of this command
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload][kname]
+        except Exception:
+            pass
+        line["roofline"] = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": probe_bytes, "kernel_ms": kernel_ms,
                             "frac_of_nominal_8000": achieved / 8000.0,
+                            "probe_phase": {"ms": probe_ms, "includes": "region partition of the probe relation + probe kernel",
+                                            "achieved": probe_bytes / (probe_ms * 1e-3) / 1e9,
+                                            "frac": probe_bytes / (probe_ms * 1e-3) / 1e9 / peak},
                             "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                                            "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
                             "table_model": "L2-resident" if l2_res else "HBM-resident (sector-granular, SURVEY 8d)"}
@@ -447,7 +487,8 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
 
     if rank == 0:
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -24,7 +24,7 @@ ERR_NAMES = {0: "DWJ_OK", -1: "DWJ_ERR_INVALID", -2: "DWJ_ERR_CUDA", -3: "DWJ_ER
 # Every symbol include/dwj.h declares (tests check the library exports exactly these).
 SYMBOLS = ("dwj_abi_version", "dwj_last_error", "dwj_create", "dwj_destroy", "dwj_get_info", "dwj_build",
            "dwj_probe_aligned", "dwj_probe_contains", "dwj_probe_pairs", "dwj_probe_count", "dwj_timings",
-           "dwj_join_host", "dwj_partition", "dwj_partition_of")
+           "dwj_join_host", "dwj_partition", "dwj_partition_hist", "dwj_partition_scatter_to", "dwj_partition_of")
 
 
 class DwjError(RuntimeError):
@@ -40,7 +40,7 @@ class Config(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("build_ms", C.c_float), ("probe_ms", C.c_float), ("partition_ms", C.c_float), ("h2d_ms", C.c_float),
-                ("d2h_ms", C.c_float), ("total_ms", C.c_float)]
+                ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("probe_kernel_ms", C.c_float), ("build_kernel_ms", C.c_float)]
 
 
 class Info(C.Structure):
@@ -58,6 +58,8 @@ class JoinTiming:
     h2d_ms: float = 0.0
     d2h_ms: float = 0.0
     total_ms: float = 0.0
+    probe_kernel_ms: float = 0.0
+    build_kernel_ms: float = 0.0
 
 
 def lib_path() -> str:
@@ -92,6 +94,8 @@ def load_library():
     lib.dwj_join_host.argtypes = [vp, vp, vp, u64, vp, vp, u64, C.c_int, vp, vp, vp, u64, C.POINTER(u64),
                                   C.POINTER(Timing)]
     lib.dwj_partition.argtypes = [vp, vp, vp, u64, u32, vp, vp, vp, vp]
+    lib.dwj_partition_hist.argtypes = [vp, vp, u64, u32, vp, vp]
+    lib.dwj_partition_scatter_to.argtypes = [vp, vp, vp, u64, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), vp]
     lib.dwj_partition_of.argtypes = [u64, C.c_int32, u32, u64]
     lib.dwj_partition_of.restype = u32
     for name in SYMBOLS:
@@ -204,6 +208,19 @@ class Engine:
     def partition(self, d_keys, d_vals, n_rows: int, n_parts: int, d_out_keys, d_out_vals, d_offsets, stream=None) -> None:
         self._check(self.lib.dwj_partition(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, n_parts, _ptr(d_out_keys),
                                            _ptr(d_out_vals), _ptr(d_offsets), _stream(stream)))
+
+
+    def partition_hist(self, d_keys, n_rows: int, n_parts: int, d_counts, stream=None) -> None:
+        self._check(self.lib.dwj_partition_hist(self._h, _ptr(d_keys), n_rows, n_parts, _ptr(d_counts), _stream(stream)))
+
+    def partition_scatter_to(self, d_keys, d_vals, n_rows: int, n_parts: int, dst_keys, dst_vals, dst_row_offsets,
+                             stream=None) -> None:
+        """dst_keys / dst_vals: sequences of device pointers (ints), possibly peer memory; dst_row_offsets: ints."""
+        pk = (C.c_void_p * n_parts)(*[int(x) for x in dst_keys])
+        pv = (C.c_void_p * n_parts)(*[int(x) for x in dst_vals]) if d_vals is not None else None
+        off = (C.c_uint64 * n_parts)(*[int(x) for x in dst_row_offsets])
+        self._check(self.lib.dwj_partition_scatter_to(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, n_parts, pk, pv, off,
+                                                      _stream(stream)))
 
 
 def partition_of(key: int, key_bytes: int, n_parts: int, hash_seed: int = 42) -> int:

@@ -59,7 +59,8 @@ constexpr StagedShape STAGED_SHAPES_4[] = {{8, 4, 4, 4}, {8, 4, 8, 2}, {8, 2, 8,
 constexpr StagedShape STAGED_SHAPES_8[] = {{8, 2, 4, 4}, {8, 2, 8, 2}, {8, 4, 2, 4}, {4, 2, 4, 8}, {8, 4, 4, 2}};
 constexpr int DEFAULT_STAGED_SHAPE_4 = 2, DEFAULT_STAGED_SHAPE_8 = 3;   // gpurun sweep, profiles/r1_probe.md
 constexpr int SIMPLE_ITEMS_4 = 4, SIMPLE_ITEMS_8 = 4;   // rows per thread per round, warp-centric kernel
-constexpr uint64_t HOST_CHUNK_BYTES = 64ull << 20;   // per column per pipeline stage in dwj_join_host
+constexpr uint64_t HOST_CHUNK_BYTES = 32ull << 20;   // per column per pipeline stage in dwj_join_host
+constexpr int HOST_STAGES = 4;                       // staging slots of the dwj_join_host pipeline
 
 }  // namespace
 
@@ -74,7 +75,7 @@ struct dwj_engine {
   bool l2_window = false;
   cudaAccessPolicyWindow window{};
   // events
-  cudaEvent_t ev_build[2]{}, ev_probe[2]{}, ev_part[2]{};
+  cudaEvent_t ev_build[2]{}, ev_probe[2]{}, ev_part[2]{}, ev_probek[2]{}, ev_buildk[2]{};
   bool have_build = false, have_probe = false, have_part = false;
   // scan / counters scratch
   unsigned long long *tile_state = nullptr;
@@ -90,8 +91,10 @@ struct dwj_engine {
   // dwj_join_host staging
   void *stage = nullptr;
   uint64_t stage_bytes = 0;
-  cudaStream_t hs[2]{};
-  cudaEvent_t hev[6]{};
+  cudaStream_t hs[3]{};                        // H2D, compute, D2H
+  cudaEvent_t hev[3 * HOST_STAGES]{};          // per slot: input landed, probe done, slot free
+  cudaEvent_t htime[4]{};
+  unsigned long long *h_counts = nullptr;      // pinned: per-slot match counts
   dwj_timing last_host{};
 };
 
@@ -182,6 +185,56 @@ int partition_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n
   return DWJ_OK;
 }
 
+// Histogram only (exchange planning): counts per partition of the independent partition hash -> d_counts[parts].
+template <int W> int partition_hist_impl(dwj_engine *e, const void *keys, uint64_t n, uint32_t log2_parts, uint64_t *d_counts, cudaStream_t s) {
+  using K = typename dwj::KeyT<W>::type;
+  dwj::PartitionArgs<W> a{};
+  a.keys = (const K *)keys;
+  a.n = n;
+  a.log2_parts = log2_parts;
+  a.seed = e->cfg.hash_seed;
+  a.hist = (unsigned long long *)d_counts;
+  constexpr int HROWS = 8;
+  CU(cudaMemsetAsync(d_counts, 0, sizeof(uint64_t) << log2_parts, s));
+  if (!n) return DWJ_OK;
+  const uint64_t htiles = (n + 256ull * HROWS - 1) / (256ull * HROWS);
+  const dim3 hgrid((unsigned)std::min<uint64_t>(htiles, (uint64_t)e->prop.multiProcessorCount * 8));
+  if (log2_parts <= 3) CU(launch(e, dwj::partition_hist8_kernel<W, false, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
+  else CU(launch(e, dwj::partition_hist_kernel<W, false, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
+  return DWJ_OK;
+}
+
+// Scatter straight into per-partition destinations (local or peer memory); <= 8 partitions.  The caller has planned
+// the layout: rows of partition p go to dst_keys[p][row_offsets[p] ...].
+template <int W>
+int partition_scatter_to_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, uint32_t log2_parts, void *const *dst_keys,
+                              void *const *dst_vals, const uint64_t *row_offsets, cudaStream_t s) {
+  using K = typename dwj::KeyT<W>::type;
+  dwj::PartitionArgs<W> a{};
+  a.keys = (const K *)keys;
+  a.vals = (const K *)vals;
+  a.n = n;
+  a.log2_parts = log2_parts;
+  a.seed = e->cfg.hash_seed;
+  a.use_dst = 1;
+  a.cursor = e->part_scratch + dwj::PART_MAX;
+  unsigned long long start[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (uint32_t p = 0; p < (1u << log2_parts); ++p) {
+    a.dst_keys[p] = (K *)dst_keys[p];
+    a.dst_vals[p] = vals ? (K *)dst_vals[p] : nullptr;
+    start[p] = row_offsets[p];
+  }
+  // The cursors start at the planned offsets; cudaMemcpyAsync from a stack array is safe because pageable H2D copies
+  // are staged before the call returns.
+  CU(cudaMemcpyAsync(a.cursor, start, sizeof(start), cudaMemcpyHostToDevice, s));
+  if (!n) return DWJ_OK;
+  constexpr int ITEMS8 = W == 4 ? 16 : 8;
+  const uint64_t tiles8 = (n + 256ull * ITEMS8 - 1) / (256ull * ITEMS8);
+  CU(launch(e, dwj::partition_scatter8_kernel<W, false, ITEMS8>, dim3((unsigned)std::min<uint64_t>(tiles8, 0x7fffffffull)),
+            dim3(dwj::PART_THREADS), s, a, false));
+  return DWJ_OK;
+}
+
 // Grow-only scratch for the region-partitioned copy of a relation: [keys | payloads], rows each.
 int ensure_region_buffer(void **buf, uint64_t *cap_rows, uint64_t rows, int W, cudaStream_t s) {
   if (rows <= *cap_rows) return DWJ_OK;
@@ -214,7 +267,9 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
     dwj::BuildArgs<W> a{(const K *)keys, (const K *)vals, n, e->table, e->buckets - 1, e->cfg.hash_seed};
     constexpr int ROWS = 4;
     const uint64_t tiles = (n + 256ull * ROWS - 1) / (256ull * ROWS);
+    CU(cudaEventRecord(e->ev_buildk[0], s));
     CU(launch(e, dwj::build_kernel<W, ROWS>, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(256), s, a, true));
+    CU(cudaEventRecord(e->ev_buildk[1], s));
     e->launches_build++;
   }
   CU(cudaEventRecord(e->ev_build[1], s));
@@ -350,6 +405,7 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
     a.vals = pv;
     extra_launches = 4;
   }
+  CU(cudaEventRecord(e->ev_probek[0], s));
   switch (mode) {
   case dwj::PROBE_ALIGNED: rc = simple_launch<W, dwj::PROBE_ALIGNED, true>(e, a, s); break;
   case dwj::PROBE_CONTAINS: rc = simple_launch<W, dwj::PROBE_CONTAINS, true>(e, a, s); break;
@@ -366,6 +422,7 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
     }
   }
   if (rc) return rc;
+  CU(cudaEventRecord(e->ev_probek[1], s));
   e->launches_probe += extra_launches;
   CU(cudaEventRecord(e->ev_probe[1], s));
   e->have_probe = true;
@@ -424,7 +481,8 @@ int dwj_create(const dwj_config *cfg, dwj_engine **out) {
     return bail(fail(DWJ_ERR_OOM, "scratch allocation failed"));
   for (int i = 0; i < 2; ++i)
     if (cudaEventCreate(&e->ev_build[i]) != cudaSuccess || cudaEventCreate(&e->ev_probe[i]) != cudaSuccess ||
-        cudaEventCreate(&e->ev_part[i]) != cudaSuccess)
+        cudaEventCreate(&e->ev_part[i]) != cudaSuccess || cudaEventCreate(&e->ev_probek[i]) != cudaSuccess ||
+        cudaEventCreate(&e->ev_buildk[i]) != cudaSuccess)
       return bail(fail(DWJ_ERR_CUDA, "cudaEventCreate failed"));
 
   {   // L2-locality regions (see partition.cuh).  DWJ_REGION_MB / DWJ_PARTITION_MIN_MB are tuning overrides.
@@ -474,10 +532,16 @@ int dwj_destroy(dwj_engine *e) {
     if (e->ev_build[i]) cudaEventDestroy(e->ev_build[i]);
     if (e->ev_probe[i]) cudaEventDestroy(e->ev_probe[i]);
     if (e->ev_part[i]) cudaEventDestroy(e->ev_part[i]);
-    if (e->hs[i]) cudaStreamDestroy(e->hs[i]);
+    if (e->ev_probek[i]) cudaEventDestroy(e->ev_probek[i]);
+    if (e->ev_buildk[i]) cudaEventDestroy(e->ev_buildk[i]);
   }
+  for (auto &st : e->hs)
+    if (st) cudaStreamDestroy(st);
   for (auto &ev : e->hev)
     if (ev) cudaEventDestroy(ev);
+  for (auto &ev : e->htime)
+    if (ev) cudaEventDestroy(ev);
+  if (e->h_counts) cudaFreeHost(e->h_counts);
   cudaGetLastError();
   delete e;
   return DWJ_OK;
@@ -555,10 +619,12 @@ int dwj_timings(dwj_engine *e, dwj_timing *t) {
   if (e->have_build) {
     CU(cudaEventSynchronize(e->ev_build[1]));
     CU(cudaEventElapsedTime(&t->build_ms, e->ev_build[0], e->ev_build[1]));
+    if (e->build_rows) CU(cudaEventElapsedTime(&t->build_kernel_ms, e->ev_buildk[0], e->ev_buildk[1]));
   }
   if (e->have_probe) {
     CU(cudaEventSynchronize(e->ev_probe[1]));
     CU(cudaEventElapsedTime(&t->probe_ms, e->ev_probe[0], e->ev_probe[1]));
+    CU(cudaEventElapsedTime(&t->probe_kernel_ms, e->ev_probek[0], e->ev_probek[1]));
   }
   if (e->have_part) {
     CU(cudaEventSynchronize(e->ev_part[1]));
@@ -588,6 +654,39 @@ int dwj_partition(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_
   return DWJ_OK;
 }
 
+int dwj_partition_hist(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t n_parts, uint64_t *d_counts, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  if (n_parts == 0 || n_parts > (uint32_t)dwj::PART_MAX || (n_parts & (n_parts - 1)))
+    return fail(DWJ_ERR_INVALID, "n_parts must be a power of two in [1, %d], got %u", dwj::PART_MAX, n_parts);
+  if (!d_counts || (n_rows && !d_keys)) return fail(DWJ_ERR_INVALID, "null partition argument");
+  uint32_t lg = 0;
+  while ((1u << lg) < n_parts) ++lg;
+  DeviceGuard g(e->cfg.device);
+  return e->W == 4 ? partition_hist_impl<4>(e, d_keys, n_rows, lg, d_counts, (cudaStream_t)stream)
+                   : partition_hist_impl<8>(e, d_keys, n_rows, lg, d_counts, (cudaStream_t)stream);
+}
+
+int dwj_partition_scatter_to(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_parts,
+                             void *const *dst_keys, void *const *dst_vals, const uint64_t *dst_row_offsets, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  if (n_parts == 0 || n_parts > 8 || (n_parts & (n_parts - 1)))
+    return fail(DWJ_ERR_INVALID, "dwj_partition_scatter_to supports 1, 2, 4 or 8 partitions, got %u", n_parts);
+  if (!dst_keys || !dst_row_offsets || (d_vals && !dst_vals) || (n_rows && !d_keys)) return fail(DWJ_ERR_INVALID, "null partition argument");
+  for (uint32_t p = 0; p < n_parts; ++p)
+    if (!dst_keys[p] || (d_vals && !dst_vals[p])) return fail(DWJ_ERR_INVALID, "null destination for partition %u", p);
+  uint32_t lg = 0;
+  while ((1u << lg) < n_parts) ++lg;
+  DeviceGuard g(e->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaEventRecord(e->ev_part[0], s));
+  const int rc = e->W == 4 ? partition_scatter_to_impl<4>(e, d_keys, d_vals, n_rows, lg, dst_keys, dst_vals, dst_row_offsets, s)
+                           : partition_scatter_to_impl<8>(e, d_keys, d_vals, n_rows, lg, dst_keys, dst_vals, dst_row_offsets, s);
+  if (rc) return rc;
+  CU(cudaEventRecord(e->ev_part[1], s));
+  e->have_part = true;
+  return DWJ_OK;
+}
+
 uint32_t dwj_partition_of(uint64_t key, int32_t key_bytes, uint32_t n_parts, uint64_t hash_seed) {
   uint32_t lg = 0;
   while ((1u << lg) < n_parts) ++lg;
@@ -595,8 +694,9 @@ uint32_t dwj_partition_of(uint64_t key, int32_t key_bytes, uint32_t n_parts, uin
 }
 
 // ---- host-buffer join ---------------------------------------------------------------------------------
-// Build columns go up in one piece; the probe relation is streamed in chunks over two streams so the
-// H2D of chunk i+1 and the D2H of chunk i-1 overlap the probe of chunk i (PCIe is full duplex).
+// Three streams (H2D, compute, D2H) and HOST_STAGES staging slots: the copy engines run continuously while the
+// host only ever waits for a chunk that is two behind the one it just enqueued.  PCIe is full duplex, so the H2D of
+// chunk c+1.. overlaps the probe of chunk c and the D2H of chunk c-1...
 int dwj_join_host(dwj_engine *e, const void *build_keys, const void *build_vals, uint64_t n_build, const void *probe_keys,
                   const void *probe_vals, uint64_t n_probe, int out_mode, void *out_key, void *out_build_val,
                   void *out_probe_val, uint64_t out_capacity, uint64_t *n_out, dwj_timing *timing) {
@@ -613,109 +713,117 @@ int dwj_join_host(dwj_engine *e, const void *build_keys, const void *build_vals,
     return fail(DWJ_ERR_CAPACITY, "%llu build rows exceed the table created for %llu", (unsigned long long)n_build,
                 (unsigned long long)e->cfg.max_build_rows);
   DeviceGuard g(e->cfg.device);
+  constexpr int NS = HOST_STAGES, LAG = 2;
   const uint64_t W = (uint64_t)e->W;
   const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint64_t>(n_probe, 1), HOST_CHUNK_BYTES / W));
-  // staging: build k,v | 2 stages x (probe k,v + out k,b,p) | 2 counters
+  // staging: build k,v | NS stages x (probe k,v + out k,b,p) | NS counters
   const uint64_t build_b = ((n_build * W + 255) / 256) * 256, chunk_b = ((chunk_rows * W + 255) / 256) * 256;
-  const uint64_t need = 2 * build_b + 2 * 5 * chunk_b + 512;
+  const uint64_t need = 2 * build_b + (uint64_t)NS * 5 * chunk_b + 64 * NS;
   if (need > e->stage_bytes) {
     if (e->stage) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->stage)); e->stage = nullptr; e->stage_bytes = 0; }
     CU(cudaMalloc(&e->stage, need));
     e->stage_bytes = need;
   }
-  for (int i = 0; i < 2; ++i)
-    if (!e->hs[i]) CU(cudaStreamCreateWithFlags(&e->hs[i], cudaStreamNonBlocking));
+  for (auto &st : e->hs)
+    if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   for (auto &ev : e->hev)
+    if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : e->htime)
     if (!ev) CU(cudaEventCreate(&ev));
+  if (!e->h_counts) CU(cudaHostAlloc((void **)&e->h_counts, NS * sizeof(unsigned long long), cudaHostAllocDefault));
+  cudaStream_t s_in = e->hs[0], s_comp = e->hs[1], s_out = e->hs[2];
+  cudaEvent_t *ev_in = e->hev, *ev_done = e->hev + NS, *ev_free = e->hev + 2 * NS;
   char *base = (char *)e->stage;
   char *d_bk = base, *d_bv = base + build_b;
   char *stage_base = base + 2 * build_b;
-  unsigned long long *d_cnt = (unsigned long long *)(stage_base + 10 * chunk_b);
-  cudaStream_t s0 = e->hs[0];
+  unsigned long long *d_cnt = (unsigned long long *)(stage_base + (uint64_t)NS * 5 * chunk_b);
+  auto stage_ptr = [&](int st, int col) { return stage_base + (uint64_t)(st * 5 + col) * chunk_b; };
 
-  // hev: 0 start, 1 build h2d done, 2 build done, 3 end
-  CU(cudaEventRecord(e->hev[0], s0));
+  // htime: 0 start, 1 build h2d done, 2 build done, 3 end
+  CU(cudaEventRecord(e->htime[0], s_in));
   if (n_build) {
-    CU(cudaMemcpyAsync(d_bk, build_keys, n_build * W, cudaMemcpyHostToDevice, s0));
-    CU(cudaMemcpyAsync(d_bv, build_vals, n_build * W, cudaMemcpyHostToDevice, s0));
+    CU(cudaMemcpyAsync(d_bk, build_keys, n_build * W, cudaMemcpyHostToDevice, s_in));
+    CU(cudaMemcpyAsync(d_bv, build_vals, n_build * W, cudaMemcpyHostToDevice, s_in));
   }
-  CU(cudaEventRecord(e->hev[1], s0));
-  if (int rc = dwj_build(e, d_bk, d_bv, n_build, s0)) return rc;
-  CU(cudaEventRecord(e->hev[2], s0));
-  CU(cudaStreamWaitEvent(e->hs[1], e->hev[2], 0));
+  CU(cudaEventRecord(e->htime[1], s_in));
+  CU(cudaStreamWaitEvent(s_comp, e->htime[1], 0));
+  if (int rc = dwj_build(e, d_bk, d_bv, n_build, s_comp)) return rc;
+  CU(cudaEventRecord(e->htime[2], s_comp));
 
   uint64_t produced = 0;       // rows written to the host outputs so far (PAIRS) / matches (COUNT)
   bool overflow = false;
   const uint64_t n_chunks = (n_probe + chunk_rows - 1) / chunk_rows;
-  struct Pending { bool active = false; uint64_t rows = 0; } pend[2];
-  auto stage_ptr = [&](int st, int col) { return stage_base + (uint64_t)(st * 5 + col) * chunk_b; };
 
-  // Finish stage st (PAIRS / COUNT): wait for its probe, learn its match count, enqueue its D2H.
-  auto drain = [&](int st) -> int {
-    Pending &p = pend[st];
-    if (!p.active) return DWJ_OK;
-    p.active = false;
-    cudaStream_t s = e->hs[st];
-    unsigned long long c = 0;
-    CU(cudaMemcpyAsync(&c, d_cnt + st * 8, sizeof(c), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+  // Finish chunk c (PAIRS / COUNT): wait for its probe, read its match count, enqueue its D2H at the running offset.
+  auto drain = [&](uint64_t c) -> int {
+    const int st = (int)(c % NS);
+    const uint64_t rows = std::min<uint64_t>(chunk_rows, n_probe - c * chunk_rows);
+    CU(cudaEventSynchronize(ev_done[st]));
+    const unsigned long long cnt = e->h_counts[st];
     if (out_mode == DWJ_OUT_PAIRS) {
-      if (c > chunk_rows)
+      if (cnt > chunk_rows)
         return fail(DWJ_ERR_OVERFLOW,
                     "a probe chunk of %llu rows produced %llu matches; dwj_join_host stages at most one match per probe "
                     "row -- use dwj_probe_pairs with device buffers for higher multiplicities",
-                    (unsigned long long)p.rows, c);
+                    (unsigned long long)rows, cnt);
       const uint64_t room = produced < out_capacity ? out_capacity - produced : 0;
-      const uint64_t take = std::min<uint64_t>(c, room);
-      if (take < c) overflow = true;
+      const uint64_t take = std::min<uint64_t>(cnt, room);
+      if (take < cnt) overflow = true;
+      CU(cudaStreamWaitEvent(s_out, ev_done[st], 0));
       if (take) {
-        if (out_key) CU(cudaMemcpyAsync((char *)out_key + produced * W, stage_ptr(st, 2), take * W, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync((char *)out_build_val + produced * W, stage_ptr(st, 3), take * W, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync((char *)out_probe_val + produced * W, stage_ptr(st, 4), take * W, cudaMemcpyDeviceToHost, s));
+        if (out_key) CU(cudaMemcpyAsync((char *)out_key + produced * W, stage_ptr(st, 2), take * W, cudaMemcpyDeviceToHost, s_out));
+        CU(cudaMemcpyAsync((char *)out_build_val + produced * W, stage_ptr(st, 3), take * W, cudaMemcpyDeviceToHost, s_out));
+        CU(cudaMemcpyAsync((char *)out_probe_val + produced * W, stage_ptr(st, 4), take * W, cudaMemcpyDeviceToHost, s_out));
       }
     }
-    produced += c;
+    CU(cudaEventRecord(ev_free[st], s_out));
+    produced += cnt;
     return DWJ_OK;
   };
 
   for (uint64_t c = 0; c < n_chunks; ++c) {
-    const int st = (int)(c & 1);
-    cudaStream_t s = e->hs[st];
-    // Stage st's previous chunk was drained one iteration ago; its D2H copies sit earlier in this same
-    // stream, so stream order protects the buffers that are overwritten now.
+    const int st = (int)(c % NS);
     const uint64_t row0 = c * chunk_rows, rows = std::min<uint64_t>(chunk_rows, n_probe - row0);
-    CU(cudaMemcpyAsync(stage_ptr(st, 0), (const char *)probe_keys + row0 * W, rows * W, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(stage_ptr(st, 1), (const char *)probe_vals + row0 * W, rows * W, cudaMemcpyHostToDevice, s));
+    if (c >= (uint64_t)NS) CU(cudaStreamWaitEvent(s_in, ev_free[st], 0));      // the slot's previous chunk has left the device
+    CU(cudaMemcpyAsync(stage_ptr(st, 0), (const char *)probe_keys + row0 * W, rows * W, cudaMemcpyHostToDevice, s_in));
+    CU(cudaMemcpyAsync(stage_ptr(st, 1), (const char *)probe_vals + row0 * W, rows * W, cudaMemcpyHostToDevice, s_in));
+    CU(cudaEventRecord(ev_in[st], s_in));
+    CU(cudaStreamWaitEvent(s_comp, ev_in[st], 0));
     int rc;
     if (out_mode == DWJ_OUT_ALIGNED) {
-      rc = dwj_probe_aligned(e, stage_ptr(st, 0), stage_ptr(st, 1), rows, stage_ptr(st, 2), stage_ptr(st, 3), stage_ptr(st, 4), s);
+      rc = dwj_probe_aligned(e, stage_ptr(st, 0), stage_ptr(st, 1), rows, stage_ptr(st, 2), stage_ptr(st, 3), stage_ptr(st, 4), s_comp);
       if (rc) return rc;
-      CU(cudaMemcpyAsync((char *)out_key + row0 * W, stage_ptr(st, 2), rows * W, cudaMemcpyDeviceToHost, s));
-      CU(cudaMemcpyAsync((char *)out_build_val + row0 * W, stage_ptr(st, 3), rows * W, cudaMemcpyDeviceToHost, s));
-      CU(cudaMemcpyAsync((char *)out_probe_val + row0 * W, stage_ptr(st, 4), rows * W, cudaMemcpyDeviceToHost, s));
+      CU(cudaEventRecord(ev_done[st], s_comp));
+      CU(cudaStreamWaitEvent(s_out, ev_done[st], 0));
+      CU(cudaMemcpyAsync((char *)out_key + row0 * W, stage_ptr(st, 2), rows * W, cudaMemcpyDeviceToHost, s_out));
+      CU(cudaMemcpyAsync((char *)out_build_val + row0 * W, stage_ptr(st, 3), rows * W, cudaMemcpyDeviceToHost, s_out));
+      CU(cudaMemcpyAsync((char *)out_probe_val + row0 * W, stage_ptr(st, 4), rows * W, cudaMemcpyDeviceToHost, s_out));
+      CU(cudaEventRecord(ev_free[st], s_out));
       continue;
     }
     if (out_mode == DWJ_OUT_PAIRS)
       rc = dwj_probe_pairs(e, stage_ptr(st, 0), stage_ptr(st, 1), rows, out_key ? stage_ptr(st, 2) : nullptr, stage_ptr(st, 3),
-                           stage_ptr(st, 4), chunk_rows, (uint64_t *)(d_cnt + st * 8), nullptr, s);
+                           stage_ptr(st, 4), chunk_rows, (uint64_t *)(d_cnt + st * 8), nullptr, s_comp);
     else
-      rc = dwj_probe_count(e, stage_ptr(st, 0), rows, (uint64_t *)(d_cnt + st * 8), nullptr, s);
+      rc = dwj_probe_count(e, stage_ptr(st, 0), rows, (uint64_t *)(d_cnt + st * 8), nullptr, s_comp);
     if (rc) return rc;
-    pend[st].active = true;
-    pend[st].rows = rows;
-    if (int rc2 = drain(1 - st)) return rc2;    // chunk c-1: overlaps with chunk c's H2D + probe
+    CU(cudaMemcpyAsync(e->h_counts + st, d_cnt + st * 8, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s_comp));
+    CU(cudaEventRecord(ev_done[st], s_comp));
+    if (c >= (uint64_t)LAG)
+      if (int rc2 = drain(c - LAG)) return rc2;         // two chunks stay queued behind the one the host waits for
   }
-  if (int rc = drain((int)(n_chunks & 1))) return rc;          // the older of the two outstanding chunks first
-  if (int rc = drain((int)((n_chunks + 1) & 1))) return rc;
-  CU(cudaStreamSynchronize(e->hs[0]));
-  CU(cudaStreamSynchronize(e->hs[1]));
-  CU(cudaEventRecord(e->hev[3], s0));
-  CU(cudaEventSynchronize(e->hev[3]));
+  if (out_mode != DWJ_OUT_ALIGNED)
+    for (uint64_t c = n_chunks > (uint64_t)LAG ? n_chunks - LAG : 0; c < n_chunks; ++c)
+      if (int rc = drain(c)) return rc;
+  CU(cudaStreamSynchronize(s_comp));
+  CU(cudaStreamSynchronize(s_out));
+  CU(cudaEventRecord(e->htime[3], s_out));
+  CU(cudaEventSynchronize(e->htime[3]));
 
   dwj_timing t{};
-  CU(cudaEventElapsedTime(&t.h2d_ms, e->hev[0], e->hev[1]));
-  CU(cudaEventElapsedTime(&t.build_ms, e->hev[1], e->hev[2]));
-  CU(cudaEventElapsedTime(&t.total_ms, e->hev[0], e->hev[3]));
+  CU(cudaEventElapsedTime(&t.h2d_ms, e->htime[0], e->htime[1]));
+  CU(cudaEventElapsedTime(&t.build_ms, e->htime[1], e->htime[2]));
+  CU(cudaEventElapsedTime(&t.total_ms, e->htime[0], e->htime[3]));
   t.probe_ms = std::max(0.f, t.total_ms - t.h2d_ms - t.build_ms);   // the streamed probe phase, copies overlapped
   e->last_host = t;
   if (timing) *timing = t;

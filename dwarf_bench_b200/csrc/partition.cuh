@@ -36,6 +36,11 @@ template <int W> struct PartitionArgs {
   uint64_t bucket_mask;
   K *out_keys;
   K *out_vals;         // may be null
+  // Per-partition destinations (<= 8 partitions, dwj_partition_scatter_to): partition p is written to
+  // dst_keys[p] / dst_vals[p] -- which may be PEER GPU memory mapped over NVLink -- instead of out_keys/out_vals.
+  uint32_t use_dst;
+  K *dst_keys[8];
+  K *dst_vals[8];
   unsigned long long *hist;     // [PART_MAX] zeroed before the histogram kernel
   unsigned long long *cursor;   // [PART_MAX] running write positions
   unsigned long long *offsets;  // [parts + 1] result
@@ -253,7 +258,8 @@ __global__ void __launch_bounds__(PART_THREADS) partition_hist8_kernel(Partition
 // before they reach HBM.
 template <int W, bool BY_BUCKET, int ITEMS, bool FULL, bool WITH_VALS>
 DWJ_D void scatter8_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t rows, unsigned int (*s_wcnt)[8],
-                         unsigned long long (*s_wbase)[8]) {
+                         unsigned long long (*s_wbase)[8], typename KeyT<W>::type *const *s_dstk,
+                         typename KeyT<W>::type *const *s_dstv) {
   using K = typename KeyT<W>::type;
   constexpr int WARPS = PART_THREADS / 32;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -297,9 +303,10 @@ DWJ_D void scatter8_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t rows
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     if (FULL || pr[j] != 8u) {
-      const unsigned long long dst = s_wbase[warp][pr[j] & 15u] + (pr[j] >> 4);
-      store_stream(a.out_keys + dst, k[j]);
-      if constexpr (WITH_VALS) store_stream(a.out_vals + dst, v[j]);
+      const uint32_t p = pr[j] & 15u;
+      const unsigned long long dst = s_wbase[warp][p] + (pr[j] >> 4);
+      store_stream(s_dstk[p] + dst, k[j]);
+      if constexpr (WITH_VALS) store_stream(s_dstv[p] + dst, v[j]);
     }
   }
 }
@@ -307,19 +314,27 @@ DWJ_D void scatter8_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t rows
 template <int W, bool BY_BUCKET, int ITEMS>
 __global__ void __launch_bounds__(PART_THREADS, 3) partition_scatter8_kernel(PartitionArgs<W> a) {
   constexpr uint32_t TILE = PART_THREADS * ITEMS;
+  using K = typename KeyT<W>::type;
   __shared__ unsigned int s_wcnt[PART_THREADS / 32][8];
   __shared__ unsigned long long s_wbase[PART_THREADS / 32][8];
+  __shared__ K *s_dstk[8];
+  __shared__ K *s_dstv[8];
+  if (threadIdx.x < 8) {
+    s_dstk[threadIdx.x] = a.use_dst ? a.dst_keys[threadIdx.x] : a.out_keys;
+    s_dstv[threadIdx.x] = a.use_dst ? a.dst_vals[threadIdx.x] : a.out_vals;
+  }
+  __syncthreads();
   const bool with_vals = a.vals != nullptr;
   const uint64_t num_tiles = (a.n + TILE - 1) / TILE;
   for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const uint64_t base = tile * TILE;
     const uint32_t rows = (uint32_t)min((uint64_t)TILE, a.n - base);
     if (rows == TILE) {
-      if (with_vals) scatter8_tile<W, BY_BUCKET, ITEMS, true, true>(a, base, rows, s_wcnt, s_wbase);
-      else scatter8_tile<W, BY_BUCKET, ITEMS, true, false>(a, base, rows, s_wcnt, s_wbase);
+      if (with_vals) scatter8_tile<W, BY_BUCKET, ITEMS, true, true>(a, base, rows, s_wcnt, s_wbase, s_dstk, s_dstv);
+      else scatter8_tile<W, BY_BUCKET, ITEMS, true, false>(a, base, rows, s_wcnt, s_wbase, s_dstk, s_dstv);
     } else {
-      if (with_vals) scatter8_tile<W, BY_BUCKET, ITEMS, false, true>(a, base, rows, s_wcnt, s_wbase);
-      else scatter8_tile<W, BY_BUCKET, ITEMS, false, false>(a, base, rows, s_wcnt, s_wbase);
+      if (with_vals) scatter8_tile<W, BY_BUCKET, ITEMS, false, true>(a, base, rows, s_wcnt, s_wbase, s_dstk, s_dstv);
+      else scatter8_tile<W, BY_BUCKET, ITEMS, false, false>(a, base, rows, s_wcnt, s_wbase, s_dstk, s_dstv);
     }
     __syncthreads();                               // s_wcnt / s_wbase are reused by the next tile
   }

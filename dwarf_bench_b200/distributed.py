@@ -1,4 +1,13 @@
-"""Multi-GPU join: radix partition on the key hash -> all-to-all-v over NCCL/NVLink -> local build + probe.
+"""Multi-GPU join: radix partition on the key hash -> exchange over NVLink -> local build + probe.
+
+Two exchange implementations:
+  P2PExchangeJoin  the partition kernel stores every row straight into the destination rank's receive buffer
+                   (peer memory mapped through torch symmetric memory): partition and transfer are ONE kernel, there
+                   is no intermediate partitioned copy and no collective on the data path -- only a tiny all-gather of
+                   the per-destination counts to plan the layout, and a symmetric-memory barrier before the local join.
+  ExchangeJoin     partition locally, then NCCL all-to-all-v (the baseline, and the fallback when peer mapping is
+                   unavailable).
+
 
 No reference counterpart (the reference is single-device).  One process per GPU; the
 plumbing is torch.distributed.  Every rank holds an arbitrary (arrival-order) slice of both relations; equal
@@ -115,4 +124,67 @@ class ExchangeJoin:
         self.ops.build(rbk, rbv, nb)
         rpk, rpv, np_ = self.exchange_rows("p", ppk, ppv, ps, pr)
         self.ops.probe_pairs(rpk, rpv, np_, out_key, out_build, out_probe, capacity, d_count)
+        return nb, np_
+
+
+def plan_exchange(counts, rank: int):
+    """counts[src][dst] = rows src sends to dst.  Receive layout on every rank: source-major (rows of rank 0, then
+    rank 1, ...).  Returns (row offset of THIS rank's rows inside each destination's receive buffer, rows this rank
+    receives)."""
+    world = len(counts)
+    offsets = [sum(int(counts[s][d]) for s in range(rank)) for d in range(world)]
+    n_recv = sum(int(counts[s][rank]) for s in range(world))
+    return offsets, n_recv
+
+
+class P2PExchangeJoin:
+    """Fused partition + exchange over peer memory (dwj_partition_scatter_to), then the local join."""
+
+    def __init__(self, engine, device, dtype, cap_build: int, cap_probe: int, group=None, stream=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.e = engine
+        self.device = device
+        self.dtype = dtype
+        self.group = group or dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world not in (1, 2, 4, 8):
+            raise ValueError(f"P2P exchange supports 1, 2, 4 or 8 ranks, got {self.world}")
+        self.stream = stream
+        self.cap_build, self.cap_probe = int(cap_build), int(cap_probe)
+        item = torch.empty(0, dtype=dtype).element_size()
+        # one symmetric buffer per rank: [build keys | build payloads | probe keys | probe payloads]
+        self.buf = symm_mem.empty(2 * (self.cap_build + self.cap_probe), dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        bases = [int(p) for p in self.hdl.buffer_ptrs]
+        off = [0, self.cap_build, 2 * self.cap_build, 2 * self.cap_build + self.cap_probe]
+        self.dst = [[b + o * item for b in bases] for o in off]          # [column][rank] -> device pointer
+        self.cols = [self.buf[o:o + n] for o, n in zip(off, (self.cap_build, self.cap_build, self.cap_probe, self.cap_probe))]
+        self.counts = torch.zeros(2, self.world, dtype=torch.int64, device=device)
+        self.all_counts = torch.zeros(self.world, 2, self.world, dtype=torch.int64, device=device)
+        self.stats = ExchangeStats()
+
+    def join(self, build_keys, build_vals, n_build, probe_keys, probe_vals, n_probe, out_key, out_build, out_probe,
+             capacity, d_count):
+        e, w = self.e, self.world
+        e.partition_hist(build_keys, n_build, w, self.counts[0], stream=self.stream)
+        e.partition_hist(probe_keys, n_probe, w, self.counts[1], stream=self.stream)
+        # The all-gather is also the point after which every rank has finished its previous local join (it is ordered
+        # behind that join on every rank's stream), so the receive buffers may be overwritten.
+        dist.all_gather_into_tensor(self.all_counts.view(-1), self.counts.view(-1), group=self.group)
+        m = self.all_counts.cpu().tolist()                              # the one host sync of the step
+        boff, nb = plan_exchange([[m[s][0][d] for d in range(w)] for s in range(w)], self.rank)
+        poff, np_ = plan_exchange([[m[s][1][d] for d in range(w)] for s in range(w)], self.rank)
+        if nb > self.cap_build or np_ > self.cap_probe:
+            raise RuntimeError(f"receive buffers too small: {nb}/{self.cap_build} build rows, {np_}/{self.cap_probe} probe rows")
+        e.partition_scatter_to(build_keys, build_vals, n_build, w, self.dst[0], self.dst[1], boff, stream=self.stream)
+        e.partition_scatter_to(probe_keys, probe_vals, n_probe, w, self.dst[2], self.dst[3], poff, stream=self.stream)
+        self.hdl.barrier(channel=0)                                     # every peer's stores have landed
+        e.build(self.cols[0], self.cols[1], nb, stream=self.stream)
+        e.probe_pairs(self.cols[2], self.cols[3], np_, out_key, out_build, out_probe, capacity, d_n_matches=d_count, sync=False,
+                      stream=self.stream)
+        item = self.buf.element_size()
+        self.stats.sent_rows += n_build + n_probe
+        self.stats.recv_rows += nb + np_
+        self.stats.sent_bytes_remote += 2 * item * (n_build + n_probe - m[self.rank][0][self.rank] - m[self.rank][1][self.rank])
         return nb, np_

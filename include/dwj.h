@@ -94,6 +94,9 @@ typedef struct {
   float h2d_ms;       /* dwj_join_host only: host->device copies                           */
   float d2h_ms;       /* dwj_join_host only: device->host copies                           */
   float total_ms;     /* dwj_join_host: first copy to last copy; else build_ms + probe_ms  */
+  float probe_kernel_ms; /* the probe kernel proper of the last dwj_probe_* (probe_ms also
+                            covers the region partition of the probe relation and memsets)  */
+  float build_kernel_ms; /* the insert kernel proper of the last dwj_build                  */
 } dwj_timing;
 
 typedef struct {
@@ -175,6 +178,20 @@ DWJ_API int dwj_join_host(dwj_engine *e, const void *build_keys, const void *bui
 DWJ_API int dwj_partition(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows,
                   uint32_t n_parts, void *d_out_keys, void *d_out_vals, uint64_t *d_offsets,
                   void *stream);
+
+/* Exchange planning: d_counts[p] (uint64, device) = rows of partition p, same partition function as dwj_partition.
+ * Asynchronous. */
+DWJ_API int dwj_partition_hist(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t n_parts, uint64_t *d_counts,
+                       void *stream);
+
+/* Fused partition + exchange: rows of partition p are stored straight to dst_keys[p] / dst_vals[p] starting at row
+ * dst_row_offsets[p] (host array).  The destinations may be PEER GPU memory mapped into this process (NVLink P2P,
+ * e.g. torch symmetric memory): the scatter kernel's stores are the transfer, no intermediate copy and no
+ * collective call.  1, 2, 4 or 8 partitions.  The caller plans the layout (dwj_partition_hist + an all-gather of the
+ * counts) and synchronises the ranks afterwards.  dst_vals/d_vals may both be NULL.  Asynchronous. */
+DWJ_API int dwj_partition_scatter_to(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_parts,
+                             void *const *dst_keys, void *const *dst_vals, const uint64_t *dst_row_offsets,
+                             void *stream);
 
 /* Partition id of one key on the host (same function the kernels use) -- lets callers and tests
  * reason about placement without a device. */

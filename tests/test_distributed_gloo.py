@@ -105,3 +105,19 @@ def test_exchange_join_world2(tmp_path, oracle, world):
     from dwarf_bench_b200 import capi
     for r, p in enumerate(parts):
         assert all(capi.partition_of(int(k), 4, world, 42) == r for k in p["k"][:200])
+
+
+def test_plan_exchange_layout():
+    """Host logic of the fused P2P exchange: source-major receive layout, no overlaps, nothing lost."""
+    from dwarf_bench_b200.distributed import plan_exchange
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 4, 8):
+        counts = rng.integers(0, 1000, (world, world)).tolist()
+        plans = [plan_exchange(counts, r) for r in range(world)]
+        for d in range(world):
+            # the ranges [offset_s, offset_s + counts[s][d]) written by every source s tile the receive buffer of d exactly
+            spans = sorted((plans[s][0][d], plans[s][0][d] + counts[s][d]) for s in range(world))
+            assert spans[0][0] == 0
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0
+            assert spans[-1][1] == plans[d][1] == sum(counts[s][d] for s in range(world))

@@ -410,3 +410,40 @@ def test_region_partitioned_path_small(dwj, oracle, monkeypatch, wide, unique):
     assert m == cnt == len(want[0])
     for w, x in zip(want, got):
         np.testing.assert_array_equal(w, x)
+
+
+@pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("parts", [2, 8])
+def test_partition_scatter_to_destinations(dwj, wide, parts):
+    """The fused partition+exchange entry point with LOCAL destinations standing in for peer buffers: every partition
+    lands in its own buffer at the planned row offset; counts from dwj_partition_hist match."""
+    from dwarf_bench_b200 import capi
+    rng = np.random.default_rng(parts + wide)
+    dt = np.uint64 if wide else np.uint32
+    n = 700_001
+    k = rng.integers(0, 2**31, n).astype(dt)
+    v = np.arange(n, dtype=dt)
+    with dwj.Engine(16, key_bytes=dt().itemsize, hash_seed=42) as e:
+        counts = torch.zeros(parts, dtype=torch.int64, device="cuda")
+        dk, dv = dev(k), dev(v)
+        e.partition_hist(dk, n, parts, counts)
+        c = counts.cpu().numpy()
+        pid = np.array([capi.partition_of(int(x), dt().itemsize, parts, 42) for x in k[:5000]])
+        assert c.sum() == n and (np.diff(np.sort(c)) >= 0).all()
+        start = [17 * (p + 1) for p in range(parts)]                    # planned offsets inside each destination
+        bufk = [empty_like_dev(int(c[p]) + start[p] + 5, dt) for p in range(parts)]
+        bufv = [empty_like_dev(int(c[p]) + start[p] + 5, dt) for p in range(parts)]
+        for b in bufk + bufv:
+            b.fill_(-1)
+        e.partition_scatter_to(dk, dv, n, parts, [b.data_ptr() for b in bufk], [b.data_ptr() for b in bufv], start)
+        torch.cuda.synchronize()
+        seen = []
+        for p in range(parts):
+            kk, vv = host(bufk[p], dt), host(bufv[p], dt)
+            assert (kk[:start[p]] == dt(~dt(0))).all() and (kk[start[p] + c[p]:] == dt(~dt(0))).all()   # nothing outside the plan
+            rows = vv[start[p]:start[p] + c[p]].astype(np.int64)
+            np.testing.assert_array_equal(k[rows], kk[start[p]:start[p] + c[p]])
+            assert all(capi.partition_of(int(x), dt().itemsize, parts, 42) == p for x in kk[start[p]:start[p] + 300])
+            seen.append(rows)
+        np.testing.assert_array_equal(np.sort(np.concatenate(seen)), np.arange(n))
+        assert np.bincount(pid, minlength=parts).sum() == 5000
