@@ -298,22 +298,26 @@ int simple_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
   return DWJ_OK;
 }
 
-// PAIRS with non-unique build keys: one look-back descriptor per CTA tile, rows written from registers.
-template <int W>
+// PAIRS with non-unique build keys: one look-back descriptor (or one atomic) per CTA tile, rows written from registers.
+template <int W, bool ORDERED>
 int multi_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
-  constexpr int THREADS = 256, ITEMS = 4, MINB = 4;
+  constexpr int THREADS = 256, ITEMS = W == 4 ? 4 : 2, MINB = 4;
   constexpr uint64_t TILE = (uint64_t)THREADS * ITEMS;
   const uint64_t tiles = (a.n + TILE - 1) / TILE;
   a.num_tiles = tiles;
-  int rc = ensure_tile_state(e, tiles, s);
-  if (rc) return rc;
-  a.tile_state = e->tile_state;
-  CU(cudaMemsetAsync(e->tile_state, 0, (tiles + 1) * sizeof(unsigned long long), s));
+  e->launches_probe = 0;
+  if (ORDERED) {
+    int rc = ensure_tile_state(e, tiles, s);
+    if (rc) return rc;
+    a.tile_state = e->tile_state;
+    CU(cudaMemsetAsync(e->tile_state, 0, (tiles + 1) * sizeof(unsigned long long), s));
+    e->launches_probe++;
+  }
   CU(cudaMemsetAsync(a.n_matches, 0, sizeof(unsigned long long), s));
-  e->launches_probe = 2;
+  e->launches_probe++;
   if (tiles) {
     if (tiles > 0x7fffffffull) return fail(DWJ_ERR_INVALID, "probe of %llu rows needs more than 2^31 tiles", (unsigned long long)a.n);
-    CU(launch(e, dwj::probe_pairs_multi_kernel<W, THREADS, ITEMS, MINB>, dim3((unsigned)tiles), dim3(THREADS), s, a, true));
+    CU(launch(e, dwj::probe_pairs_multi_kernel<W, ORDERED, THREADS, ITEMS, MINB>, dim3((unsigned)tiles), dim3(THREADS), s, a, true));
     e->launches_probe++;
   }
   return DWJ_OK;
@@ -418,7 +422,7 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
       if (ordered) rc = ok ? staged_launch<W, true, true>(e, a, s) : staged_launch<W, true, false>(e, a, s);
       else rc = ok ? staged_launch<W, false, true>(e, a, s) : staged_launch<W, false, false>(e, a, s);
     } else {
-      rc = multi_launch<W>(e, a, s);
+      rc = (e->cfg.flags & DWJ_FLAG_UNORDERED_OUTPUT) ? multi_launch<W, false>(e, a, s) : multi_launch<W, true>(e, a, s);
     }
   }
   if (rc) return rc;

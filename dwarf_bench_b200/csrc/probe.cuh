@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) probe_simple_kernel(ProbeArgs<W> a) {
 // ---- CTA-tile PAIRS kernel for NON-unique build keys (every equal build row is emitted) -----------------
 // One look-back descriptor per tile; rows are written straight from registers (a probe row may have any
 // number of matches, so they cannot be staged in a fixed amount of shared memory).
-template <int W, int THREADS, int ITEMS, int MINB>
+template <int W, bool ORDERED, int THREADS, int ITEMS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeArgs<W> a) {
   using K = typename KeyT<W>::type;
   constexpr int TILE = THREADS * ITEMS;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeA
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_warp_sums[ITEMS][WARPS];
   const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  if (t == 0) s_tile = atomicAdd(a.tile_state, 1ull);     // scheduling order: look-back needs predecessors running
+  if (t == 0) s_tile = ORDERED ? atomicAdd(a.tile_state, 1ull) : (unsigned long long)blockIdx.x;   // ticket: look-back needs predecessors running
   __syncthreads();
   const uint64_t tile = s_tile;
   const uint64_t base = tile * TILE;
@@ -267,11 +267,14 @@ __global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeA
     }
   }
   if (warp == 0) {
-    const unsigned long long excl = lookback_exclusive_prefix(a.tile_state + 1, tile, tile_total);
-    if (lane == 0) {
-      s_base = excl;
-      if (tile == a.num_tiles - 1) *a.n_matches = excl + tile_total;
+    unsigned long long excl = 0;
+    if constexpr (ORDERED) {
+      excl = lookback_exclusive_prefix(a.tile_state + 1, tile, tile_total);
+      if (lane == 0 && tile == a.num_tiles - 1) *a.n_matches = excl + tile_total;
+    } else {
+      if (lane == 0 && tile_total) excl = atomicAdd(a.n_matches, (unsigned long long)tile_total);
     }
+    if (lane == 0) s_base = excl;
   }
   __syncthreads();
   const unsigned long long out_base = s_base;
@@ -333,7 +336,7 @@ DWJ_D void staged_round(const ProbeArgs<W> &a, uint64_t base, unsigned lane, uns
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     hb[j] = slot_hash(key[j], a.seed) & a.bucket_mask;
-    bk[j] = load_bucket_ro<W>(a.table, hb[j]);
+    bk[j] = load_bucket_stream<W>(a.table, hb[j]);
   }
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {

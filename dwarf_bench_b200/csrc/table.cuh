@@ -98,12 +98,14 @@ template <> struct Bucket<8> {
 // One 32-byte sector in ONE instruction (LDG.E.256, sm_100+): measured on B200, a random-sector gather
 // costs one L1TEX wavefront per instruction, so two 128-bit loads would halve the probe rate
 // (tools/gather_bench.cu: 285 vs 143 G gathers/s on an L2-resident table).  Read-only path for the probe
-// (the table is immutable while a probe kernel runs); L1 is bypassed -- a random sector is never re-used
-// by the same SM.
+// (the table is immutable while a probe kernel runs).  The line is allowed into L1: for uniform keys that
+// neither helps nor hurts (same gather rate with and without L1::no_allocate), but with skewed probe keys
+// (Zipf 1.0: 6 % of all rows ask for the same sector) every SM then serves the hot buckets from its own L1
+// instead of all 148 SMs queueing on one L2 slice -- bypassing L1 made that workload 4x slower.
 DWJ_D Bucket<4> load_bucket_ro(const void *table, uint64_t b, Bucket<4> *) {
   Bucket<4> r;
   const char *p = (const char *)table + (b << 5);
-  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r.f[0]), "=r"(r.f[1]), "=r"(r.f[2]), "=r"(r.f[3]), "=r"(r.f[4]), "=r"(r.f[5]), "=r"(r.f[6]), "=r"(r.f[7])
                : "l"(p));
   return r;
@@ -111,13 +113,35 @@ DWJ_D Bucket<4> load_bucket_ro(const void *table, uint64_t b, Bucket<4> *) {
 DWJ_D Bucket<8> load_bucket_ro(const void *table, uint64_t b, Bucket<8> *) {
   Bucket<8> r;
   const char *p = (const char *)table + (b << 5);
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
                : "=l"(r.f[0]), "=l"(r.f[1]), "=l"(r.f[2]), "=l"(r.f[3])
                : "l"(p));
   return r;
 }
 template <int W> DWJ_D Bucket<W> load_bucket_ro(const void *table, uint64_t b) {
   return load_bucket_ro(table, b, (Bucket<W> *)nullptr);
+}
+// L1-bypassing variant for the staged PAIRS kernel (unique build keys): that kernel keeps 32-48 KB of staging per
+// CTA in shared memory and measured 20-60 % slower when the table sectors also competed for the L1 carve-out.
+// It is therefore the one probe kernel that is not protected against hot probe keys (open items).
+DWJ_D Bucket<4> load_bucket_stream(const void *table, uint64_t b, Bucket<4> *) {
+  Bucket<4> r;
+  const char *p = (const char *)table + (b << 5);
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.f[0]), "=r"(r.f[1]), "=r"(r.f[2]), "=r"(r.f[3]), "=r"(r.f[4]), "=r"(r.f[5]), "=r"(r.f[6]), "=r"(r.f[7])
+               : "l"(p));
+  return r;
+}
+DWJ_D Bucket<8> load_bucket_stream(const void *table, uint64_t b, Bucket<8> *) {
+  Bucket<8> r;
+  const char *p = (const char *)table + (b << 5);
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(r.f[0]), "=l"(r.f[1]), "=l"(r.f[2]), "=l"(r.f[3])
+               : "l"(p));
+  return r;
+}
+template <int W> DWJ_D Bucket<W> load_bucket_stream(const void *table, uint64_t b) {
+  return load_bucket_stream(table, b, (Bucket<W> *)nullptr);
 }
 // Coherent variant for the build kernel (other CTAs are inserting concurrently): L2 is the point of
 // coherence, so skip L1 (.cg).  A stale view can only show a slot as still empty, and the CAS that

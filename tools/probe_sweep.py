@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--load-factor", type=float, default=0.5)
     ap.add_argument("--flags", type=int, default=dwj.FLAG_UNIQUE_BUILD_KEYS)
     ap.add_argument("--unordered", action="store_true")
+    ap.add_argument("--dup", type=int, default=0, help="dup_zipf workload with this many duplicates per build key")
     args = ap.parse_args()
     S = args.probe_rows
     if args.unordered:
@@ -44,9 +45,10 @@ def main():
     print(f"{'build':>10} {'table MB':>9} | {'build ms':>9} {'Gins/s':>7} | {'count':>8} {'contains':>8} {'aligned':>8} {'pairs':>8} {'pairs+key':>9}  (ms; G probes/s in brackets)")
     for lg in args.build_log2:
         R = 1 << lg
-        inp = workloads.fk_pk(R, S, args.key_bytes, keep_map=False)
+        inp = workloads.dup_zipf(R, S, dup=args.dup, key_bytes=args.key_bytes) if args.dup else workloads.fk_pk(R, S, args.key_bytes, keep_map=False)
+        M = inp.expected_matches
         e = dwj.Engine(R, key_bytes=args.key_bytes, load_factor=args.load_factor, flags=args.flags)
-        ok, ob, op = (torch.empty(S, dtype=tdt, device="cuda") for _ in range(3))
+        ok, ob, op = (torch.empty(M, dtype=tdt, device="cuda") for _ in range(3))
         fl = torch.empty(S, dtype=torch.int32, device="cuda")
         cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
         tb = timed(lambda: e.build(inp.build_keys, inp.build_vals, R))
@@ -54,8 +56,8 @@ def main():
             timed(lambda: e.probe_count(inp.probe_keys, S, d_n_matches=cnt, sync=False)),
             timed(lambda: e.probe_contains(inp.probe_keys, S, fl)),
             timed(lambda: e.probe_aligned(inp.probe_keys, inp.probe_vals, S, ok, ob, op)),
-            timed(lambda: e.probe_pairs(inp.probe_keys, inp.probe_vals, S, None, ob, op, S, d_n_matches=cnt, sync=False)),
-            timed(lambda: e.probe_pairs(inp.probe_keys, inp.probe_vals, S, ok, ob, op, S, d_n_matches=cnt, sync=False)),
+            timed(lambda: e.probe_pairs(inp.probe_keys, inp.probe_vals, S, None, ob, op, M, d_n_matches=cnt, sync=False)),
+            timed(lambda: e.probe_pairs(inp.probe_keys, inp.probe_vals, S, ok, ob, op, M, d_n_matches=cnt, sync=False)),
         ]
         mb = e.info()["table_bytes"] / 2**20
         print(f"parts {e.info()['radix_parts']:>4}", end=" ")
