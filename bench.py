@@ -382,7 +382,7 @@ def main():
                    "key_bytes": key_bytes, "payload_bytes": key_bytes, "unique_build_keys": inp.unique_build,
                    "output": "compacted (build payload, probe payload" + (", key)" if args.emit_key else ")"),
                    "table_slots": info["slots"], "table_bytes": info["table_bytes"], "load_factor": args.load_factor,
-                   "l2_persist_window": bool(info["l2_persist"]), "table_regions": info["radix_parts"],
+                   "l2_persist_window": bool(info["l2_persist"]), "table_regions": info["radix_parts"], "probe_passes": info["probe_passes"],
                    "output_order": "probe-row order" if info["radix_parts"] == 1 and not args.unordered else "region-major / unordered",
                    "l2_between_iterations": "inputs and outputs (%.1f GB per step) far exceed the 126 MB L2; no explicit flush"
                                             % (((n_build + n_probe) * 2 + matches * 2) * key_bytes / 1e9),
@@ -407,7 +407,12 @@ def main():
         kname = "probe_pairs_staged_kernel" if inp.unique_build else "probe_pairs_multi_kernel"
         slot = 2 * key_bytes
         out_row = (2 + (1 if args.emit_key else 0)) * key_bytes
-        if info["radix_parts"] > 1:
+        if info["probe_passes"] > 1 and inp.unique_build:
+            # Multi-pass region probe: the kernel sweeps the probe KEYS once per table slice, reads each payload once,
+            # writes the result rows and pulls every slice through L2 once -- all of it inside this one launch.
+            kernel_bytes = n_probe * key_bytes * info["probe_passes"] + n_probe * key_bytes + matches * out_row + info["table_bytes"]
+            kmodel = "passes*S*K + S*P + M*out_row + T*slot (one sweep of the probe keys per L2-resident table slice)"
+        elif info["radix_parts"] > 1:
             # The kernel runs on region-partitioned input: it must read both probe columns, write the result rows and
             # pull every table region through L2 once.  (The partition pass that makes this possible is accounted for
             # in `survey_model.probe_phase`.)

@@ -47,7 +47,7 @@ class Info(C.Structure):
     _fields_ = [("slots", C.c_uint64), ("table_bytes", C.c_uint64), ("build_rows", C.c_uint64), ("slot_bytes", C.c_uint32),
                 ("slots_per_bucket", C.c_uint32), ("l2_persist", C.c_uint32), ("sm_count", C.c_uint32),
                 ("l2_bytes", C.c_uint64), ("launches_build", C.c_uint32), ("launches_probe", C.c_uint32),
-                ("radix_parts", C.c_uint32), ("reserved", C.c_uint32)]
+                ("radix_parts", C.c_uint32), ("probe_passes", C.c_uint32)]
 
 
 @dataclass

@@ -113,7 +113,8 @@ typedef struct {
   uint32_t radix_parts;      /* > 1: build and probe rows are first radix-partitioned into
                                 this many table regions (L2 locality); dwj_probe_pairs then
                                 emits rows region by region instead of in probe-row order   */
-  uint32_t reserved;
+  uint32_t probe_passes;     /* > 1: dwj_probe_pairs (unique build keys) sweeps the probe relation
+                                this many times, one table slice per pass, instead of partitioning it */
 } dwj_info;
 
 DWJ_API int dwj_abi_version(void);

@@ -60,7 +60,7 @@ def main():
             timed(lambda: e.probe_pairs(inp.probe_keys, inp.probe_vals, S, ok, ob, op, M, d_n_matches=cnt, sync=False)),
         ]
         mb = e.info()["table_bytes"] / 2**20
-        print(f"parts {e.info()['radix_parts']:>4}", end=" ")
+        print(f"parts {e.info()['radix_parts']:>4} passes {e.info()['probe_passes']:>2}", end=" ")
         print(f"{R:>10} {mb:>9.0f} | {tb:>9.3f} {R / tb / 1e6:>7.2f} | " + " ".join(f"{t:>5.2f}[{S / t / 1e6:>4.0f}]" for t in res), flush=True)
         e.close()
         del inp, ok, ob, op, fl
