@@ -262,14 +262,40 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
     vals = pv;
     e->launches_build += 4;
   }
+  // Opt-in only: measured 3x SLOWER than memset + build_kernel (profiles/r1_probe.md, negative results).
+  static const bool fused_ok = getenv("DWJ_FUSED_BUILD") && atoi(getenv("DWJ_FUSED_BUILD"));
+  if (e->region_bits && n && fused_ok && e->prop.cooperativeLaunch) {
+    // Region-fused build: clear slice, grid-sync, insert the region's rows -- one persistent cooperative kernel.
+    dwj::RegionBuildArgs<W> ra{(const K *)keys, (const K *)vals, e->part_scratch + 2 * dwj::PART_MAX, e->table, e->buckets - 1,
+                               e->cfg.hash_seed, e->table_bytes >> e->region_bits, 1u << e->region_bits};
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwj::build_regions_kernel<W, 4>, 256, 0));
+    if (per_sm < 1) return fail(DWJ_ERR_CUDA, "build_regions_kernel does not fit on an SM");
+    void *kargs[] = {&ra};
+    CU(cudaEventRecord(e->ev_buildk[0], s));
+    CU(cudaLaunchCooperativeKernel((const void *)dwj::build_regions_kernel<W, 4>, dim3((unsigned)(per_sm * e->prop.multiProcessorCount)),
+                                   dim3(256), kargs, 0, s));
+    CU(cudaEventRecord(e->ev_buildk[1], s));
+    e->launches_build++;
+    CU(cudaEventRecord(e->ev_build[1], s));
+    e->have_build = true;
+    e->build_rows = n;
+    e->built = true;
+    return DWJ_OK;
+  }
   CU(cudaMemsetAsync(e->table, 0xFF, e->table_bytes, s));
   e->launches_build++;
   if (n) {
     dwj::BuildArgs<W> a{(const K *)keys, (const K *)vals, n, e->table, e->buckets - 1, e->cfg.hash_seed};
-    constexpr int ROWS = 4;
-    const uint64_t tiles = (n + 256ull * ROWS - 1) / (256ull * ROWS);
+    static const int variant = getenv("DWJ_BUILD_VARIANT") ? atoi(getenv("DWJ_BUILD_VARIANT")) : 0;   // tuning sweeps
+    const int rows = variant == 2 ? 8 : variant == 3 ? 2 : 4;
+    const uint64_t tiles = (n + 256ull * rows - 1) / (256ull * rows);
+    const dim3 grid((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull));
     CU(cudaEventRecord(e->ev_buildk[0], s));
-    CU(launch(e, dwj::build_kernel<W, ROWS>, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(256), s, a, true));
+    if (variant == 1) CU(launch(e, dwj::build_kernel<W, 4, 1>, grid, dim3(256), s, a, true));
+    else if (variant == 2) CU(launch(e, dwj::build_kernel<W, 8, 0>, grid, dim3(256), s, a, true));
+    else if (variant == 3) CU(launch(e, dwj::build_kernel<W, 2, 0>, grid, dim3(256), s, a, true));
+    else CU(launch(e, dwj::build_kernel<W, 4, 0>, grid, dim3(256), s, a, true));
     CU(cudaEventRecord(e->ev_buildk[1], s));
     e->launches_build++;
   }

@@ -53,14 +53,14 @@ template <int W, bool BY_BUCKET> DWJ_D uint32_t part_id(const PartitionArgs<W> &
 
 constexpr uint32_t PART_DEAD = 0xFFFFFFFFu;   // partition id of a lane past the end of the input
 
-// Histogram: HROWS coalesced key loads in flight per thread; the lanes of a warp that share a partition are found
-// with one MATCH.ANY, and one of them adds the group's size to the shared-memory counter.
+// Histogram for more than 8 partitions: HROWS coalesced key loads in flight per thread, one fire-and-forget
+// shared-memory atomic per row.  (With 16+ bins a warp rarely has more than 2-3 lanes on one bin; grouping the
+// lanes with MATCH.ANY first was 8x slower than the packed-counter kernel below, 1.86 ms per 268 M rows.)
 template <int W, bool BY_BUCKET, int HROWS>
 __global__ void __launch_bounds__(PART_THREADS) partition_hist_kernel(PartitionArgs<W> a) {
   using K = typename KeyT<W>::type;
   __shared__ unsigned int s_hist[PART_MAX];
   const uint32_t parts = 1u << a.log2_parts;
-  const unsigned lane = threadIdx.x & 31;
   for (uint32_t p = threadIdx.x; p < parts; p += blockDim.x) s_hist[p] = 0;
   __syncthreads();
   constexpr uint64_t TILE = (uint64_t)PART_THREADS * HROWS;
@@ -76,11 +76,8 @@ __global__ void __launch_bounds__(PART_THREADS) partition_hist_kernel(PartitionA
       k[j] = live[j] ? load_stream(a.keys + i) : (K)0;
     }
 #pragma unroll
-    for (int j = 0; j < HROWS; ++j) {
-      const uint32_t p = live[j] ? part_id<W, BY_BUCKET>(a, k[j]) : PART_DEAD;
-      const unsigned peers = __match_any_sync(0xffffffffu, p);
-      if (live[j] && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&s_hist[p], (unsigned)__popc(peers));
-    }
+    for (int j = 0; j < HROWS; ++j)
+      if (live[j]) atomicAdd(&s_hist[part_id<W, BY_BUCKET>(a, k[j])], 1u);   // > 8 bins: few same-bin lanes per warp
   }
   __syncthreads();
   for (uint32_t p = threadIdx.x; p < parts; p += blockDim.x)
@@ -118,7 +115,6 @@ __global__ void __launch_bounds__(PART_THREADS, 3) partition_scatter_kernel(Part
 
   const uint32_t parts = 1u << a.log2_parts;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt = (1u << lane) - 1u;
   const bool with_vals = a.vals != nullptr;
   const uint64_t num_tiles = (a.n + TILE - 1) / TILE;
   for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -140,11 +136,7 @@ __global__ void __launch_bounds__(PART_THREADS, 3) partition_scatter_kernel(Part
     for (int j = 0; j < ITEMS; ++j) {
       const bool live = j * PART_THREADS + threadIdx.x < rows;
       part[j] = live ? part_id<W, BY_BUCKET>(a, k[j]) : PART_DEAD;
-      const unsigned peers = __match_any_sync(0xffffffffu, part[j]);
-      const int leader = __ffs(peers) - 1;
-      unsigned wbase = 0;
-      if (live && (int)lane == leader) wbase = atomicAdd(&s_count[part[j]], (unsigned)__popc(peers));
-      rank[j] = __shfl_sync(0xffffffffu, wbase, leader) + __popc(peers & lt);
+      rank[j] = live ? atomicAdd(&s_count[part[j]], 1u) : 0u;        // > 8 bins: few same-bin lanes per warp
     }
     __syncthreads();
     // Exclusive scan of s_count[0..parts) by the whole CTA (parts <= 512 = 2 per thread), global reservation.
