@@ -229,10 +229,13 @@ int partition_scatter_to_impl(dwj_engine *e, const void *keys, const void *vals,
   // are staged before the call returns.
   CU(cudaMemcpyAsync(a.cursor, start, sizeof(start), cudaMemcpyHostToDevice, s));
   if (!n) return DWJ_OK;
+  // Staged variant: destinations may sit behind NVLink, which wants 128-byte pieces (partition.cuh).
   constexpr int ITEMS8 = W == 4 ? 16 : 8;
   const uint64_t tiles8 = (n + 256ull * ITEMS8 - 1) / (256ull * ITEMS8);
-  CU(launch(e, dwj::partition_scatter8_kernel<W, false, ITEMS8>, dim3((unsigned)std::min<uint64_t>(tiles8, 0x7fffffffull)),
-            dim3(dwj::PART_THREADS), s, a, false));
+  static const bool direct = getenv("DWJ_SCATTER_TO_DIRECT") && atoi(getenv("DWJ_SCATTER_TO_DIRECT"));   // tuning
+  const dim3 grid((unsigned)std::min<uint64_t>(tiles8, 0x7fffffffull));
+  if (direct) CU(launch(e, dwj::partition_scatter8_kernel<W, false, ITEMS8>, grid, dim3(dwj::PART_THREADS), s, a, false));
+  else CU(launch(e, dwj::partition_scatter8_staged_kernel<W, false, ITEMS8>, grid, dim3(dwj::PART_THREADS), s, a, false));
   return DWJ_OK;
 }
 
