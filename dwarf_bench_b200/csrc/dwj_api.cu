@@ -84,7 +84,6 @@ struct dwj_engine {
   unsigned long long *part_scratch = nullptr;  // hist[PART_MAX] + cursor[PART_MAX] + region offsets[PART_MAX + 1]
   // L2-locality regions: inputs are radix-partitioned on the top `region_bits` bits of the bucket index first
   uint32_t region_bits = 0;
-  uint32_t sweep_bits = 0;      // unique-key PAIRS: probe the relation 2^sweep_bits times, one table slice per pass
   void *region_build = nullptr, *region_probe = nullptr;   // partitioned copies (keys then payloads)
   uint64_t region_build_rows = 0, region_probe_rows = 0;   // capacities in rows
   uint32_t launches_build = 0, launches_probe = 0;
@@ -265,40 +264,14 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
     vals = pv;
     e->launches_build += 4;
   }
-  // Opt-in only: measured 3x SLOWER than memset + build_kernel (profiles/r1_probe.md, negative results).
-  static const bool fused_ok = getenv("DWJ_FUSED_BUILD") && atoi(getenv("DWJ_FUSED_BUILD"));
-  if (e->region_bits && n && fused_ok && e->prop.cooperativeLaunch) {
-    // Region-fused build: clear slice, grid-sync, insert the region's rows -- one persistent cooperative kernel.
-    dwj::RegionBuildArgs<W> ra{(const K *)keys, (const K *)vals, e->part_scratch + 2 * dwj::PART_MAX, e->table, e->buckets - 1,
-                               e->cfg.hash_seed, e->table_bytes >> e->region_bits, 1u << e->region_bits};
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwj::build_regions_kernel<W, 4>, 256, 0));
-    if (per_sm < 1) return fail(DWJ_ERR_CUDA, "build_regions_kernel does not fit on an SM");
-    void *kargs[] = {&ra};
-    CU(cudaEventRecord(e->ev_buildk[0], s));
-    CU(cudaLaunchCooperativeKernel((const void *)dwj::build_regions_kernel<W, 4>, dim3((unsigned)(per_sm * e->prop.multiProcessorCount)),
-                                   dim3(256), kargs, 0, s));
-    CU(cudaEventRecord(e->ev_buildk[1], s));
-    e->launches_build++;
-    CU(cudaEventRecord(e->ev_build[1], s));
-    e->have_build = true;
-    e->build_rows = n;
-    e->built = true;
-    return DWJ_OK;
-  }
   CU(cudaMemsetAsync(e->table, 0xFF, e->table_bytes, s));
   e->launches_build++;
   if (n) {
     dwj::BuildArgs<W> a{(const K *)keys, (const K *)vals, n, e->table, e->buckets - 1, e->cfg.hash_seed};
-    static const int variant = getenv("DWJ_BUILD_VARIANT") ? atoi(getenv("DWJ_BUILD_VARIANT")) : 0;   // tuning sweeps
-    const int rows = variant == 2 ? 8 : variant == 3 ? 2 : 4;
-    const uint64_t tiles = (n + 256ull * rows - 1) / (256ull * rows);
-    const dim3 grid((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull));
+    constexpr int ROWS = 4;
+    const uint64_t tiles = (n + 256ull * ROWS - 1) / (256ull * ROWS);
     CU(cudaEventRecord(e->ev_buildk[0], s));
-    if (variant == 1) CU(launch(e, dwj::build_kernel<W, 4, 1>, grid, dim3(256), s, a, true));
-    else if (variant == 2) CU(launch(e, dwj::build_kernel<W, 8, 0>, grid, dim3(256), s, a, true));
-    else if (variant == 3) CU(launch(e, dwj::build_kernel<W, 2, 0>, grid, dim3(256), s, a, true));
-    else CU(launch(e, dwj::build_kernel<W, 4, 0>, grid, dim3(256), s, a, true));
+    CU(launch(e, dwj::build_kernel<W, ROWS>, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(256), s, a, true));
     CU(cudaEventRecord(e->ev_buildk[1], s));
     e->launches_build++;
   }
@@ -357,8 +330,7 @@ template <int W, bool ORDERED, bool WITH_KEY, int SHAPE>
 int staged_launch_shape(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
   constexpr StagedShape S = W == 4 ? STAGED_SHAPES_4[SHAPE] : STAGED_SHAPES_8[SHAPE];
   constexpr uint64_t CHUNK = (uint64_t)S.warps * 32 * S.items * S.sub;
-  a.chunks_per_pass = (a.n + CHUNK - 1) / CHUNK;
-  const uint64_t chunks = a.chunks_per_pass * std::max<uint32_t>(a.regions, 1);   // pass-major chunk ids
+  const uint64_t chunks = (a.n + CHUNK - 1) / CHUNK;
   a.num_tiles = chunks;
   e->launches_probe = 0;
   if (ORDERED) {
@@ -427,16 +399,7 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
   CU(cudaEventRecord(e->ev_probe[0], s));
   int rc;
   uint32_t extra_launches = 0;
-  a.regions = 1;
-  const bool sweep = e->sweep_bits && n && mode == dwj::PROBE_PAIRS && unique;
-  if (sweep) {
-    // Few regions: instead of materialising a partitioned copy of the probe relation, sweep it once per region and
-    // let every pass handle only its own slice of the table (rows of other regions are skipped after the hash).
-    uint32_t lgb = 0;
-    while ((1ull << lgb) < e->buckets) ++lgb;
-    a.regions = 1u << e->sweep_bits;
-    a.region_shift = lgb - e->sweep_bits;
-  } else if (e->region_bits && n && (mode == dwj::PROBE_PAIRS || mode == dwj::PROBE_COUNT)) {
+  if (e->region_bits && n && (mode == dwj::PROBE_PAIRS || mode == dwj::PROBE_COUNT)) {
     // Same grouping for the probe relation: its rows then walk the table slice by slice (output order becomes
     // region-major; the row multiset is unchanged).
     if ((rc = ensure_region_buffer(&e->region_probe, &e->region_probe_rows, n, W, s))) return rc;
@@ -540,14 +503,6 @@ int dwj_create(const dwj_config *cfg, dwj_engine **out) {
       uint32_t max_bits = 0;
       while ((1u << (max_bits + 1)) <= (uint32_t)dwj::PART_MAX) ++max_bits;
       e->region_bits = std::min(std::min(bits, max_bits), lgb);
-      // Up to DWJ_SWEEP_MAX (default 4) slices of <= 64 MB: multi-pass probe instead of a partitioned copy.
-      double sweep_mb = 64.0;
-      int sweep_max = 1;     // measured slower than the partitioned copy (profiles/r1_probe.md): off unless DWJ_SWEEP_MAX > 1
-      if (const char *v = getenv("DWJ_SWEEP_MB")) sweep_mb = atof(v);
-      if (const char *v = getenv("DWJ_SWEEP_MAX")) sweep_max = atoi(v);
-      uint32_t sbits = 0;
-      while ((double)(e->table_bytes >> sbits) > sweep_mb * 1048576.0) ++sbits;
-      if (sweep_max > 1 && (1u << sbits) <= (uint32_t)sweep_max && sbits <= lgb) e->sweep_bits = sbits;
     }
   }
 
@@ -612,7 +567,7 @@ int dwj_get_info(const dwj_engine *e, dwj_info *info) {
   info->launches_build = e->launches_build;
   info->launches_probe = e->launches_probe;
   info->radix_parts = 1u << e->region_bits;
-  info->probe_passes = e->sweep_bits ? 1u << e->sweep_bits : 1u;
+  info->probe_passes = 1u;
   return DWJ_OK;
 }
 

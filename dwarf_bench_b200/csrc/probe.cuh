@@ -33,11 +33,6 @@ template <int W> struct ProbeArgs {
   unsigned long long *n_matches;   // PAIRS / COUNT (device)
   unsigned long long *tile_state;  // PAIRS: [0] = ticket counter, [1..] = lookback descriptors
   uint64_t num_tiles;
-  // Multi-pass region probe (staged kernel): the relation is swept `regions` times; pass r only handles the rows
-  // whose bucket index has (bucket >> region_shift) == r, so its gathers stay inside one L2-resident table slice.
-  uint32_t regions;        // 1 = single pass over everything
-  uint32_t region_shift;
-  uint64_t chunks_per_pass;
 };
 
 // ---- decoupled look-back ----------------------------------------------------------------------
@@ -322,46 +317,31 @@ __global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeA
 // One round of a warp: 32*ITEMS consecutive rows starting at `base`.  FULL = no row of the round is past the end
 // of the relation: no bounds predicates at all (interior rounds; the 64-bit compares and predicated loads of the
 // guarded version were a third of the instruction stream).
-template <int W, bool WITH_KEY, int ITEMS, bool FULL, bool REGION>
-DWJ_D void staged_round(const ProbeArgs<W> &a, uint64_t base, uint32_t region, unsigned lane, unsigned lt,
+template <int W, bool WITH_KEY, int ITEMS, bool FULL>
+DWJ_D void staged_round(const ProbeArgs<W> &a, uint64_t base, unsigned lane, unsigned lt,
                         typename KeyT<W>::type *wb, typename KeyT<W>::type *wp, typename KeyT<W>::type *wk, uint32_t &staged) {
   using K = typename KeyT<W>::type;
   constexpr K SENTINEL = ~(K)0;
   K key[ITEMS], pval[ITEMS];
   Bucket<W> bk[ITEMS];
   uint64_t hb[ITEMS];
-  bool active[ITEMS];
   const K *kp = a.keys + base + lane, *vp = a.vals + base + lane;
   const uint32_t rows = FULL ? 0u : (uint32_t)min((uint64_t)(32 * ITEMS), a.n - base);
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const bool live = FULL || j * 32 + lane < rows;
     key[j] = live ? load_stream(kp + j * 32) : SENTINEL;       // SENTINEL never matches (reserved key)
-    if constexpr (!REGION) pval[j] = live ? load_stream(vp + j * 32) : SENTINEL;
+    pval[j] = live ? load_stream(vp + j * 32) : SENTINEL;
   }
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     hb[j] = slot_hash(key[j], a.seed) & a.bucket_mask;
-    if constexpr (REGION) {
-      // Rows of other table regions are some other pass's business: no gather, no payload load, no output.
-      active[j] = key[j] != SENTINEL && (uint32_t)(hb[j] >> a.region_shift) == region;
-#pragma unroll
-      for (int f = 0; f < (W == 4 ? 8 : 4); ++f) bk[j].f[f] = ~(K)0;   // reads as an empty bucket
-      if (active[j]) {
-        bk[j] = load_bucket_stream<W>(a.table, hb[j]);
-        pval[j] = load_stream(vp + j * 32);
-      } else {
-        pval[j] = SENTINEL;
-      }
-    } else {
-      active[j] = key[j] != SENTINEL;
-      bk[j] = load_bucket_stream<W>(a.table, hb[j]);
-    }
+    bk[j] = load_bucket_stream<W>(a.table, hb[j]);
   }
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     K payload = SENTINEL;
-    const bool hit = find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload) && active[j];
+    const bool hit = find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload) && key[j] != SENTINEL;
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     if (hit) {
       const uint32_t o = staged + __popc(m & lt);
@@ -389,37 +369,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) probe_pairs_staged_kernel(Pr
   const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (t == 0) s_chunk = ORDERED ? atomicAdd(a.tile_state, 1ull) : (unsigned long long)blockIdx.x;
   __syncthreads();
-  const uint64_t chunk = s_chunk;                   // global chunk id: pass-major when the relation is swept per region
-  const uint32_t region = a.regions > 1 ? (uint32_t)(chunk / a.chunks_per_pass) : 0u;
-  const uint64_t local_chunk = a.regions > 1 ? chunk - (uint64_t)region * a.chunks_per_pass : chunk;
-  const uint64_t warp_base = local_chunk * CHUNK + (uint64_t)warp * WROWS;
+  const uint64_t chunk = s_chunk;
+  const uint64_t warp_base = chunk * CHUNK + (uint64_t)warp * WROWS;
   K *wb = s_build + warp * WROWS, *wp = s_probe + warp * WROWS, *wk = s_key + warp * WROWS;
   const unsigned lt = (1u << lane) - 1u;
   uint32_t staged = 0;                              // warp-uniform running count
 
-  if (a.regions > 1) {                              // CTA-uniform
-    if (warp_base + WROWS <= a.n) {
-#pragma unroll 1
-      for (int sub = 0; sub < SUB; ++sub)
-        staged_round<W, WITH_KEY, ITEMS, true, true>(a, warp_base + (uint64_t)sub * (32 * ITEMS), region, lane, lt, wb, wp, wk, staged);
-    } else {
-#pragma unroll 1
-      for (int sub = 0; sub < SUB; ++sub) {
-        const uint64_t base = warp_base + (uint64_t)sub * (32 * ITEMS);
-        if (base >= a.n) break;
-        staged_round<W, WITH_KEY, ITEMS, false, true>(a, base, region, lane, lt, wb, wp, wk, staged);
-      }
-    }
-  } else if (warp_base + WROWS <= a.n) {            // warp-uniform: the whole slice is inside the relation
+  if (warp_base + WROWS <= a.n) {                   // warp-uniform: the whole slice is inside the relation
 #pragma unroll 1
     for (int sub = 0; sub < SUB; ++sub)
-      staged_round<W, WITH_KEY, ITEMS, true, false>(a, warp_base + (uint64_t)sub * (32 * ITEMS), 0u, lane, lt, wb, wp, wk, staged);
+      staged_round<W, WITH_KEY, ITEMS, true>(a, warp_base + (uint64_t)sub * (32 * ITEMS), lane, lt, wb, wp, wk, staged);
   } else {
 #pragma unroll 1
     for (int sub = 0; sub < SUB; ++sub) {
       const uint64_t base = warp_base + (uint64_t)sub * (32 * ITEMS);
       if (base >= a.n) break;
-      staged_round<W, WITH_KEY, ITEMS, false, false>(a, base, 0u, lane, lt, wb, wp, wk, staged);
+      staged_round<W, WITH_KEY, ITEMS, false>(a, base, lane, lt, wb, wp, wk, staged);
     }
   }
   if (lane == 0) s_wtot[warp] = staged;
