@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--emit-key", action="store_true", help="also materialise the key column (reference row shape)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU exchange: fused partition+P2P stores over NVLink (default) or NCCL all-to-all-v")
+    ap.add_argument("--exchange-chunks", type=int, default=1,
+                    help="p2p exchange: probe relation travels in this many pieces, overlapped with the local probes (1 = no overlap; measured no gain: both kernels are SM-bound)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-probe-rows", type=int, default=1 << 26)
@@ -293,13 +295,18 @@ def main():
                             sync=False, stream=stream)
         launches_per_step = None
     else:
-        from dwarf_bench_b200.distributed import CudaJoinOps, ExchangeJoin, P2PExchangeJoin
+        from dwarf_bench_b200.distributed import CudaJoinOps, ExchangeJoin, P2PExchangeJoin, PipelinedP2PExchangeJoin
         exchange_used = "nccl all-to-all-v"
         xj = None
         if args.exchange == "p2p":
             try:
-                xj = P2PExchangeJoin(eng, device, tdt, cap_rows, out_cap, stream=stream)
-                exchange_used = "fused partition + P2P stores into peer memory (NVLink), counts by all-gather"
+                if args.exchange_chunks > 1:
+                    xj = PipelinedP2PExchangeJoin(eng, device, tdt, cap_rows, out_cap, chunks=args.exchange_chunks, stream=stream)
+                    exchange_used = (f"fused partition + P2P stores into peer memory (NVLink), probe relation in {args.exchange_chunks} "
+                                     "chunks overlapped with the local probes, counts by one all-gather")
+                else:
+                    xj = P2PExchangeJoin(eng, device, tdt, cap_rows, out_cap, stream=stream)
+                    exchange_used = "fused partition + P2P stores into peer memory (NVLink), counts by all-gather"
             except Exception as ex:      # peer mapping unavailable on this box: NCCL path (still GPU-only)
                 print(f"[rank {rank}] symmetric memory unavailable ({ex!r}); using NCCL all-to-all-v", file=sys.stderr)
                 xj = None

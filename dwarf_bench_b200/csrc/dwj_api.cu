@@ -82,6 +82,8 @@ struct dwj_engine {
   uint64_t tile_state_cap = 0;                 // in descriptors
   unsigned long long *counter = nullptr;       // device uint64 used when the caller passes no d_n_matches
   unsigned long long *part_scratch = nullptr;  // hist[PART_MAX] + cursor[PART_MAX] + region offsets[PART_MAX + 1]
+  unsigned long long *xchg_cursor = nullptr;   // 8 cursors of dwj_partition_scatter_to: its own scratch, so an exchange
+                                               // on one stream can overlap a build/probe (region partition) on another
   // L2-locality regions: inputs are radix-partitioned on the top `region_bits` bits of the bucket index first
   uint32_t region_bits = 0;
   void *region_build = nullptr, *region_probe = nullptr;   // partitioned copies (keys then payloads)
@@ -217,7 +219,7 @@ int partition_scatter_to_impl(dwj_engine *e, const void *keys, const void *vals,
   a.log2_parts = log2_parts;
   a.seed = e->cfg.hash_seed;
   a.use_dst = 1;
-  a.cursor = e->part_scratch + dwj::PART_MAX;
+  a.cursor = e->xchg_cursor;
   unsigned long long start[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (uint32_t p = 0; p < (1u << log2_parts); ++p) {
     a.dst_keys[p] = (K *)dst_keys[p];
@@ -484,7 +486,7 @@ int dwj_create(const dwj_config *cfg, dwj_engine **out) {
   e->table_bytes = e->buckets * 32ull;
   cudaError_t me = cudaMalloc(&e->table, e->table_bytes);
   if (me != cudaSuccess) return bail(fail(DWJ_ERR_OOM, "cudaMalloc of a %llu-byte table failed: %s", (unsigned long long)e->table_bytes, cudaGetErrorString(me)));
-  if (cudaMalloc(&e->counter, 64) != cudaSuccess || cudaMalloc(&e->part_scratch, (3 * dwj::PART_MAX + 1) * sizeof(unsigned long long)) != cudaSuccess)
+  if (cudaMalloc(&e->xchg_cursor, 64) != cudaSuccess || cudaMalloc(&e->counter, 64) != cudaSuccess || cudaMalloc(&e->part_scratch, (3 * dwj::PART_MAX + 1) * sizeof(unsigned long long)) != cudaSuccess)
     return bail(fail(DWJ_ERR_OOM, "scratch allocation failed"));
   for (int i = 0; i < 2; ++i)
     if (cudaEventCreate(&e->ev_build[i]) != cudaSuccess || cudaEventCreate(&e->ev_probe[i]) != cudaSuccess ||
@@ -532,6 +534,7 @@ int dwj_destroy(dwj_engine *e) {
   cudaFree(e->tile_state);
   cudaFree(e->counter);
   cudaFree(e->part_scratch);
+  cudaFree(e->xchg_cursor);
   cudaFree(e->region_build);
   cudaFree(e->region_probe);
   cudaFree(e->stage);
