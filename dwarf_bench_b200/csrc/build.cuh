@@ -3,9 +3,20 @@
 // Replaces kernel `join_build` (join/join.cpp:60-77) / `hash_build` (hash/hash_build.cpp:36-50),
 // i.e. SimpleNonOwningHashTable::insert + update_bitmask (common/dpcpp/hashtable.hpp:15-21,70-92):
 // claim the first free slot at or after hash(key); duplicate keys each take their own slot.
-// Here the claim and the (key, payload) store are ONE atomic compare-and-swap on the whole slot
-// (64-bit CAS for 4-byte keys, 128-bit CAS for 8-byte keys), so there is no separate bitmask and
-// no window in which a slot is claimed but not yet filled.
+//
+// The reference claims a slot with fetch_or on a bitmask word and then fills keys[] / vals[].  Here a row takes a
+// TICKET: one atomicAdd on a per-bucket fill counter returns the slot index inside the 32-byte bucket, and the
+// (key, payload) pair is then written with one plain fire-and-forget store.  One L2 round trip per row, no bucket
+// snapshot, no retry; only rows whose home bucket is already full (ticket >= SLOTS, 3.7 % of the rows at load 0.5)
+// hop to the next bucket.  Slots are handed out in order, so the occupied slots of a bucket always form a prefix
+// (probe.cuh relies on that).  The counters live in a scratch array (4 B per bucket) that only the build touches.
+//
+// What bounds it (tools/build_bench.cu, 268 M rows into a 4 GB table, input grouped into 128 table regions):
+//   tickets alone 209 G rows/s; slot stores alone 54 G rows/s -- an 8-byte store into a sector that is not in L2
+//   goes through the write-miss path, which is far slower than the read-miss path; with the region's slice
+//   brought into L2 by `prefetch.global.L2` while the PREVIOUS region is being built the same stores run at
+//   130 G rows/s and the whole insert at 77 G rows/s (3.5 ms instead of 5.7 ms).  Hence the look-ahead below.
+//   (The first version -- bucket snapshot, then one 64/128-bit CAS per row -- ran at 28-46 G rows/s everywhere.)
 #pragma once
 #include "table.cuh"
 
@@ -16,81 +27,99 @@ template <int W> struct BuildArgs {
   const typename KeyT<W>::type *vals;
   uint64_t n;
   void *table;
+  unsigned int *fill;                  // [buckets] ticket counters, zeroed before the launch
   uint64_t bucket_mask;
   uint64_t seed;
+  // Region look-ahead (input grouped by table region, dwj_api.cu): rows [offsets[r], offsets[r+1]) go to the table
+  // slice [r * slice_bytes, (r+1) * slice_bytes).  regions <= 1: no look-ahead.
+  const unsigned long long *offsets;   // [regions + 1], device
+  uint32_t regions;
+  uint64_t slice_bytes;
 };
 
-// One CAS attempt on slot i of bucket b; returns true when the row now owns the slot.
-DWJ_D bool cas_slot(void *table, uint64_t b, int i, uint32_t k, uint32_t v) {
+DWJ_D void store_slot(void *table, uint64_t b, uint32_t i, uint32_t k, uint32_t v) {
   unsigned long long *bp = (unsigned long long *)table + (b << 2);
-  return atomicCAS(bp + i, ~0ull, (unsigned long long)k | ((unsigned long long)v << 32)) == ~0ull;
+  bp[i] = (unsigned long long)k | ((unsigned long long)v << 32);
 }
-DWJ_D bool cas_slot(void *table, uint64_t b, int i, uint64_t k, uint64_t v) {
-  unsigned __int128 *bp = (unsigned __int128 *)table + (b << 1);
-  const unsigned __int128 empty = ~(unsigned __int128)0;
-  return atomicCAS(bp + i, empty, (unsigned __int128)k | ((unsigned __int128)v << 64)) == empty;
-}
-
-// First slot the snapshot shows as empty (SLOTS when the bucket looks full).  Occupied slots form a prefix.
-template <int W> DWJ_D int first_empty(const Bucket<W> &bk) {
-  int i = Bucket<W>::SLOTS;
-#pragma unroll
-  for (int s = Bucket<W>::SLOTS - 1; s >= 0; --s) i = bk.empty(s) ? s : i;
-  return i;
+DWJ_D void store_slot(void *table, uint64_t b, uint32_t i, uint64_t k, uint64_t v) {
+  ulonglong2 *bp = (ulonglong2 *)table + (b << 1);
+  bp[i] = make_ulonglong2(k, v);
 }
 
-// Cold path: the optimistic CAS lost its slot to another row (or the home bucket was full).  Re-read and walk on;
-// a failed CAS means another row took the slot meanwhile, and slots are never emptied again.
-template <int W, class K>
-DWJ_D void insert_slow(void *table, uint64_t mask, uint64_t b, K k, K v) {
-  for (;;) {
-    const Bucket<W> bk = load_bucket_cg<W>(table, b);
-#pragma unroll
-    for (int i = 0; i < Bucket<W>::SLOTS; ++i)
-      if (bk.empty(i) && cas_slot(table, b, i, k, v)) return;
-    b = (b + 1) & mask;                 // linear probing at sector granularity
+DWJ_D void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// While the tiles of region r are being inserted, each of them pulls its share of region r+1's table slice (and of
+// its ticket counters) into L2.  Only a hint: a wrong guess costs bandwidth, never correctness.
+template <int W>
+DWJ_D void prefetch_next_region(const BuildArgs<W> &a, uint64_t row0, uint64_t tile_rows) {
+  uint32_t lo = 0, hi = a.regions;                  // offsets[lo] <= row0 < offsets[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(a.offsets + mid) <= row0) lo = mid; else hi = mid;
   }
+  if (lo + 1 >= a.regions) return;
+  const uint64_t start = __ldg(a.offsets + lo), end = __ldg(a.offsets + lo + 1);
+  const uint64_t len = max(end - start, tile_rows), lines = a.slice_bytes >> 7;
+  const uint64_t l0 = (row0 - start) * lines / len, l1 = min((row0 - start + tile_rows) * lines / len, lines);
+  const char *tb = (const char *)a.table + (uint64_t)(lo + 1) * a.slice_bytes;
+  const char *fb = (const char *)a.fill + (uint64_t)(lo + 1) * (a.slice_bytes >> 3);
+  for (uint64_t l = l0 + threadIdx.x; l < l1; l += blockDim.x) prefetch_l2(tb + (l << 7));
+  for (uint64_t l = (l0 >> 3) + threadIdx.x; l < ((l1 + 7) >> 3); l += blockDim.x) prefetch_l2(fb + (l << 7));
 }
 
-// A CTA takes tiles of 256*ROWS CONSECUTIVE rows (tile = blockIdx, grid-stride over tiles), so the rows in
-// flight across the GPU form one contiguous window of the input: when the engine has pre-partitioned the input by
-// table region (dwj_api.cu) that window touches one L2-resident slice of the table.  ROWS independent rows per
-// thread, in three phases so that the long latencies overlap instead of adding up: all home-bucket sectors are
-// requested, then ONE optimistic CAS per row is issued on the first slot its snapshot shows as empty (the CAS
-// round trips of the ROWS rows are in flight together -- the first version checked each result before issuing
-// the next and spent 87 % of its stall samples there), and only rows that lost their slot take the retry loop.
+// A CTA takes one tile of 256*ROWS CONSECUTIVE rows, so the rows in flight across the GPU form one contiguous window
+// of the input: when the engine has grouped the input by table region that window touches one L2-resident slice of
+// the table.  The tickets of a thread's ROWS rows are in flight together, and so are the hops of the rows that
+// overflow (one round trip per hop level, not per row).  From the third hop on a bucket's counter is read before it
+// is bumped, so long chains of full buckets (heavily duplicated keys) are walked with plain loads and the counters
+// cannot run away.
 template <int W, int ROWS>
 __global__ void __launch_bounds__(256) build_kernel(BuildArgs<W> a) {
   using K = typename KeyT<W>::type;
+  constexpr uint32_t SLOTS = Bucket<W>::SLOTS;
   constexpr uint64_t TILE = 256ull * ROWS;
   const uint64_t tiles = (a.n + TILE - 1) / TILE;
   for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    if (a.regions > 1) prefetch_next_region<W>(a, tile * TILE, TILE);
     const uint64_t base = tile * TILE + threadIdx.x;
     K k[ROWS], v[ROWS];
     uint64_t b[ROWS];
-    Bucket<W> bk[ROWS];
+    uint32_t t[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const uint64_t i = base + (uint64_t)r * 256;
       const bool live = i < a.n;
-      k[r] = live ? load_stream(a.keys + i) : ~(K)0;       // the reserved key is never stored
+      k[r] = live ? load_stream(a.keys + i) : ~(K)0;       // the reserved key (and a row past the end) is never stored
       v[r] = live ? load_stream(a.vals + i) : ~(K)0;
     }
-    bool done[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       b[r] = slot_hash(k[r], a.seed) & a.bucket_mask;
-      bk[r] = load_bucket_cg<W>(a.table, b[r]);
+      t[r] = k[r] != ~(K)0 ? atomicAdd(a.fill + b[r], 1u) : 0u;
     }
+    uint32_t pending = 0;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      const int slot = first_empty<W>(bk[r]);
-      done[r] = k[r] == ~(K)0;                              // the reserved key (and rows past the end) is not stored
-      if (!done[r] && slot < Bucket<W>::SLOTS) done[r] = cas_slot(a.table, b[r], slot, k[r], v[r]);
+      if (k[r] == ~(K)0) continue;
+      if (t[r] < SLOTS) store_slot(a.table, b[r], t[r], k[r], v[r]);
+      else pending |= 1u << r;
     }
+    for (uint32_t hop = 1; pending; ++hop) {
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-      if (!done[r]) insert_slow<W, K>(a.table, a.bucket_mask, b[r], k[r], v[r]);
+      for (int r = 0; r < ROWS; ++r) {
+        if (pending >> r & 1u) {
+          b[r] = (b[r] + 1) & a.bucket_mask;               // linear probing at sector granularity
+          t[r] = hop > 2 && __ldcg(a.fill + b[r]) >= SLOTS ? SLOTS : atomicAdd(a.fill + b[r], 1u);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        if ((pending >> r & 1u) && t[r] < SLOTS) {
+          store_slot(a.table, b[r], t[r], k[r], v[r]);
+          pending &= ~(1u << r);
+        }
+      }
+    }
   }
 }
 

@@ -69,6 +69,7 @@ struct dwj_engine {
   int W = 4;
   cudaDeviceProp prop{};
   void *table = nullptr;
+  unsigned int *fill = nullptr;                // per-bucket ticket counters of the build (build.cuh)
   uint64_t slots = 0, buckets = 0, table_bytes = 0;
   uint64_t build_rows = 0;
   bool built = false;
@@ -103,11 +104,15 @@ struct dwj_engine {
 namespace {
 
 template <class Kern, class Args>
-cudaError_t launch(dwj_engine *e, Kern kern, dim3 grid, dim3 block, cudaStream_t s, Args args, bool table_window) {
+cudaError_t launch(dwj_engine *e, Kern kern, dim3 grid, dim3 block, cudaStream_t s, Args args, bool table_window, size_t smem = 0) {
+  if (smem > 48 * 1024) {
+    cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ae != cudaSuccess) return ae;
+  }
   cudaLaunchConfig_t lc{};
   lc.gridDim = grid;
   lc.blockDim = block;
-  lc.dynamicSmemBytes = 0;
+  lc.dynamicSmemBytes = smem;
   lc.stream = s;
   cudaLaunchAttribute attr[1];
   if (table_window && e->l2_window) {
@@ -131,6 +136,44 @@ int ensure_tile_state(dwj_engine *e, uint64_t tiles, cudaStream_t s) {
   CU(cudaMalloc(&e->tile_state, cap * sizeof(unsigned long long)));
   e->tile_state_cap = cap;
   return DWJ_OK;
+}
+
+// > 8 partitions: thread-private byte counters (histogram) and ballot-ranked, shared-memory-staged scatter.
+template <int W, bool BY_BUCKET, int THREADS>
+int hist_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
+  constexpr int HROWS = 8;
+  auto kern = dwj::partition_hist_private_kernel<W, BY_BUCKET, THREADS, HROWS>;
+  const size_t smem = (size_t)THREADS << a.log2_parts;
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+  const uint64_t htiles = (a.n + (uint64_t)THREADS * HROWS - 1) / ((uint64_t)THREADS * HROWS);
+  const unsigned grid = (unsigned)std::min<uint64_t>(htiles, (uint64_t)e->prop.multiProcessorCount * std::max(per_sm, 1));
+  CU(launch(e, kern, dim3(grid), dim3(THREADS), s, a, false, smem));
+  return DWJ_OK;
+}
+template <int W, bool BY_BUCKET> int hist_many(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
+  return a.log2_parts <= 8 ? hist_many_launch<W, BY_BUCKET, 256>(e, a, s) : hist_many_launch<W, BY_BUCKET, 128>(e, a, s);
+}
+
+template <int W, bool BY_BUCKET, int BITS>
+int scatter_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
+  constexpr int THREADS = 256, ITEMS = W == 4 ? 16 : 8, MINB = 3;
+  using SM = dwj::ScatterManySmem<W, THREADS, ITEMS>;
+  const uint64_t tiles = (a.n + SM::TILE - 1) / SM::TILE;
+  auto kern = dwj::partition_scatter_many_kernel<W, BY_BUCKET, BITS, THREADS, ITEMS, MINB>;
+  CU(launch(e, kern, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(THREADS), s, a, false, SM::bytes(1u << BITS)));
+  return DWJ_OK;
+}
+template <int W, bool BY_BUCKET> int scatter_many(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
+  switch (a.log2_parts) {
+  case 4: return scatter_many_launch<W, BY_BUCKET, 4>(e, a, s);
+  case 5: return scatter_many_launch<W, BY_BUCKET, 5>(e, a, s);
+  case 6: return scatter_many_launch<W, BY_BUCKET, 6>(e, a, s);
+  case 7: return scatter_many_launch<W, BY_BUCKET, 7>(e, a, s);
+  case 8: return scatter_many_launch<W, BY_BUCKET, 8>(e, a, s);
+  default: return scatter_many_launch<W, BY_BUCKET, 9>(e, a, s);
+  }
 }
 
 // by_bucket = false: partition id from the independent partition hash (multi-GPU exchange, dwj_partition)
@@ -165,13 +208,16 @@ int partition_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n
   const dim3 hgrid((unsigned)std::min<uint64_t>(htiles, sms * 8ull)), sgrid((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull));
   const dim3 sgrid8((unsigned)std::min<uint64_t>(tiles8, 0x7fffffffull));
   const bool small = log2_parts <= 3;     // <= 8 partitions: packed-register counters, no shared-memory atomics
+  static const bool old_many = getenv("DWJ_PART_OLD") && atoi(getenv("DWJ_PART_OLD"));   // A/B switch (development)
   if (n) {
     if (small) {
       if (by_bucket) CU(launch(e, dwj::partition_hist8_kernel<W, true, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
       else CU(launch(e, dwj::partition_hist8_kernel<W, false, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
-    } else {
+    } else if (old_many) {
       if (by_bucket) CU(launch(e, dwj::partition_hist_kernel<W, true, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
       else CU(launch(e, dwj::partition_hist_kernel<W, false, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
+    } else {
+      if (int rc = by_bucket ? hist_many<W, true>(e, a, s) : hist_many<W, false>(e, a, s)) return rc;
     }
   }
   CU(launch(e, dwj::partition_offsets_kernel<W>, dim3(1), dim3(32), s, a, false));
@@ -179,9 +225,11 @@ int partition_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n
     if (small) {
       if (by_bucket) CU(launch(e, dwj::partition_scatter8_kernel<W, true, ITEMS8>, sgrid8, dim3(dwj::PART_THREADS), s, a, false));
       else CU(launch(e, dwj::partition_scatter8_kernel<W, false, ITEMS8>, sgrid8, dim3(dwj::PART_THREADS), s, a, false));
-    } else {
+    } else if (old_many) {
       if (by_bucket) CU(launch(e, dwj::partition_scatter_kernel<W, true, ITEMS>, sgrid, dim3(dwj::PART_THREADS), s, a, false));
       else CU(launch(e, dwj::partition_scatter_kernel<W, false, ITEMS>, sgrid, dim3(dwj::PART_THREADS), s, a, false));
+    } else {
+      if (int rc = by_bucket ? scatter_many<W, true>(e, a, s) : scatter_many<W, false>(e, a, s)) return rc;
     }
   }
   return DWJ_OK;
@@ -202,7 +250,7 @@ template <int W> int partition_hist_impl(dwj_engine *e, const void *keys, uint64
   const uint64_t htiles = (n + 256ull * HROWS - 1) / (256ull * HROWS);
   const dim3 hgrid((unsigned)std::min<uint64_t>(htiles, (uint64_t)e->prop.multiProcessorCount * 8));
   if (log2_parts <= 3) CU(launch(e, dwj::partition_hist8_kernel<W, false, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
-  else CU(launch(e, dwj::partition_hist_kernel<W, false, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
+  else return hist_many<W, false>(e, a, s);
   return DWJ_OK;
 }
 
@@ -258,7 +306,8 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
   using K = typename dwj::KeyT<W>::type;
   CU(cudaEventRecord(e->ev_build[0], s));
   e->launches_build = 0;
-  if (e->region_bits && n) {      // group the rows by table region first: the inserts then hit an L2-resident slice
+  const bool partitioned = e->region_bits && n;
+  if (partitioned) {      // group the rows by table region first: the inserts then hit an L2-resident slice
     if (int rc = ensure_region_buffer(&e->region_build, &e->region_build_rows, std::max<uint64_t>(n, e->cfg.max_build_rows), W, s)) return rc;
     K *pk = (K *)e->region_build, *pv = pk + e->region_build_rows;
     if (int rc = partition_impl<W>(e, keys, vals, n, e->region_bits, true, pk, pv, (uint64_t *)(e->part_scratch + 2 * dwj::PART_MAX), s)) return rc;
@@ -269,13 +318,27 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
   CU(cudaMemsetAsync(e->table, 0xFF, e->table_bytes, s));
   e->launches_build++;
   if (n) {
-    dwj::BuildArgs<W> a{(const K *)keys, (const K *)vals, n, e->table, e->buckets - 1, e->cfg.hash_seed};
+    CU(cudaMemsetAsync(e->fill, 0, e->buckets * sizeof(unsigned int), s));
+    dwj::BuildArgs<W> a{};
+    a.keys = (const K *)keys;
+    a.vals = (const K *)vals;
+    a.n = n;
+    a.table = e->table;
+    a.fill = e->fill;
+    a.bucket_mask = e->buckets - 1;
+    a.seed = e->cfg.hash_seed;
+    static const bool no_ahead = getenv("DWJ_BUILD_NO_AHEAD") && atoi(getenv("DWJ_BUILD_NO_AHEAD"));   // A/B switch (development)
+    if (partitioned && !no_ahead) {      // region look-ahead: the partition offsets stay on the device
+      a.offsets = e->part_scratch + 2 * dwj::PART_MAX;
+      a.regions = 1u << e->region_bits;
+      a.slice_bytes = e->table_bytes >> e->region_bits;
+    }
     constexpr int ROWS = 4;
     const uint64_t tiles = (n + 256ull * ROWS - 1) / (256ull * ROWS);
     CU(cudaEventRecord(e->ev_buildk[0], s));
     CU(launch(e, dwj::build_kernel<W, ROWS>, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(256), s, a, true));
     CU(cudaEventRecord(e->ev_buildk[1], s));
-    e->launches_build++;
+    e->launches_build += 2;
   }
   CU(cudaEventRecord(e->ev_build[1], s));
   e->have_build = true;
@@ -413,6 +476,12 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
     a.keys = pk;
     a.vals = pv;
     extra_launches = 4;
+    static const bool no_ahead = getenv("DWJ_PROBE_NO_AHEAD") && atoi(getenv("DWJ_PROBE_NO_AHEAD"));   // A/B switch (development)
+    if (!no_ahead) {
+      a.offsets = e->part_scratch + 2 * dwj::PART_MAX;
+      a.regions = 1u << e->region_bits;
+      a.slice_bytes = e->table_bytes >> e->region_bits;
+    }
   }
   CU(cudaEventRecord(e->ev_probek[0], s));
   switch (mode) {
@@ -486,6 +555,8 @@ int dwj_create(const dwj_config *cfg, dwj_engine **out) {
   e->table_bytes = e->buckets * 32ull;
   cudaError_t me = cudaMalloc(&e->table, e->table_bytes);
   if (me != cudaSuccess) return bail(fail(DWJ_ERR_OOM, "cudaMalloc of a %llu-byte table failed: %s", (unsigned long long)e->table_bytes, cudaGetErrorString(me)));
+  if (cudaMalloc((void **)&e->fill, e->buckets * sizeof(unsigned int)) != cudaSuccess)
+    return bail(fail(DWJ_ERR_OOM, "cudaMalloc of the %llu-byte ticket array failed", (unsigned long long)(e->buckets * sizeof(unsigned int))));
   if (cudaMalloc(&e->xchg_cursor, 64) != cudaSuccess || cudaMalloc(&e->counter, 64) != cudaSuccess || cudaMalloc(&e->part_scratch, (3 * dwj::PART_MAX + 1) * sizeof(unsigned long long)) != cudaSuccess)
     return bail(fail(DWJ_ERR_OOM, "scratch allocation failed"));
   for (int i = 0; i < 2; ++i)
@@ -531,6 +602,7 @@ int dwj_destroy(dwj_engine *e) {
   cudaDeviceSynchronize();
   if (e->l2_window) cudaCtxResetPersistingL2Cache();
   cudaFree(e->table);
+  cudaFree(e->fill);
   cudaFree(e->tile_state);
   cudaFree(e->counter);
   cudaFree(e->part_scratch);

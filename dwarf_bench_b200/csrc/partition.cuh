@@ -191,6 +191,231 @@ __global__ void __launch_bounds__(PART_THREADS, 3) partition_scatter_kernel(Part
   }
 }
 
+// ---- many-way path (16 .. 512 partitions) without shared-memory atomics ------------------------------------------
+// Shared-memory atomics cost ~2 cycles per LANE on this machine (64 cycles per warp instruction, per SM): one atomic
+// per row caps a kernel at ~140 G rows/s, 2 ms per 268 M rows, whatever else it does.  The two kernels below use none.
+//
+//   histogram: every thread owns a private 8-bit counter per partition in shared memory (parts x THREADS bytes, laid
+//              out so that lane l always hits bank l); a row is LDS.U8 / IADD / STS.U8.  Counters are folded into
+//              per-thread 32-bit registers before they can overflow (every 255 rows per thread).
+//   scatter  : the ranking of CUB's onesweep -- the lanes of a warp that go to the same partition find each other with
+//              one ballot per partition-id bit, the lowest such lane bumps a WARP-PRIVATE counter by the group size with
+//              a plain read-modify-write, the others take their rank from the ballot.  Per tile: per-warp counts ->
+//              exclusive scan over (partition, warp) -> one global reservation per partition -> rows staged in shared
+//              memory grouped by partition -> streamed out, consecutive threads writing consecutive addresses of a run.
+template <int BITS> DWJ_D unsigned match_partition(uint32_t p, unsigned alive) {
+  unsigned peers = alive;
+#pragma unroll
+  for (int b = 0; b < BITS; ++b) {
+    const bool bit = (p >> b) & 1u;
+    const unsigned m = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? m : ~m;
+  }
+  return peers;
+}
+
+template <int W, bool BY_BUCKET, int THREADS, int HROWS>
+__global__ void __launch_bounds__(THREADS) partition_hist_private_kernel(PartitionArgs<W> a) {
+  using K = typename KeyT<W>::type;
+  extern __shared__ __align__(16) unsigned char s_cnt[];      // [parts][THREADS] bytes
+  const uint32_t parts = 1u << a.log2_parts;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // byte of (this thread, partition 0): lane l -> word l of a 128-byte group (bank l for every partition), the four
+  // warps of a group take the four bytes of the word
+  unsigned char *mine = s_cnt + (warp >> 2) * 128 + lane * 4 + (warp & 3);
+  constexpr int WORDS = THREADS / 4;                           // 32-bit words per partition row
+  constexpr int PER = PART_MAX / THREADS;                      // partitions folded by one thread
+  uint32_t *words = reinterpret_cast<uint32_t *>(s_cnt);
+  for (uint32_t i = threadIdx.x; i < parts * WORDS; i += THREADS) words[i] = 0;
+  __syncthreads();
+  unsigned long long acc[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) acc[q] = 0;
+  auto fold = [&]() {      // all threads: sum and clear the THREADS byte counters of `my` partitions
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const uint32_t p = threadIdx.x + q * THREADS;
+      if (p < parts) {
+        uint32_t sum = 0;
+#pragma unroll 8
+        for (int k = 0; k < WORDS; ++k) {
+          const uint32_t idx = p * WORDS + ((k + lane) & (WORDS - 1));   // rotated: the lanes of a warp hit 32 banks
+          sum = __dp4a(words[idx], 0x01010101u, sum);
+          words[idx] = 0;
+        }
+        acc[q] += sum;
+      }
+    }
+    __syncthreads();
+  };
+  constexpr uint64_t TILE = (uint64_t)THREADS * HROWS;
+  const uint64_t tiles = (a.n + TILE - 1) / TILE;
+  uint32_t pending = 0;
+  for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const uint64_t base = tile * TILE + threadIdx.x;
+    K k[HROWS];
+    if (tile * TILE + TILE <= a.n) {
+#pragma unroll
+      for (int j = 0; j < HROWS; ++j) k[j] = load_stream(a.keys + base + (uint64_t)j * THREADS);
+#pragma unroll
+      for (int j = 0; j < HROWS; ++j) {
+        unsigned char *c = mine + part_id<W, BY_BUCKET>(a, k[j]) * THREADS;
+        *c = (unsigned char)(*c + 1);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < HROWS; ++j) {
+        const uint64_t i = base + (uint64_t)j * THREADS;
+        if (i < a.n) {
+          unsigned char *c = mine + part_id<W, BY_BUCKET>(a, load_stream(a.keys + i)) * THREADS;
+          *c = (unsigned char)(*c + 1);
+        }
+      }
+    }
+    pending += HROWS;
+    if (pending > 255 - HROWS) { fold(); pending = 0; }       // block-uniform: every thread has seen the same tiles
+  }
+  fold();
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const uint32_t p = threadIdx.x + q * THREADS;
+    if (p < parts && acc[q]) atomicAdd(a.hist + p, acc[q]);
+  }
+}
+
+template <int W, int THREADS, int ITEMS> struct ScatterManySmem {
+  using K = typename KeyT<W>::type;
+  static constexpr uint32_t TILE = THREADS * ITEMS;
+  static constexpr int WARPS = THREADS / 32;
+  // dynamic shared memory: keys[TILE] | vals[TILE] | delta[parts] (int64) | wc[WARPS][parts] (uint32)
+  static size_t bytes(uint32_t parts) { return (size_t)TILE * 2 * sizeof(K) + (size_t)parts * (8 + 4 * WARPS); }
+};
+
+template <int W, bool BY_BUCKET, int BITS, int THREADS, int ITEMS, bool FULL>
+DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t rows, unsigned char *smem, unsigned int *s_scan) {
+  using K = typename KeyT<W>::type;
+  constexpr uint32_t TILE = THREADS * ITEMS;
+  constexpr int WARPS = THREADS / 32;
+  constexpr uint32_t PARTS = 1u << BITS;
+  constexpr int PER = (PARTS + THREADS - 1) / THREADS;
+  K *s_keys = reinterpret_cast<K *>(smem);
+  K *s_vals = s_keys + TILE;
+  long long *s_delta = reinterpret_cast<long long *>(s_vals + TILE);
+  unsigned int *s_wc = reinterpret_cast<unsigned int *>(s_delta + PARTS);
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const bool with_vals = a.vals != nullptr;
+  unsigned int *mywc = s_wc + warp * PARTS;
+#pragma unroll
+  for (uint32_t p = lane; p < PARTS; p += 32) mywc[p] = 0;
+
+  K k[ITEMS], v[ITEMS];
+  uint32_t pr[ITEMS];                               // partition << 16 | rank inside (warp, partition); PART_DEAD = dead row
+  const K *kp = a.keys + base + threadIdx.x, *vp = a.vals + base + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const bool live = FULL || j * THREADS + threadIdx.x < rows;
+    k[j] = live ? load_stream(kp + j * THREADS) : (K)0;
+    v[j] = live && with_vals ? load_stream(vp + j * THREADS) : (K)0;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const bool live = FULL || j * THREADS + threadIdx.x < rows;
+    const uint32_t p = part_id<W, BY_BUCKET>(a, k[j]);
+    const unsigned alive = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, live);
+    const unsigned peers = match_partition<BITS>(p, alive);
+    uint32_t old = 0;
+    if (live && (peers & lt) == 0) {                // lowest lane of the group: plain RMW on the warp's own counter
+      old = mywc[p];
+      mywc[p] = old + __popc(peers);
+    }
+    __syncwarp();
+    old = __shfl_sync(0xffffffffu, old, (__ffs(peers) - 1) & 31);
+    pr[j] = live ? (p << 16 | (old + __popc(peers & lt))) : PART_DEAD;
+  }
+  __syncthreads();
+  // (partition, warp) exclusive scan + one global reservation per partition.  Thread t owns partitions t*PER .. +PER.
+  {
+    unsigned local[PER], sum = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const uint32_t p = threadIdx.x * PER + q;
+      unsigned total = 0;
+      if (p < PARTS) {
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) total += s_wc[w * PARTS + p];
+      }
+      local[q] = total;
+      sum += total;
+    }
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (unsigned)o) incl += n;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    unsigned before = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) before += w < (int)warp ? s_scan[w] : 0u;
+    unsigned run = before + incl - sum;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const uint32_t p = threadIdx.x * PER + q;
+      if (p < PARTS) {
+        const unsigned long long g = local[q] ? atomicAdd(a.cursor + p, (unsigned long long)local[q]) : 0ull;
+        s_delta[p] = (long long)g - (long long)run;
+        unsigned at = run;                          // warp w's rows of partition p are staged at s_wc[w][p] + rank
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+          const unsigned c = s_wc[w * PARTS + p];
+          s_wc[w * PARTS + p] = at;
+          at += c;
+        }
+      }
+      run += local[q];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    if (FULL || pr[j] != PART_DEAD) {
+      const uint32_t s = mywc[pr[j] >> 16] + (pr[j] & 0xFFFFu);
+      s_keys[s] = k[j];
+      s_vals[s] = v[j];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const uint32_t s = j * THREADS + threadIdx.x;
+    if (FULL || s < rows) {
+      const K key = s_keys[s];
+      const long long dst = (long long)s + s_delta[part_id<W, BY_BUCKET>(a, key)];
+      store_stream(a.out_keys + dst, key);
+      if (with_vals) store_stream(a.out_vals + dst, s_vals[s]);
+    }
+  }
+}
+
+template <int W, bool BY_BUCKET, int BITS, int THREADS, int ITEMS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) partition_scatter_many_kernel(PartitionArgs<W> a) {
+  constexpr uint32_t TILE = THREADS * ITEMS;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ unsigned int s_scan[THREADS / 32];
+  const uint64_t num_tiles = (a.n + TILE - 1) / TILE;
+  for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint64_t base = tile * TILE;
+    const uint32_t rows = (uint32_t)min((uint64_t)TILE, a.n - base);
+    if (rows == TILE) scatter_many_tile<W, BY_BUCKET, BITS, THREADS, ITEMS, true>(a, base, rows, s_dyn, s_scan);
+    else scatter_many_tile<W, BY_BUCKET, BITS, THREADS, ITEMS, false>(a, base, rows, s_dyn, s_scan);
+    __syncthreads();                                // shared memory is reused by the next tile
+  }
+}
+
 // ---- fast path: at most 8 partitions ---------------------------------------------------------------------
 // No shared-memory atomics and no MATCH: per-partition counters are PACKED into 64-bit registers.
 //   histogram: 8 fields x 8 bits per thread, flushed to shared memory before a field can overflow;

@@ -319,7 +319,7 @@ def test_join_host_buffers(dwj, wide, n_build, n_probe):
 
 
 @pytest.mark.parametrize("wide", [False, True])
-@pytest.mark.parametrize("parts", [1, 2, 8, 256])
+@pytest.mark.parametrize("parts", [1, 2, 8, 16, 64, 128, 256, 512])
 def test_partition(dwj, wide, parts):
     from dwarf_bench_b200 import capi
     rng = np.random.default_rng(parts)
@@ -331,9 +331,12 @@ def test_partition(dwj, wide, parts):
         ok, ov = empty_like_dev(n, dt), empty_like_dev(n, dt)
         offs = torch.zeros(parts + 1, dtype=torch.int64, device="cuda")
         e.partition(dev(k), dev(v), n, parts, ok, ov, offs)
+        counts = torch.zeros(parts, dtype=torch.int64, device="cuda")
+        e.partition_hist(dev(k), n, parts, counts)
         torch.cuda.synchronize()
         offs = offs.cpu().numpy()
         ok, ov = host(ok, dt)[:n], host(ov, dt)[:n]
+    np.testing.assert_array_equal(counts.cpu().numpy(), np.diff(offs))   # histogram-only entry point agrees
     assert offs[0] == 0 and offs[-1] == n and (np.diff(offs) >= 0).all()
     np.testing.assert_array_equal(k[ov.astype(np.int64)], ok)        # (key, payload) pairs stay together
     np.testing.assert_array_equal(np.sort(ov), v)                    # a permutation: nothing lost or duplicated
