@@ -138,7 +138,7 @@ int ensure_tile_state(dwj_engine *e, uint64_t tiles, cudaStream_t s) {
   return DWJ_OK;
 }
 
-// > 8 partitions: thread-private byte counters (histogram) and ballot-ranked, shared-memory-staged scatter.
+// Thread-private byte counters (histogram, > 8 partitions) and the ballot-ranked, shared-memory-staged scatter.
 template <int W, bool BY_BUCKET, int THREADS>
 int hist_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
   constexpr int HROWS = 8;
@@ -167,6 +167,9 @@ int scatter_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStrea
 }
 template <int W, bool BY_BUCKET> int scatter_many(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
   switch (a.log2_parts) {
+  case 1: return scatter_many_launch<W, BY_BUCKET, 1>(e, a, s);
+  case 2: return scatter_many_launch<W, BY_BUCKET, 2>(e, a, s);
+  case 3: return scatter_many_launch<W, BY_BUCKET, 3>(e, a, s);
   case 4: return scatter_many_launch<W, BY_BUCKET, 4>(e, a, s);
   case 5: return scatter_many_launch<W, BY_BUCKET, 5>(e, a, s);
   case 6: return scatter_many_launch<W, BY_BUCKET, 6>(e, a, s);
@@ -199,38 +202,23 @@ int partition_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n
   a.cursor = e->part_scratch + dwj::PART_MAX;
   a.offsets = (unsigned long long *)d_offsets;
   CU(cudaMemsetAsync(e->part_scratch, 0, 2 * dwj::PART_MAX * sizeof(unsigned long long), s));
-  const unsigned sms = (unsigned)e->prop.multiProcessorCount;
-  constexpr int HROWS = 8, ITEMS = 8;
-  const uint64_t htiles = (n + 256ull * HROWS - 1) / (256ull * HROWS);
-  const uint64_t tiles = (n + 256ull * ITEMS - 1) / (256ull * ITEMS);
-  constexpr int ITEMS8 = W == 4 ? 16 : 8;      // <= 8 partitions: bigger tiles, fewer global reservations
-  const uint64_t tiles8 = (n + 256ull * ITEMS8 - 1) / (256ull * ITEMS8);
-  const dim3 hgrid((unsigned)std::min<uint64_t>(htiles, sms * 8ull)), sgrid((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull));
-  const dim3 sgrid8((unsigned)std::min<uint64_t>(tiles8, 0x7fffffffull));
-  const bool small = log2_parts <= 3;     // <= 8 partitions: packed-register counters, no shared-memory atomics
-  static const bool old_many = getenv("DWJ_PART_OLD") && atoi(getenv("DWJ_PART_OLD"));   // A/B switch (development)
   if (n) {
-    if (small) {
+    if (log2_parts <= 3) {      // <= 8 partitions: packed-register counters
+      constexpr int HROWS = 8;
+      const uint64_t htiles = (n + 256ull * HROWS - 1) / (256ull * HROWS);
+      const dim3 hgrid((unsigned)std::min<uint64_t>(htiles, (uint64_t)e->prop.multiProcessorCount * 8));
       if (by_bucket) CU(launch(e, dwj::partition_hist8_kernel<W, true, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
       else CU(launch(e, dwj::partition_hist8_kernel<W, false, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
-    } else if (old_many) {
-      if (by_bucket) CU(launch(e, dwj::partition_hist_kernel<W, true, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
-      else CU(launch(e, dwj::partition_hist_kernel<W, false, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
     } else {
       if (int rc = by_bucket ? hist_many<W, true>(e, a, s) : hist_many<W, false>(e, a, s)) return rc;
     }
   }
   CU(launch(e, dwj::partition_offsets_kernel<W>, dim3(1), dim3(32), s, a, false));
-  if (n) {
-    if (small) {
-      if (by_bucket) CU(launch(e, dwj::partition_scatter8_kernel<W, true, ITEMS8>, sgrid8, dim3(dwj::PART_THREADS), s, a, false));
-      else CU(launch(e, dwj::partition_scatter8_kernel<W, false, ITEMS8>, sgrid8, dim3(dwj::PART_THREADS), s, a, false));
-    } else if (old_many) {
-      if (by_bucket) CU(launch(e, dwj::partition_scatter_kernel<W, true, ITEMS>, sgrid, dim3(dwj::PART_THREADS), s, a, false));
-      else CU(launch(e, dwj::partition_scatter_kernel<W, false, ITEMS>, sgrid, dim3(dwj::PART_THREADS), s, a, false));
-    } else {
-      if (int rc = by_bucket ? scatter_many<W, true>(e, a, s) : scatter_many<W, false>(e, a, s)) return rc;
-    }
+  if (n && log2_parts)
+    if (int rc = by_bucket ? scatter_many<W, true>(e, a, s) : scatter_many<W, false>(e, a, s)) return rc;
+  if (n && !log2_parts) {       // one partition: a copy
+    CU(cudaMemcpyAsync(ok, keys, n * W, cudaMemcpyDeviceToDevice, s));
+    if (vals) CU(cudaMemcpyAsync(ov, vals, n * W, cudaMemcpyDeviceToDevice, s));
   }
   return DWJ_OK;
 }
@@ -281,10 +269,8 @@ int partition_scatter_to_impl(dwj_engine *e, const void *keys, const void *vals,
   // Staged variant: destinations may sit behind NVLink, which wants 128-byte pieces (partition.cuh).
   constexpr int ITEMS8 = W == 4 ? 16 : 8;
   const uint64_t tiles8 = (n + 256ull * ITEMS8 - 1) / (256ull * ITEMS8);
-  static const bool direct = getenv("DWJ_SCATTER_TO_DIRECT") && atoi(getenv("DWJ_SCATTER_TO_DIRECT"));   // tuning
   const dim3 grid((unsigned)std::min<uint64_t>(tiles8, 0x7fffffffull));
-  if (direct) CU(launch(e, dwj::partition_scatter8_kernel<W, false, ITEMS8>, grid, dim3(dwj::PART_THREADS), s, a, false));
-  else CU(launch(e, dwj::partition_scatter8_staged_kernel<W, false, ITEMS8>, grid, dim3(dwj::PART_THREADS), s, a, false));
+  CU(launch(e, dwj::partition_scatter8_staged_kernel<W, false, ITEMS8>, grid, dim3(dwj::PART_THREADS), s, a, false));
   return DWJ_OK;
 }
 
@@ -476,12 +462,6 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
     a.keys = pk;
     a.vals = pv;
     extra_launches = 4;
-    static const bool no_ahead = getenv("DWJ_PROBE_NO_AHEAD") && atoi(getenv("DWJ_PROBE_NO_AHEAD"));   // A/B switch (development)
-    if (!no_ahead) {
-      a.offsets = e->part_scratch + 2 * dwj::PART_MAX;
-      a.regions = 1u << e->region_bits;
-      a.slice_bytes = e->table_bytes >> e->region_bits;
-    }
   }
   CU(cudaEventRecord(e->ev_probek[0], s));
   switch (mode) {

@@ -8,12 +8,22 @@
 //     fills a 128-byte line (profiles/r1_gather_microbench.md), so a random probe of an HBM-resident table costs
 //     ~100 B of DRAM traffic per row; partitioning first costs 4 + 16 B per row of pure streaming instead.
 //
-// Three launches: histogram -> offsets (one block) -> scatter.  Ranks are computed warp-cooperatively: the lanes
-// of a warp that go to the same partition are found with log2(parts) ballots, one lane adds their count to the
-// shared-memory counter and the others derive their rank from the ballot -- ~4x fewer shared-memory atomics than
-// one per row at 8 partitions.  The scatter stages each tile in shared memory grouped by partition and reserves
-// one contiguous output range per (tile, partition) with a single global atomicAdd, so global writes are
-// contiguous runs (2 KB on average at 8 partitions), not a row-by-row scatter.
+// Three launches: histogram -> offsets (one block) -> scatter.  Neither hot kernel uses shared-memory atomics with a
+// result: those cost ~2 cycles per LANE on this machine (64 cycles per warp instruction per SM), i.e. one per row caps
+// a kernel at ~140 G rows/s whatever else it does.
+//   histogram: <= 8 partitions: eight 8-bit counters packed in a 64-bit register per thread;
+//              more: a private 8-bit counter per (thread, partition) in shared memory, laid out so lane l always
+//              hits bank l; a row is LDS.U8 / IADD / STS.U8.  Both fold into 32-bit totals before a byte can overflow.
+//   scatter  : the ranking of CUB's onesweep -- the lanes of a warp that go to the same partition find each other
+//              with one ballot per partition-id bit, the lowest of them bumps a WARP-PRIVATE shared-memory counter by
+//              the group size with a plain read-modify-write, the others take their rank from the ballot.  Per tile
+//              of 4096 (4-byte keys) / 2048 rows: per-warp counts -> exclusive scan over (partition, warp) -> one
+//              global reservation per partition -> rows staged in shared memory grouped by partition -> streamed out,
+//              consecutive threads writing consecutive addresses of a run.
+//   Measured (tools/partition_sweep.py, 268 M rows of 4+4 bytes): histogram 0.22 ms at 8..128 partitions (4.9 TB/s),
+//   0.66 ms at 512; scatter 1.26 ms at 16 partitions (3.4 TB/s), 1.50 ms at 128, 2.0 ms at 512; 8+8-byte rows reach
+//   5.0 TB/s at 16 partitions.  The scatter replaced a shared-memory-atomic version (1.65 ms at 128, 2.7 ms at 512)
+//   and, for <= 8 partitions, a register-only ballot kernel that stored rows unstaged (1.26-1.8 ms).
 #pragma once
 #include "table.cuh"
 
@@ -53,37 +63,6 @@ template <int W, bool BY_BUCKET> DWJ_D uint32_t part_id(const PartitionArgs<W> &
 
 constexpr uint32_t PART_DEAD = 0xFFFFFFFFu;   // partition id of a lane past the end of the input
 
-// Histogram for more than 8 partitions: HROWS coalesced key loads in flight per thread, one fire-and-forget
-// shared-memory atomic per row.  (With 16+ bins a warp rarely has more than 2-3 lanes on one bin; grouping the
-// lanes with MATCH.ANY first was 8x slower than the packed-counter kernel below, 1.86 ms per 268 M rows.)
-template <int W, bool BY_BUCKET, int HROWS>
-__global__ void __launch_bounds__(PART_THREADS) partition_hist_kernel(PartitionArgs<W> a) {
-  using K = typename KeyT<W>::type;
-  __shared__ unsigned int s_hist[PART_MAX];
-  const uint32_t parts = 1u << a.log2_parts;
-  for (uint32_t p = threadIdx.x; p < parts; p += blockDim.x) s_hist[p] = 0;
-  __syncthreads();
-  constexpr uint64_t TILE = (uint64_t)PART_THREADS * HROWS;
-  const uint64_t tiles = (a.n + TILE - 1) / TILE;
-  for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const uint64_t base = tile * TILE + threadIdx.x;
-    K k[HROWS];
-    bool live[HROWS];
-#pragma unroll
-    for (int j = 0; j < HROWS; ++j) {
-      const uint64_t i = base + (uint64_t)j * PART_THREADS;
-      live[j] = i < a.n;
-      k[j] = live[j] ? load_stream(a.keys + i) : (K)0;
-    }
-#pragma unroll
-    for (int j = 0; j < HROWS; ++j)
-      if (live[j]) atomicAdd(&s_hist[part_id<W, BY_BUCKET>(a, k[j])], 1u);   // > 8 bins: few same-bin lanes per warp
-  }
-  __syncthreads();
-  for (uint32_t p = threadIdx.x; p < parts; p += blockDim.x)
-    if (s_hist[p]) atomicAdd(a.hist + p, (unsigned long long)s_hist[p]);
-}
-
 template <int W> __global__ void partition_offsets_kernel(PartitionArgs<W> a) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const uint32_t parts = 1u << a.log2_parts;
@@ -97,112 +76,7 @@ template <int W> __global__ void partition_offsets_kernel(PartitionArgs<W> a) {
   }
 }
 
-// Scatter.  Per tile of 256*ITEMS rows: rank every row inside its partition (MATCH.ANY groups + one shared-memory
-// atomic per group), scan the per-partition counts, reserve one global range per partition, stage (key, payload,
-// partition id) in shared memory grouped by partition, then stream the tile out: consecutive threads write
-// consecutive addresses inside each partition's run.
-template <int W, bool BY_BUCKET, int ITEMS>
-__global__ void __launch_bounds__(PART_THREADS, 3) partition_scatter_kernel(PartitionArgs<W> a) {
-  using K = typename KeyT<W>::type;
-  constexpr uint32_t TILE = PART_THREADS * ITEMS;
-  __shared__ K s_keys[TILE];
-  __shared__ K s_vals[TILE];
-  __shared__ unsigned short s_part[TILE];
-  __shared__ unsigned int s_count[PART_MAX];        // rows of this tile per partition
-  __shared__ unsigned int s_start[PART_MAX];        // exclusive scan of s_count (staging offsets)
-  __shared__ long long s_delta[PART_MAX];           // global start of the partition's run minus its staging offset
-  __shared__ unsigned int s_scan[PART_THREADS / 32];
-
-  const uint32_t parts = 1u << a.log2_parts;
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool with_vals = a.vals != nullptr;
-  const uint64_t num_tiles = (a.n + TILE - 1) / TILE;
-  for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const uint64_t base = tile * TILE;
-    const uint32_t rows = (uint32_t)min((uint64_t)TILE, a.n - base);
-    for (uint32_t p = threadIdx.x; p < parts; p += PART_THREADS) s_count[p] = 0;
-    __syncthreads();
-
-    K k[ITEMS], v[ITEMS];
-    uint32_t part[ITEMS], rank[ITEMS];
-    const K *kp = a.keys + base + threadIdx.x, *vp = a.vals + base + threadIdx.x;
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      const bool live = j * PART_THREADS + threadIdx.x < rows;
-      k[j] = live ? load_stream(kp + j * PART_THREADS) : (K)0;
-      v[j] = live && with_vals ? load_stream(vp + j * PART_THREADS) : (K)0;
-    }
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      const bool live = j * PART_THREADS + threadIdx.x < rows;
-      part[j] = live ? part_id<W, BY_BUCKET>(a, k[j]) : PART_DEAD;
-      rank[j] = live ? atomicAdd(&s_count[part[j]], 1u) : 0u;        // > 8 bins: few same-bin lanes per warp
-    }
-    __syncthreads();
-    // Exclusive scan of s_count[0..parts) by the whole CTA (parts <= 512 = 2 per thread), global reservation.
-    {
-      unsigned local[PART_MAX / PART_THREADS], sum = 0;
-#pragma unroll
-      for (int q = 0; q < PART_MAX / PART_THREADS; ++q) {
-        const uint32_t p = threadIdx.x * (PART_MAX / PART_THREADS) + q;
-        local[q] = p < parts ? s_count[p] : 0u;
-        sum += local[q];
-      }
-      unsigned incl = sum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += n;
-      }
-      if (lane == 31) s_scan[warp] = incl;
-      __syncthreads();
-      unsigned before = 0;
-#pragma unroll
-      for (int w = 0; w < PART_THREADS / 32; ++w) before += w < (int)warp ? s_scan[w] : 0u;
-      unsigned run = before + incl - sum;
-#pragma unroll
-      for (int q = 0; q < PART_MAX / PART_THREADS; ++q) {
-        const uint32_t p = threadIdx.x * (PART_MAX / PART_THREADS) + q;
-        if (p < parts) {
-          s_start[p] = run;
-          const unsigned long long g = local[q] ? atomicAdd(a.cursor + p, (unsigned long long)local[q]) : 0ull;
-          s_delta[p] = (long long)g - (long long)run;
-        }
-        run += local[q];
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      if (part[j] != PART_DEAD) {
-        const uint32_t s = s_start[part[j]] + rank[j];
-        s_keys[s] = k[j];
-        s_vals[s] = v[j];
-        s_part[s] = (unsigned short)part[j];
-      }
-    }
-    __syncthreads();
-    for (uint32_t s = threadIdx.x; s < rows; s += PART_THREADS) {
-      const long long dst = (long long)s + s_delta[s_part[s]];
-      store_stream(a.out_keys + dst, s_keys[s]);
-      if (with_vals) store_stream(a.out_vals + dst, s_vals[s]);
-    }
-    __syncthreads();
-  }
-}
-
-// ---- many-way path (16 .. 512 partitions) without shared-memory atomics ------------------------------------------
-// Shared-memory atomics cost ~2 cycles per LANE on this machine (64 cycles per warp instruction, per SM): one atomic
-// per row caps a kernel at ~140 G rows/s, 2 ms per 268 M rows, whatever else it does.  The two kernels below use none.
-//
-//   histogram: every thread owns a private 8-bit counter per partition in shared memory (parts x THREADS bytes, laid
-//              out so that lane l always hits bank l); a row is LDS.U8 / IADD / STS.U8.  Counters are folded into
-//              per-thread 32-bit registers before they can overflow (every 255 rows per thread).
-//   scatter  : the ranking of CUB's onesweep -- the lanes of a warp that go to the same partition find each other with
-//              one ballot per partition-id bit, the lowest such lane bumps a WARP-PRIVATE counter by the group size with
-//              a plain read-modify-write, the others take their rank from the ballot.  Per tile: per-warp counts ->
-//              exclusive scan over (partition, warp) -> one global reservation per partition -> rows staged in shared
-//              memory grouped by partition -> streamed out, consecutive threads writing consecutive addresses of a run.
+// ---- scatter (2 .. 512 partitions) and the many-way histogram ----------------------------------------------------
 template <int BITS> DWJ_D unsigned match_partition(uint32_t p, unsigned alive) {
   unsigned peers = alive;
 #pragma unroll
@@ -416,13 +290,10 @@ __global__ void __launch_bounds__(THREADS, MINB) partition_scatter_many_kernel(P
   }
 }
 
-// ---- fast path: at most 8 partitions ---------------------------------------------------------------------
-// No shared-memory atomics and no MATCH: per-partition counters are PACKED into 64-bit registers.
-//   histogram: 8 fields x 8 bits per thread, flushed to shared memory before a field can overflow;
-//   scatter  : ballots + warp-distributed counters (see scatter8_tile); no atomics decide the order inside a
-//              tile, so the output is deterministic up to the order of the tiles' global reservations.
-// Interior tiles run a FULL = true instantiation of the tile body without any bounds predicate (the 64-bit
-// compares and the per-row branches they cause were most of the instruction stream in the first version).
+// ---- histogram for at most 8 partitions ------------------------------------------------------------------------
+// Per-partition counters are PACKED into one 64-bit register per thread: 8 fields x 8 bits, flushed to shared memory
+// before a field can overflow.  Interior tiles run a FULL = true instantiation of the tile body without any bounds
+// predicate (the 64-bit compares and the per-row branches they cause were most of the instruction stream at first).
 template <int W, bool BY_BUCKET, int HROWS, bool FULL>
 DWJ_D void hist8_tile(const PartitionArgs<W> &a, uint64_t tile_base, unsigned long long &acc) {
   using K = typename KeyT<W>::type;
@@ -467,98 +338,9 @@ __global__ void __launch_bounds__(PART_THREADS) partition_hist8_kernel(Partition
   if (threadIdx.x < 8 && s_hist[threadIdx.x]) atomicAdd(a.hist + threadIdx.x, (unsigned long long)s_hist[threadIdx.x]);
 }
 
-// Scatter for <= 8 partitions, straight from registers (no staging): a warp ranks its rows with three ballots per
-// 32 rows and warp-distributed counters (lane q keeps the warp's running count of partition q), the CTA combines
-// the per-warp totals once (one barrier pair), reserves one global range per partition, and every row is stored at
-// range + rank.  A warp's store instruction then covers <= 8 contiguous pieces instead of one -- more sectors per
-// request than a staged copy-out, but half the instructions and no shared-memory traffic; L2 merges the pieces
-// before they reach HBM.
-template <int W, bool BY_BUCKET, int ITEMS, bool FULL, bool WITH_VALS>
-DWJ_D void scatter8_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t rows, unsigned int (*s_wcnt)[8],
-                         unsigned long long (*s_wbase)[8], typename KeyT<W>::type *const *s_dstk,
-                         typename KeyT<W>::type *const *s_dstv) {
-  using K = typename KeyT<W>::type;
-  constexpr int WARPS = PART_THREADS / 32;
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt = (1u << lane) - 1u;
-  // lane-constant selectors for "my own partition q = lane & 7" (used by the counter lanes)
-  const unsigned q0 = (lane & 1) ? 0xffffffffu : 0u, q1 = (lane & 2) ? 0xffffffffu : 0u, q2 = (lane & 4) ? 0xffffffffu : 0u;
-  K k[ITEMS], v[ITEMS];
-  uint32_t pr[ITEMS];                              // rank << 4 | partition (partition 8 = dead row)
-  const K *kp = a.keys + base + threadIdx.x, *vp = a.vals + base + threadIdx.x;
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const bool live = FULL || j * PART_THREADS + threadIdx.x < rows;
-    k[j] = live ? load_stream(kp + j * PART_THREADS) : (K)0;
-    if constexpr (WITH_VALS) v[j] = live ? load_stream(vp + j * PART_THREADS) : (K)0;
-  }
-  uint32_t run = 0;                                // lanes 0..7: rows of partition `lane` seen so far by this warp
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const bool live = FULL || j * PART_THREADS + threadIdx.x < rows;
-    const uint32_t p = part_id<W, BY_BUCKET>(a, k[j]);
-    const unsigned alive = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, live);
-    const unsigned b0 = __ballot_sync(0xffffffffu, p & 1u), b1 = __ballot_sync(0xffffffffu, p & 2u), b2 = __ballot_sync(0xffffffffu, p & 4u);
-    const unsigned m0 = (p & 1u) ? b0 : ~b0, m1 = (p & 2u) ? b1 : ~b1, m2 = (p & 4u) ? b2 : ~b2;
-    const unsigned peers = m0 & m1 & m2 & alive;                       // live lanes with my partition
-    const uint32_t before = __shfl_sync(0xffffffffu, run, p);         // the warp's count of my partition so far
-    pr[j] = live ? ((before + __popc(peers & lt)) << 4 | p) : 8u;
-    run += __popc(~(b0 ^ q0) & ~(b1 ^ q1) & ~(b2 ^ q2) & alive);       // counter lanes: rows of partition (lane & 7)
-  }
-  if (lane < 8) s_wcnt[warp][lane] = run;
-  __syncthreads();
-  if (threadIdx.x < 8) {                           // partition q: prefix over the warps, one global reservation
-    const unsigned q = threadIdx.x;
-    unsigned total = 0, pre[WARPS];
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) { pre[w] = total; total += s_wcnt[w][q]; }
-    const unsigned long long g = total ? atomicAdd(a.cursor + q, (unsigned long long)total) : 0ull;
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) s_wbase[w][q] = g + pre[w];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    if (FULL || pr[j] != 8u) {
-      const uint32_t p = pr[j] & 15u;
-      const unsigned long long dst = s_wbase[warp][p] + (pr[j] >> 4);
-      store_stream(s_dstk[p] + dst, k[j]);
-      if constexpr (WITH_VALS) store_stream(s_dstv[p] + dst, v[j]);
-    }
-  }
-}
-
-template <int W, bool BY_BUCKET, int ITEMS>
-__global__ void __launch_bounds__(PART_THREADS, 3) partition_scatter8_kernel(PartitionArgs<W> a) {
-  constexpr uint32_t TILE = PART_THREADS * ITEMS;
-  using K = typename KeyT<W>::type;
-  __shared__ unsigned int s_wcnt[PART_THREADS / 32][8];
-  __shared__ unsigned long long s_wbase[PART_THREADS / 32][8];
-  __shared__ K *s_dstk[8];
-  __shared__ K *s_dstv[8];
-  if (threadIdx.x < 8) {
-    s_dstk[threadIdx.x] = a.use_dst ? a.dst_keys[threadIdx.x] : a.out_keys;
-    s_dstv[threadIdx.x] = a.use_dst ? a.dst_vals[threadIdx.x] : a.out_vals;
-  }
-  __syncthreads();
-  const bool with_vals = a.vals != nullptr;
-  const uint64_t num_tiles = (a.n + TILE - 1) / TILE;
-  for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const uint64_t base = tile * TILE;
-    const uint32_t rows = (uint32_t)min((uint64_t)TILE, a.n - base);
-    if (rows == TILE) {
-      if (with_vals) scatter8_tile<W, BY_BUCKET, ITEMS, true, true>(a, base, rows, s_wcnt, s_wbase, s_dstk, s_dstv);
-      else scatter8_tile<W, BY_BUCKET, ITEMS, true, false>(a, base, rows, s_wcnt, s_wbase, s_dstk, s_dstv);
-    } else {
-      if (with_vals) scatter8_tile<W, BY_BUCKET, ITEMS, false, true>(a, base, rows, s_wcnt, s_wbase, s_dstk, s_dstv);
-      else scatter8_tile<W, BY_BUCKET, ITEMS, false, false>(a, base, rows, s_wcnt, s_wbase, s_dstk, s_dstv);
-    }
-    __syncthreads();                               // s_wcnt / s_wbase are reused by the next tile
-  }
-}
-
-// Scatter for <= 8 partitions with STAGING, for destinations on the far side of NVLink (dwj_partition_scatter_to):
-// same ballot ranking as scatter8_tile, but the tile is first grouped by partition in shared memory and then
+// Scatter for <= 8 partitions with one DESTINATION POINTER per partition, for destinations on the far side of NVLink
+// (dwj_partition_scatter_to): three ballots per 32 rows and warp-distributed counters (lane q keeps the warp's running
+// count of partition q) rank the rows; the tile is first grouped by partition in shared memory and then
 // streamed out so that every warp-level store is one contiguous 128-byte (4-byte keys) / 256-byte (8-byte keys)
 // piece of ONE destination.  Storing straight from registers hands each peer ~16-byte pieces per instruction, which
 // NVLink moves at a fraction of its bandwidth (8 GPUs: 26.8 ms per step against a 2.6 ms transfer floor).

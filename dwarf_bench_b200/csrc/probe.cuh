@@ -33,29 +33,7 @@ template <int W> struct ProbeArgs {
   unsigned long long *n_matches;   // PAIRS / COUNT (device)
   unsigned long long *tile_state;  // PAIRS: [0] = ticket counter, [1..] = lookback descriptors
   uint64_t num_tiles;
-  // Region look-ahead (input grouped by table region, dwj_api.cu): rows [offsets[r], offsets[r+1]) probe the table
-  // slice [r * slice_bytes, (r+1) * slice_bytes).  regions <= 1: none.
-  const unsigned long long *offsets;
-  uint32_t regions;
-  uint64_t slice_bytes;
 };
-
-// While region r is being probed, every chunk pulls its share of region r+1's table slice into L2 (a hint only), so
-// that the gathers of the next region never wait for a DRAM line fill.  Same scheme as build.cuh.
-template <int W>
-DWJ_D void probe_prefetch_next_region(const ProbeArgs<W> &a, uint64_t row0, uint64_t chunk_rows) {
-  uint32_t lo = 0, hi = a.regions;                  // offsets[lo] <= row0 < offsets[hi]
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(a.offsets + mid) <= row0) lo = mid; else hi = mid;
-  }
-  if (lo + 1 >= a.regions) return;
-  const uint64_t start = __ldg(a.offsets + lo), end = __ldg(a.offsets + lo + 1);
-  const uint64_t len = max(end - start, chunk_rows), lines = a.slice_bytes >> 7;
-  const uint64_t l0 = (row0 - start) * lines / len, l1 = min((row0 - start + chunk_rows) * lines / len, lines);
-  const char *tb = (const char *)a.table + (uint64_t)(lo + 1) * a.slice_bytes;
-  for (uint64_t l = l0 + threadIdx.x; l < l1; l += blockDim.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(tb + (l << 7)));
-}
 
 // ---- decoupled look-back ----------------------------------------------------------------------
 // One 64-bit descriptor per tile: status in the top two bits, value in the low 62.
@@ -392,7 +370,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) probe_pairs_staged_kernel(Pr
   if (t == 0) s_chunk = ORDERED ? atomicAdd(a.tile_state, 1ull) : (unsigned long long)blockIdx.x;
   __syncthreads();
   const uint64_t chunk = s_chunk;
-  if (a.regions > 1) probe_prefetch_next_region<W>(a, chunk * CHUNK, CHUNK);
   const uint64_t warp_base = chunk * CHUNK + (uint64_t)warp * WROWS;
   K *wb = s_build + warp * WROWS, *wp = s_probe + warp * WROWS, *wk = s_key + warp * WROWS;
   const unsigned lt = (1u << lane) - 1u;

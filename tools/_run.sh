@@ -1,18 +1,15 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-run() { # name, env...
-  name=$1; shift
-  for wl in join_16Mx256M_u32_unique join_256Mx256M_u32_unique join_512Mx1G_u64_unique; do
-    env "$@" python bench.py --workload $wl --steps 4 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/la_${name}_$wl.json 2> gpurun_out/la.err
-  done
-}
-run both X=1
-run nobuild DWJ_BUILD_NO_AHEAD=1
-run noprobe DWJ_PROBE_NO_AHEAD=1
+python tools/partition_sweep.py --parts 2 4 8 16 > gpurun_out/psweep2_u32.txt 2>&1; cat gpurun_out/psweep2_u32.txt
+for wl in join_16Mx256M_u32_unique join_256Mx256M_u32_unique join_512Mx1G_u64_unique join_16Mx256M_u32_dup4_zipf; do
+  python bench.py --workload $wl --steps 4 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/lc_$wl.json 2> gpurun_out/lc.err
+done
+DWJ_REGION_MB=16 python bench.py --workload join_16Mx256M_u32_unique --steps 4 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/lc_r16_join_16Mx256M_u32_unique.json 2> gpurun_out/lc.err
+DWJ_REGION_MB=16 python bench.py --workload join_256Mx256M_u32_unique --steps 4 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/lc_r16_join_256Mx256M_u32_unique.json 2> gpurun_out/lc.err
 python - <<'PY'
 import json,glob
-for f in sorted(glob.glob("gpurun_out/la_*.json")):
+for f in sorted(glob.glob("gpurun_out/lc_*.json")):
     try:
-        d=json.load(open(f)); print(f, round(d["ms_per_step"],3), {k:round(v,3) for k,v in d["phases_ms"].items()}, round(d["roofline"]["kernel_ms"],3))
+        d=json.load(open(f)); print(f, round(d["ms_per_step"],3), {k:round(v,3) for k,v in d["phases_ms"].items()}, round(d["roofline"]["kernel_ms"],3), d["config"]["table_regions"])
     except Exception as ex: print(f, "ERR", ex)
 PY
-tail -3 gpurun_out/la.err
+tail -3 gpurun_out/lc.err
