@@ -55,10 +55,12 @@ def parse_args():
     ap.add_argument("--no-partition", action="store_true", help="probe the table directly (probe-row output order)")
     ap.add_argument("--unordered", action="store_true", help="DWJ_FLAG_UNORDERED_OUTPUT")
     ap.add_argument("--emit-key", action="store_true", help="also materialise the key column (reference row shape)")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="multi-GPU exchange: fused partition+P2P stores over NVLink (default) or NCCL all-to-all-v")
-    ap.add_argument("--exchange-chunks", type=int, default=1,
-                    help="p2p exchange: probe relation travels in this many pieces, overlapped with the local probes (1 = no overlap; measured no gain: both kernels are SM-bound)")
+    ap.add_argument("--exchange", default="fold", choices=["fold", "p2p", "nccl"],
+                    help="multi-GPU exchange: fold = one (rank x table region) partition pass + copy-engine pushes into peer "
+                         "memory, overlapped with the local probes (default); p2p = fused partition + SM stores into peer memory; "
+                         "nccl = local partition + NCCL all-to-all-v")
+    ap.add_argument("--exchange-chunks", type=int, default=2,
+                    help="fold / p2p exchange: the probe relation travels in this many pieces")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-probe-rows", type=int, default=1 << 26)
@@ -295,12 +297,18 @@ def main():
                             sync=False, stream=stream)
         launches_per_step = None
     else:
-        from dwarf_bench_b200.distributed import CudaJoinOps, ExchangeJoin, P2PExchangeJoin, PipelinedP2PExchangeJoin
+        from dwarf_bench_b200.distributed import (CudaJoinOps, ExchangeJoin, FoldedExchangeJoin, P2PExchangeJoin,
+                                                  PipelinedP2PExchangeJoin)
         exchange_used = "nccl all-to-all-v"
         xj = None
-        if args.exchange == "p2p":
+        if args.exchange in ("fold", "p2p"):
             try:
-                if args.exchange_chunks > 1:
+                if args.exchange == "fold":
+                    xj = FoldedExchangeJoin(eng, device, tdt, cap_rows, out_cap, n_build, n_probe, chunks=args.exchange_chunks,
+                                            stream=stream)
+                    exchange_used = (f"one (rank x {xj.regions} table regions) partition pass, copy-engine pushes into peer memory "
+                                     f"(NVLink), probe relation in {xj.chunks} chunks overlapped with the local probes, counts by one all-gather")
+                elif args.exchange_chunks > 1:
                     xj = PipelinedP2PExchangeJoin(eng, device, tdt, cap_rows, out_cap, chunks=args.exchange_chunks, stream=stream)
                     exchange_used = (f"fused partition + P2P stores into peer memory (NVLink), probe relation in {args.exchange_chunks} "
                                      "chunks overlapped with the local probes, counts by one all-gather")
@@ -345,6 +353,8 @@ def main():
         del rows
     info = eng.info()
     launches_per_step = info["launches_build"] + info["launches_probe"] + (0 if world == 1 else 2 * 4)   # + 2 x dwj_partition
+    if world > 1 and isinstance(xj, FoldedExchangeJoin):     # per batch: histogram + memset, offsets + scatter; one probe per chunk
+        launches_per_step = (1 + xj.chunks) * 4 + info["launches_build"] + xj.chunks * info["launches_probe"]
 
     # ---- timed region ----------------------------------------------------------------------------------------
     def barrier():

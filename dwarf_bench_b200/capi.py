@@ -24,7 +24,9 @@ ERR_NAMES = {0: "DWJ_OK", -1: "DWJ_ERR_INVALID", -2: "DWJ_ERR_CUDA", -3: "DWJ_ER
 # Every symbol include/dwj.h declares (tests check the library exports exactly these).
 SYMBOLS = ("dwj_abi_version", "dwj_last_error", "dwj_create", "dwj_destroy", "dwj_get_info", "dwj_build",
            "dwj_probe_aligned", "dwj_probe_contains", "dwj_probe_pairs", "dwj_probe_count", "dwj_timings",
-           "dwj_join_host", "dwj_partition", "dwj_partition_hist", "dwj_partition_scatter_to", "dwj_partition_of")
+           "dwj_join_host", "dwj_partition", "dwj_partition_hist", "dwj_partition_scatter_to", "dwj_partition_of",
+           "dwj_xpart_regions", "dwj_xpart_hist", "dwj_xpart_scatter", "dwj_build_grouped", "dwj_probe_pairs_grouped",
+           "dwj_copy_many")
 
 
 class DwjError(RuntimeError):
@@ -98,9 +100,16 @@ def load_library():
     lib.dwj_partition_scatter_to.argtypes = [vp, vp, vp, u64, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), vp]
     lib.dwj_partition_of.argtypes = [u64, C.c_int32, u32, u64]
     lib.dwj_partition_of.restype = u32
+    lib.dwj_xpart_regions.argtypes = [vp, u32]
+    lib.dwj_xpart_regions.restype = u32
+    lib.dwj_xpart_hist.argtypes = [vp, vp, u64, u32, vp, vp]
+    lib.dwj_xpart_scatter.argtypes = [vp, vp, vp, u64, u32, vp, vp, vp, vp, vp]
+    lib.dwj_build_grouped.argtypes = [vp, vp, vp, u64, vp, vp]
+    lib.dwj_probe_pairs_grouped.argtypes = [vp, vp, vp, u64, vp, vp, vp, u64, vp, C.POINTER(u64), vp]
+    lib.dwj_copy_many.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(vp)]
     for name in SYMBOLS:
         f = getattr(lib, name)
-        if name not in ("dwj_last_error", "dwj_partition_of"):
+        if name not in ("dwj_last_error", "dwj_partition_of", "dwj_xpart_regions"):
             f.restype = C.c_int
     _lib = lib
     return lib
@@ -221,6 +230,55 @@ class Engine:
         off = (C.c_uint64 * n_parts)(*[int(x) for x in dst_row_offsets])
         self._check(self.lib.dwj_partition_scatter_to(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, n_parts, pk, pv, off,
                                                       _stream(stream)))
+
+
+    # ---- exchange partition folded with the receiver's region grouping (include/dwj.h, dwj_xpart_*) -------------------
+    def xpart_regions(self, n_ranks: int) -> int:
+        return int(self.lib.dwj_xpart_regions(self._h, n_ranks))
+
+    def xpart_hist(self, d_keys, n_rows: int, n_ranks: int, d_counts, stream=None) -> None:
+        self._check(self.lib.dwj_xpart_hist(self._h, _ptr(d_keys), n_rows, n_ranks, _ptr(d_counts), _stream(stream)))
+
+    def xpart_scatter(self, d_keys, d_vals, n_rows: int, n_ranks: int, d_counts, d_out_keys, d_out_vals, d_offsets,
+                      stream=None) -> None:
+        self._check(self.lib.dwj_xpart_scatter(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, n_ranks, _ptr(d_counts),
+                                               _ptr(d_out_keys), _ptr(d_out_vals), _ptr(d_offsets), _stream(stream)))
+
+    def build_grouped(self, d_keys, d_vals, n_rows: int, d_region_offsets=None, stream=None) -> None:
+        self._check(self.lib.dwj_build_grouped(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, _ptr(d_region_offsets),
+                                               _stream(stream)))
+
+    def probe_pairs_grouped(self, d_keys, d_vals, n_rows: int, d_out_key, d_out_build_val, d_out_probe_val, capacity: int,
+                            d_n_matches=None, sync: bool = True, stream=None):
+        n = C.c_uint64(0)
+        rc = self.lib.dwj_probe_pairs_grouped(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, _ptr(d_out_key),
+                                              _ptr(d_out_build_val), _ptr(d_out_probe_val), capacity, _ptr(d_n_matches),
+                                              C.byref(n) if sync else None, _stream(stream))
+        self._check(rc)
+        return int(n.value) if sync else None
+
+    def copy_many(self, copies) -> None:
+        """copies: list of (dst pointer, src pointer, bytes, stream); device-to-device, possibly to peer memory."""
+        n = len(copies)
+        if not n:
+            return
+        d = (C.c_void_p * n)(*[int(c[0]) for c in copies])
+        s = (C.c_void_p * n)(*[int(c[1]) for c in copies])
+        b = (C.c_uint64 * n)(*[int(c[2]) for c in copies])
+        st = (C.c_void_p * n)(*[_stream(c[3]) for c in copies])
+        self._check(self.lib.dwj_copy_many(self._h, n, d, s, b, st))
+
+
+    def copy_many_arrays(self, dsts, srcs, nbytes, streams) -> None:
+        """dwj_copy_many from four equally long numpy uint64 arrays (no per-copy Python work)."""
+        import numpy as np
+        arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in (dsts, srcs, nbytes, streams)]
+        n = len(arrs[0])
+        if not n:
+            return
+        vpp, u64p = C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)
+        self._check(self.lib.dwj_copy_many(self._h, n, arrs[0].ctypes.data_as(vpp), arrs[1].ctypes.data_as(vpp),
+                                           arrs[2].ctypes.data_as(u64p), arrs[3].ctypes.data_as(vpp)))
 
 
 def partition_of(key: int, key_bytes: int, n_parts: int, hash_seed: int = 42) -> int:

@@ -83,6 +83,7 @@ struct dwj_engine {
   uint64_t tile_state_cap = 0;                 // in descriptors
   unsigned long long *counter = nullptr;       // device uint64 used when the caller passes no d_n_matches
   unsigned long long *part_scratch = nullptr;  // hist[PART_MAX] + cursor[PART_MAX] + region offsets[PART_MAX + 1]
+  unsigned long long *xpart_cursor = nullptr;  // PART_MAX cursors of dwj_xpart_scatter (own scratch: may run beside a local join)
   unsigned long long *xchg_cursor = nullptr;   // 8 cursors of dwj_partition_scatter_to: its own scratch, so an exchange
                                                // on one stream can overlap a build/probe (region partition) on another
   // L2-locality regions: inputs are radix-partitioned on the top `region_bits` bits of the bucket index first
@@ -139,10 +140,10 @@ int ensure_tile_state(dwj_engine *e, uint64_t tiles, cudaStream_t s) {
 }
 
 // Thread-private byte counters (histogram, > 8 partitions) and the ballot-ranked, shared-memory-staged scatter.
-template <int W, bool BY_BUCKET, int THREADS>
+template <int W, int THREADS>
 int hist_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
   constexpr int HROWS = 8;
-  auto kern = dwj::partition_hist_private_kernel<W, BY_BUCKET, THREADS, HROWS>;
+  auto kern = dwj::partition_hist_private_kernel<W, THREADS, HROWS>;
   const size_t smem = (size_t)THREADS << a.log2_parts;
   if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
@@ -152,38 +153,51 @@ int hist_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t
   CU(launch(e, kern, dim3(grid), dim3(THREADS), s, a, false, smem));
   return DWJ_OK;
 }
-template <int W, bool BY_BUCKET> int hist_many(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
-  return a.log2_parts <= 8 ? hist_many_launch<W, BY_BUCKET, 256>(e, a, s) : hist_many_launch<W, BY_BUCKET, 128>(e, a, s);
+// Histogram of a.keys into a.hist (zeroed by the caller).
+template <int W> int hist_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
+  if (!a.n) return DWJ_OK;
+  if (a.log2_parts <= 3) {      // <= 8 partitions: packed-register counters
+    constexpr int HROWS = 8;
+    const uint64_t htiles = (a.n + 256ull * HROWS - 1) / (256ull * HROWS);
+    const dim3 hgrid((unsigned)std::min<uint64_t>(htiles, (uint64_t)e->prop.multiProcessorCount * 8));
+    CU(launch(e, dwj::partition_hist8_kernel<W, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
+    return DWJ_OK;
+  }
+  return a.log2_parts <= 8 ? hist_many_launch<W, 256>(e, a, s) : hist_many_launch<W, 128>(e, a, s);
 }
 
-template <int W, bool BY_BUCKET, int BITS>
+template <int W, int BITS>
 int scatter_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
   constexpr int THREADS = 256, ITEMS = W == 4 ? 16 : 8, MINB = 3;
   using SM = dwj::ScatterManySmem<W, THREADS, ITEMS>;
   const uint64_t tiles = (a.n + SM::TILE - 1) / SM::TILE;
-  auto kern = dwj::partition_scatter_many_kernel<W, BY_BUCKET, BITS, THREADS, ITEMS, MINB>;
+  auto kern = dwj::partition_scatter_many_kernel<W, BITS, THREADS, ITEMS, MINB>;
   CU(launch(e, kern, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(THREADS), s, a, false, SM::bytes(1u << BITS)));
   return DWJ_OK;
 }
-template <int W, bool BY_BUCKET> int scatter_many(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
+// Scatter a.keys / a.vals to a.out_* at the running positions in a.cursor (1 .. 512 partitions).
+template <int W> int scatter_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
+  if (!a.n) return DWJ_OK;
   switch (a.log2_parts) {
-  case 1: return scatter_many_launch<W, BY_BUCKET, 1>(e, a, s);
-  case 2: return scatter_many_launch<W, BY_BUCKET, 2>(e, a, s);
-  case 3: return scatter_many_launch<W, BY_BUCKET, 3>(e, a, s);
-  case 4: return scatter_many_launch<W, BY_BUCKET, 4>(e, a, s);
-  case 5: return scatter_many_launch<W, BY_BUCKET, 5>(e, a, s);
-  case 6: return scatter_many_launch<W, BY_BUCKET, 6>(e, a, s);
-  case 7: return scatter_many_launch<W, BY_BUCKET, 7>(e, a, s);
-  case 8: return scatter_many_launch<W, BY_BUCKET, 8>(e, a, s);
-  default: return scatter_many_launch<W, BY_BUCKET, 9>(e, a, s);
+  case 0:                         // one partition: a copy
+    CU(cudaMemcpyAsync(a.out_keys, a.keys, a.n * W, cudaMemcpyDeviceToDevice, s));
+    if (a.vals) CU(cudaMemcpyAsync(a.out_vals, a.vals, a.n * W, cudaMemcpyDeviceToDevice, s));
+    return DWJ_OK;
+  case 1: return scatter_many_launch<W, 1>(e, a, s);
+  case 2: return scatter_many_launch<W, 2>(e, a, s);
+  case 3: return scatter_many_launch<W, 3>(e, a, s);
+  case 4: return scatter_many_launch<W, 4>(e, a, s);
+  case 5: return scatter_many_launch<W, 5>(e, a, s);
+  case 6: return scatter_many_launch<W, 6>(e, a, s);
+  case 7: return scatter_many_launch<W, 7>(e, a, s);
+  case 8: return scatter_many_launch<W, 8>(e, a, s);
+  default: return scatter_many_launch<W, 9>(e, a, s);
   }
 }
 
-// by_bucket = false: partition id from the independent partition hash (multi-GPU exchange, dwj_partition)
-// by_bucket = true : partition id = top log2_parts bits of the bucket index (engine regions)
 template <int W>
-int partition_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, uint32_t log2_parts, bool by_bucket, void *ok,
-                   void *ov, uint64_t *d_offsets, cudaStream_t s) {
+dwj::PartitionArgs<W> partition_args(const dwj_engine *e, const void *keys, const void *vals, uint64_t n, uint32_t log2_parts, uint32_t mode,
+                                     uint32_t rank_bits) {
   using K = typename dwj::KeyT<W>::type;
   dwj::PartitionArgs<W> a{};
   a.keys = (const K *)keys;
@@ -191,55 +205,58 @@ int partition_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n
   a.n = n;
   a.log2_parts = log2_parts;
   a.seed = e->cfg.hash_seed;
-  a.by_bucket = by_bucket ? 1u : 0u;
+  a.mode = mode;
+  a.rank_bits = rank_bits;
   a.bucket_mask = e->buckets - 1;
   uint32_t lgb = 0;
   while ((1ull << lgb) < e->buckets) ++lgb;
-  a.bucket_shift = lgb >= log2_parts ? lgb - log2_parts : 0;
+  const uint32_t region_bits = mode == dwj::PART_BY_BOTH ? log2_parts - rank_bits : log2_parts;
+  a.bucket_shift = lgb >= region_bits ? lgb - region_bits : 0;
+  return a;
+}
+
+// mode PART_BY_HASH  : partition id from the independent partition hash (multi-GPU exchange, dwj_partition)
+// mode PART_BY_BUCKET: partition id = top log2_parts bits of the bucket index (engine regions)
+template <int W>
+int partition_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, uint32_t log2_parts, uint32_t mode, void *ok,
+                   void *ov, uint64_t *d_offsets, cudaStream_t s) {
+  using K = typename dwj::KeyT<W>::type;
+  dwj::PartitionArgs<W> a = partition_args<W>(e, keys, vals, n, log2_parts, mode, 0);
   a.out_keys = (K *)ok;
   a.out_vals = (K *)ov;
   a.hist = e->part_scratch;
   a.cursor = e->part_scratch + dwj::PART_MAX;
   a.offsets = (unsigned long long *)d_offsets;
   CU(cudaMemsetAsync(e->part_scratch, 0, 2 * dwj::PART_MAX * sizeof(unsigned long long), s));
-  if (n) {
-    if (log2_parts <= 3) {      // <= 8 partitions: packed-register counters
-      constexpr int HROWS = 8;
-      const uint64_t htiles = (n + 256ull * HROWS - 1) / (256ull * HROWS);
-      const dim3 hgrid((unsigned)std::min<uint64_t>(htiles, (uint64_t)e->prop.multiProcessorCount * 8));
-      if (by_bucket) CU(launch(e, dwj::partition_hist8_kernel<W, true, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
-      else CU(launch(e, dwj::partition_hist8_kernel<W, false, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
-    } else {
-      if (int rc = by_bucket ? hist_many<W, true>(e, a, s) : hist_many<W, false>(e, a, s)) return rc;
-    }
-  }
+  if (int rc = hist_launch<W>(e, a, s)) return rc;
   CU(launch(e, dwj::partition_offsets_kernel<W>, dim3(1), dim3(32), s, a, false));
-  if (n && log2_parts)
-    if (int rc = by_bucket ? scatter_many<W, true>(e, a, s) : scatter_many<W, false>(e, a, s)) return rc;
-  if (n && !log2_parts) {       // one partition: a copy
-    CU(cudaMemcpyAsync(ok, keys, n * W, cudaMemcpyDeviceToDevice, s));
-    if (vals) CU(cudaMemcpyAsync(ov, vals, n * W, cudaMemcpyDeviceToDevice, s));
-  }
-  return DWJ_OK;
+  return scatter_launch<W>(e, a, s);
 }
 
-// Histogram only (exchange planning): counts per partition of the independent partition hash -> d_counts[parts].
-template <int W> int partition_hist_impl(dwj_engine *e, const void *keys, uint64_t n, uint32_t log2_parts, uint64_t *d_counts, cudaStream_t s) {
-  using K = typename dwj::KeyT<W>::type;
-  dwj::PartitionArgs<W> a{};
-  a.keys = (const K *)keys;
-  a.n = n;
-  a.log2_parts = log2_parts;
-  a.seed = e->cfg.hash_seed;
+// Histogram only (exchange planning) -> d_counts[parts].  PART_BY_HASH: the independent partition hash; PART_BY_BOTH:
+// the combined (destination rank, table region) id of dwj_xpart_*.
+template <int W> int partition_hist_impl(dwj_engine *e, const void *keys, uint64_t n, uint32_t log2_parts, uint32_t mode, uint32_t rank_bits,
+                                         uint64_t *d_counts, cudaStream_t s) {
+  dwj::PartitionArgs<W> a = partition_args<W>(e, keys, nullptr, n, log2_parts, mode, rank_bits);
   a.hist = (unsigned long long *)d_counts;
-  constexpr int HROWS = 8;
   CU(cudaMemsetAsync(d_counts, 0, sizeof(uint64_t) << log2_parts, s));
-  if (!n) return DWJ_OK;
-  const uint64_t htiles = (n + 256ull * HROWS - 1) / (256ull * HROWS);
-  const dim3 hgrid((unsigned)std::min<uint64_t>(htiles, (uint64_t)e->prop.multiProcessorCount * 8));
-  if (log2_parts <= 3) CU(launch(e, dwj::partition_hist8_kernel<W, false, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
-  else return hist_many<W, false>(e, a, s);
-  return DWJ_OK;
+  return hist_launch<W>(e, a, s);
+}
+
+// Scatter with the histogram already known (d_counts from partition_hist_impl, same mode): offsets from the counts,
+// then the scatter -- the second half of a partition whose first half fed the exchange plan.
+template <int W>
+int partition_scatter_counted_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, uint32_t log2_parts, uint32_t mode,
+                                   uint32_t rank_bits, const uint64_t *d_counts, void *ok, void *ov, uint64_t *d_offsets, cudaStream_t s) {
+  using K = typename dwj::KeyT<W>::type;
+  dwj::PartitionArgs<W> a = partition_args<W>(e, keys, vals, n, log2_parts, mode, rank_bits);
+  a.out_keys = (K *)ok;
+  a.out_vals = (K *)ov;
+  a.hist = (unsigned long long *)d_counts;
+  a.cursor = e->xpart_cursor;
+  a.offsets = (unsigned long long *)d_offsets;
+  CU(launch(e, dwj::partition_offsets_kernel<W>, dim3(1), dim3(32), s, a, false));
+  return scatter_launch<W>(e, a, s);
 }
 
 // Scatter straight into per-partition destinations (local or peer memory); <= 8 partitions.  The caller has planned
@@ -254,6 +271,7 @@ int partition_scatter_to_impl(dwj_engine *e, const void *keys, const void *vals,
   a.n = n;
   a.log2_parts = log2_parts;
   a.seed = e->cfg.hash_seed;
+  a.mode = dwj::PART_BY_HASH;
   a.use_dst = 1;
   a.cursor = e->xchg_cursor;
   unsigned long long start[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -270,7 +288,7 @@ int partition_scatter_to_impl(dwj_engine *e, const void *keys, const void *vals,
   constexpr int ITEMS8 = W == 4 ? 16 : 8;
   const uint64_t tiles8 = (n + 256ull * ITEMS8 - 1) / (256ull * ITEMS8);
   const dim3 grid((unsigned)std::min<uint64_t>(tiles8, 0x7fffffffull));
-  CU(launch(e, dwj::partition_scatter8_staged_kernel<W, false, ITEMS8>, grid, dim3(dwj::PART_THREADS), s, a, false));
+  CU(launch(e, dwj::partition_scatter8_staged_kernel<W, ITEMS8>, grid, dim3(dwj::PART_THREADS), s, a, false));
   return DWJ_OK;
 }
 
@@ -288,15 +306,18 @@ int ensure_region_buffer(void **buf, uint64_t *cap_rows, uint64_t rows, int W, c
   return DWJ_OK;
 }
 
-template <int W> int build_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, cudaStream_t s) {
+// grouped: the caller's rows are already grouped by table region (dwj_build_grouped); `grouped_offsets` (device,
+// regions + 1 entries, may be null) are the regions' row ranges for the look-ahead.
+template <int W> int build_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, cudaStream_t s, bool grouped = false,
+                                const uint64_t *grouped_offsets = nullptr) {
   using K = typename dwj::KeyT<W>::type;
   CU(cudaEventRecord(e->ev_build[0], s));
   e->launches_build = 0;
-  const bool partitioned = e->region_bits && n;
+  const bool partitioned = e->region_bits && n && !grouped;
   if (partitioned) {      // group the rows by table region first: the inserts then hit an L2-resident slice
     if (int rc = ensure_region_buffer(&e->region_build, &e->region_build_rows, std::max<uint64_t>(n, e->cfg.max_build_rows), W, s)) return rc;
     K *pk = (K *)e->region_build, *pv = pk + e->region_build_rows;
-    if (int rc = partition_impl<W>(e, keys, vals, n, e->region_bits, true, pk, pv, (uint64_t *)(e->part_scratch + 2 * dwj::PART_MAX), s)) return rc;
+    if (int rc = partition_impl<W>(e, keys, vals, n, e->region_bits, dwj::PART_BY_BUCKET, pk, pv, (uint64_t *)(e->part_scratch + 2 * dwj::PART_MAX), s)) return rc;
     keys = pk;
     vals = pv;
     e->launches_build += 4;
@@ -314,8 +335,8 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
     a.bucket_mask = e->buckets - 1;
     a.seed = e->cfg.hash_seed;
     static const bool no_ahead = getenv("DWJ_BUILD_NO_AHEAD") && atoi(getenv("DWJ_BUILD_NO_AHEAD"));   // A/B switch (development)
-    if (partitioned && !no_ahead) {      // region look-ahead: the partition offsets stay on the device
-      a.offsets = e->part_scratch + 2 * dwj::PART_MAX;
+    if ((partitioned || (grouped && grouped_offsets && e->region_bits)) && !no_ahead) {   // region look-ahead: offsets stay on the device
+      a.offsets = partitioned ? e->part_scratch + 2 * dwj::PART_MAX : (const unsigned long long *)grouped_offsets;
       a.regions = 1u << e->region_bits;
       a.slice_bytes = e->table_bytes >> e->region_bits;
     }
@@ -430,7 +451,7 @@ int staged_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
 
 template <int W>
 int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint64_t n, void *ok, void *ob, void *op,
-               uint32_t *flags, uint64_t capacity, uint64_t *d_n, uint64_t *h_n, cudaStream_t s) {
+               uint32_t *flags, uint64_t capacity, uint64_t *d_n, uint64_t *h_n, cudaStream_t s, bool grouped = false) {
   using K = typename dwj::KeyT<W>::type;
   if (!e->built) return fail(DWJ_ERR_STATE, "probe before dwj_build");
   dwj::ProbeArgs<W> a{};
@@ -450,13 +471,13 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
   CU(cudaEventRecord(e->ev_probe[0], s));
   int rc;
   uint32_t extra_launches = 0;
-  if (e->region_bits && n && (mode == dwj::PROBE_PAIRS || mode == dwj::PROBE_COUNT)) {
+  if (e->region_bits && n && !grouped && (mode == dwj::PROBE_PAIRS || mode == dwj::PROBE_COUNT)) {
     // Same grouping for the probe relation: its rows then walk the table slice by slice (output order becomes
     // region-major; the row multiset is unchanged).
     if ((rc = ensure_region_buffer(&e->region_probe, &e->region_probe_rows, n, W, s))) return rc;
     K *pk = (K *)e->region_probe, *pv = pk + e->region_probe_rows;
     const bool with_vals = mode == dwj::PROBE_PAIRS;
-    if ((rc = partition_impl<W>(e, keys, with_vals ? vals : nullptr, n, e->region_bits, true, pk, with_vals ? pv : nullptr,
+    if ((rc = partition_impl<W>(e, keys, with_vals ? vals : nullptr, n, e->region_bits, dwj::PART_BY_BUCKET, pk, with_vals ? pv : nullptr,
                                 (uint64_t *)(e->part_scratch + 2 * dwj::PART_MAX), s)))
       return rc;
     a.keys = pk;
@@ -537,7 +558,7 @@ int dwj_create(const dwj_config *cfg, dwj_engine **out) {
   if (me != cudaSuccess) return bail(fail(DWJ_ERR_OOM, "cudaMalloc of a %llu-byte table failed: %s", (unsigned long long)e->table_bytes, cudaGetErrorString(me)));
   if (cudaMalloc((void **)&e->fill, e->buckets * sizeof(unsigned int)) != cudaSuccess)
     return bail(fail(DWJ_ERR_OOM, "cudaMalloc of the %llu-byte ticket array failed", (unsigned long long)(e->buckets * sizeof(unsigned int))));
-  if (cudaMalloc(&e->xchg_cursor, 64) != cudaSuccess || cudaMalloc(&e->counter, 64) != cudaSuccess || cudaMalloc(&e->part_scratch, (3 * dwj::PART_MAX + 1) * sizeof(unsigned long long)) != cudaSuccess)
+  if (cudaMalloc(&e->xpart_cursor, dwj::PART_MAX * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&e->xchg_cursor, 64) != cudaSuccess || cudaMalloc(&e->counter, 64) != cudaSuccess || cudaMalloc(&e->part_scratch, (3 * dwj::PART_MAX + 1) * sizeof(unsigned long long)) != cudaSuccess)
     return bail(fail(DWJ_ERR_OOM, "scratch allocation failed"));
   for (int i = 0; i < 2; ++i)
     if (cudaEventCreate(&e->ev_build[i]) != cudaSuccess || cudaEventCreate(&e->ev_probe[i]) != cudaSuccess ||
@@ -587,6 +608,7 @@ int dwj_destroy(dwj_engine *e) {
   cudaFree(e->counter);
   cudaFree(e->part_scratch);
   cudaFree(e->xchg_cursor);
+  cudaFree(e->xpart_cursor);
   cudaFree(e->region_build);
   cudaFree(e->region_probe);
   cudaFree(e->stage);
@@ -709,8 +731,8 @@ int dwj_partition(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_
   DeviceGuard g(e->cfg.device);
   cudaStream_t s = (cudaStream_t)stream;
   CU(cudaEventRecord(e->ev_part[0], s));
-  const int rc = e->W == 4 ? partition_impl<4>(e, d_keys, d_vals, n_rows, lg, false, d_out_keys, d_out_vals, d_offsets, s)
-                           : partition_impl<8>(e, d_keys, d_vals, n_rows, lg, false, d_out_keys, d_out_vals, d_offsets, s);
+  const int rc = e->W == 4 ? partition_impl<4>(e, d_keys, d_vals, n_rows, lg, dwj::PART_BY_HASH, d_out_keys, d_out_vals, d_offsets, s)
+                           : partition_impl<8>(e, d_keys, d_vals, n_rows, lg, dwj::PART_BY_HASH, d_out_keys, d_out_vals, d_offsets, s);
   if (rc) return rc;
   CU(cudaEventRecord(e->ev_part[1], s));
   e->have_part = true;
@@ -725,8 +747,8 @@ int dwj_partition_hist(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint3
   uint32_t lg = 0;
   while ((1u << lg) < n_parts) ++lg;
   DeviceGuard g(e->cfg.device);
-  return e->W == 4 ? partition_hist_impl<4>(e, d_keys, n_rows, lg, d_counts, (cudaStream_t)stream)
-                   : partition_hist_impl<8>(e, d_keys, n_rows, lg, d_counts, (cudaStream_t)stream);
+  return e->W == 4 ? partition_hist_impl<4>(e, d_keys, n_rows, lg, dwj::PART_BY_HASH, 0, d_counts, (cudaStream_t)stream)
+                   : partition_hist_impl<8>(e, d_keys, n_rows, lg, dwj::PART_BY_HASH, 0, d_counts, (cudaStream_t)stream);
 }
 
 int dwj_partition_scatter_to(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_parts,
@@ -747,6 +769,81 @@ int dwj_partition_scatter_to(dwj_engine *e, const void *d_keys, const void *d_va
   if (rc) return rc;
   CU(cudaEventRecord(e->ev_part[1], s));
   e->have_part = true;
+  return DWJ_OK;
+}
+
+// ---- exchange partition folded with the receiver's region grouping ------------------------------------------------------
+namespace {
+int xpart_bits(const dwj_engine *e, uint32_t n_ranks, uint32_t *rank_bits, uint32_t *fold_bits) {
+  if (n_ranks == 0 || (n_ranks & (n_ranks - 1)) || n_ranks > (uint32_t)dwj::PART_MAX)
+    return fail(DWJ_ERR_INVALID, "n_ranks must be a power of two in [1, %d], got %u", dwj::PART_MAX, n_ranks);
+  uint32_t rb = 0, max_bits = 0;
+  while ((1u << rb) < n_ranks) ++rb;
+  while ((1u << (max_bits + 1)) <= (uint32_t)dwj::PART_MAX) ++max_bits;
+  *rank_bits = rb;
+  *fold_bits = rb + e->region_bits <= max_bits ? e->region_bits : 0;     // all region bits or none
+  return DWJ_OK;
+}
+}  // namespace
+
+uint32_t dwj_xpart_regions(const dwj_engine *e, uint32_t n_ranks) {
+  uint32_t rb = 0, fb = 0;
+  if (!e || xpart_bits(e, n_ranks, &rb, &fb)) return 0;
+  return 1u << fb;
+}
+
+int dwj_xpart_hist(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t n_ranks, uint64_t *d_counts, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  uint32_t rb = 0, fb = 0;
+  if (int rc = xpart_bits(e, n_ranks, &rb, &fb)) return rc;
+  if (!d_counts || (n_rows && !d_keys)) return fail(DWJ_ERR_INVALID, "null partition argument");
+  DeviceGuard g(e->cfg.device);
+  const uint32_t mode = fb ? dwj::PART_BY_BOTH : dwj::PART_BY_HASH;
+  return e->W == 4 ? partition_hist_impl<4>(e, d_keys, n_rows, rb + fb, mode, rb, d_counts, (cudaStream_t)stream)
+                   : partition_hist_impl<8>(e, d_keys, n_rows, rb + fb, mode, rb, d_counts, (cudaStream_t)stream);
+}
+
+int dwj_xpart_scatter(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_ranks, const uint64_t *d_counts,
+                      void *d_out_keys, void *d_out_vals, uint64_t *d_offsets, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  uint32_t rb = 0, fb = 0;
+  if (int rc = xpart_bits(e, n_ranks, &rb, &fb)) return rc;
+  if (!d_counts || !d_offsets || (n_rows && (!d_keys || !d_out_keys))) return fail(DWJ_ERR_INVALID, "null partition argument");
+  if ((d_vals == nullptr) != (d_out_vals == nullptr)) return fail(DWJ_ERR_INVALID, "d_vals and d_out_vals must both be given or both be null");
+  DeviceGuard g(e->cfg.device);
+  const uint32_t mode = fb ? dwj::PART_BY_BOTH : dwj::PART_BY_HASH;
+  cudaStream_t s = (cudaStream_t)stream;
+  return e->W == 4 ? partition_scatter_counted_impl<4>(e, d_keys, d_vals, n_rows, rb + fb, mode, rb, d_counts, d_out_keys, d_out_vals, d_offsets, s)
+                   : partition_scatter_counted_impl<8>(e, d_keys, d_vals, n_rows, rb + fb, mode, rb, d_counts, d_out_keys, d_out_vals, d_offsets, s);
+}
+
+int dwj_build_grouped(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, const uint64_t *d_region_offsets, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  if (n_rows && (!d_keys || !d_vals)) return fail(DWJ_ERR_INVALID, "null build column");
+  if (n_rows > e->cfg.max_build_rows && (double)n_rows > 0.9 * (double)e->slots)
+    return fail(DWJ_ERR_CAPACITY, "%llu build rows exceed the table created for %llu", (unsigned long long)n_rows,
+                (unsigned long long)e->cfg.max_build_rows);
+  DeviceGuard g(e->cfg.device);
+  return e->W == 4 ? build_impl<4>(e, d_keys, d_vals, n_rows, (cudaStream_t)stream, true, d_region_offsets)
+                   : build_impl<8>(e, d_keys, d_vals, n_rows, (cudaStream_t)stream, true, d_region_offsets);
+}
+
+int dwj_probe_pairs_grouped(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *d_out_key, void *d_out_build_val,
+                            void *d_out_probe_val, uint64_t capacity, uint64_t *d_n_matches, uint64_t *n_matches, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  if (n_rows && (!d_keys || !d_vals)) return fail(DWJ_ERR_INVALID, "null probe column");
+  if (capacity && (!d_out_build_val || !d_out_probe_val)) return fail(DWJ_ERR_INVALID, "null output column");
+  DeviceGuard g(e->cfg.device);
+  return e->W == 4 ? probe_impl<4>(e, dwj::PROBE_PAIRS, d_keys, d_vals, n_rows, d_out_key, d_out_build_val, d_out_probe_val, nullptr, capacity, d_n_matches, n_matches, (cudaStream_t)stream, true)
+                   : probe_impl<8>(e, dwj::PROBE_PAIRS, d_keys, d_vals, n_rows, d_out_key, d_out_build_val, d_out_probe_val, nullptr, capacity, d_n_matches, n_matches, (cudaStream_t)stream, true);
+}
+
+int dwj_copy_many(dwj_engine *e, uint32_t n_copies, void *const *dsts, const void *const *srcs, const uint64_t *bytes, void *const *streams) {
+  if (int rc = check_engine(e)) return rc;
+  if (n_copies && (!dsts || !srcs || !bytes || !streams)) return fail(DWJ_ERR_INVALID, "null copy list");
+  DeviceGuard g(e->cfg.device);
+  for (uint32_t i = 0; i < n_copies; ++i)
+    if (bytes[i]) CU(cudaMemcpyAsync(dsts[i], srcs[i], bytes[i], cudaMemcpyDeviceToDevice, (cudaStream_t)streams[i]));
   return DWJ_OK;
 }
 

@@ -39,9 +39,8 @@ template <int W> struct PartitionArgs {
   uint64_t n;
   uint32_t log2_parts;
   uint64_t seed;
-  // by_bucket: partition id = (slot_hash(key) & bucket_mask) >> bucket_shift   (engine regions)
-  // else     : partition id = partition_of(key, log2_parts, seed)              (multi-GPU exchange)
-  uint32_t by_bucket;
+  uint32_t mode;         // PartMode, see part_id
+  uint32_t rank_bits;    // PART_BY_BOTH: bits of the destination rank (log2_parts = rank_bits + region bits)
   uint32_t bucket_shift;
   uint64_t bucket_mask;
   K *out_keys;
@@ -56,9 +55,17 @@ template <int W> struct PartitionArgs {
   unsigned long long *offsets;  // [parts + 1] result
 };
 
-template <int W, bool BY_BUCKET> DWJ_D uint32_t part_id(const PartitionArgs<W> &a, typename KeyT<W>::type key) {
-  if constexpr (BY_BUCKET) return (uint32_t)((slot_hash(key, a.seed) & a.bucket_mask) >> a.bucket_shift);
-  else return partition_of(key, a.log2_parts, a.seed);
+// Partition id of a key.  `mode` is uniform across the grid, so the branch costs one predicate.
+//   PART_BY_HASH   : top bits of the independent partition hash (multi-GPU exchange: destination rank)
+//   PART_BY_BUCKET : top bits of the bucket index (engine regions: the rows of a partition touch one table slice)
+//   PART_BY_BOTH   : destination rank (rank_bits) in the high bits, table region of the DESTINATION's table in the low
+//                    bits -- one pass that serves the exchange and the receiver's region grouping (dwj_xpart_*)
+enum PartMode : uint32_t { PART_BY_HASH = 0, PART_BY_BUCKET = 1, PART_BY_BOTH = 2 };
+template <int W> DWJ_D uint32_t part_id(const PartitionArgs<W> &a, typename KeyT<W>::type key) {
+  if (a.mode == PART_BY_BUCKET) return (uint32_t)((slot_hash(key, a.seed) & a.bucket_mask) >> a.bucket_shift);
+  if (a.mode == PART_BY_HASH) return partition_of(key, a.log2_parts, a.seed);
+  const uint32_t region_bits = a.log2_parts - a.rank_bits;
+  return partition_of(key, a.rank_bits, a.seed) << region_bits | (uint32_t)((slot_hash(key, a.seed) & a.bucket_mask) >> a.bucket_shift);
 }
 
 constexpr uint32_t PART_DEAD = 0xFFFFFFFFu;   // partition id of a lane past the end of the input
@@ -88,7 +95,7 @@ template <int BITS> DWJ_D unsigned match_partition(uint32_t p, unsigned alive) {
   return peers;
 }
 
-template <int W, bool BY_BUCKET, int THREADS, int HROWS>
+template <int W, int THREADS, int HROWS>
 __global__ void __launch_bounds__(THREADS) partition_hist_private_kernel(PartitionArgs<W> a) {
   using K = typename KeyT<W>::type;
   extern __shared__ __align__(16) unsigned char s_cnt[];      // [parts][THREADS] bytes
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(THREADS) partition_hist_private_kernel(Partiti
       for (int j = 0; j < HROWS; ++j) k[j] = load_stream(a.keys + base + (uint64_t)j * THREADS);
 #pragma unroll
       for (int j = 0; j < HROWS; ++j) {
-        unsigned char *c = mine + part_id<W, BY_BUCKET>(a, k[j]) * THREADS;
+        unsigned char *c = mine + part_id<W>(a, k[j]) * THREADS;
         *c = (unsigned char)(*c + 1);
       }
     } else {
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(THREADS) partition_hist_private_kernel(Partiti
       for (int j = 0; j < HROWS; ++j) {
         const uint64_t i = base + (uint64_t)j * THREADS;
         if (i < a.n) {
-          unsigned char *c = mine + part_id<W, BY_BUCKET>(a, load_stream(a.keys + i)) * THREADS;
+          unsigned char *c = mine + part_id<W>(a, load_stream(a.keys + i)) * THREADS;
           *c = (unsigned char)(*c + 1);
         }
       }
@@ -166,7 +173,7 @@ template <int W, int THREADS, int ITEMS> struct ScatterManySmem {
   static size_t bytes(uint32_t parts) { return (size_t)TILE * 2 * sizeof(K) + (size_t)parts * (8 + 4 * WARPS); }
 };
 
-template <int W, bool BY_BUCKET, int BITS, int THREADS, int ITEMS, bool FULL>
+template <int W, int BITS, int THREADS, int ITEMS, bool FULL>
 DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t rows, unsigned char *smem, unsigned int *s_scan) {
   using K = typename KeyT<W>::type;
   constexpr uint32_t TILE = THREADS * ITEMS;
@@ -197,7 +204,7 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t 
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const bool live = FULL || j * THREADS + threadIdx.x < rows;
-    const uint32_t p = part_id<W, BY_BUCKET>(a, k[j]);
+    const uint32_t p = part_id<W>(a, k[j]);
     const unsigned alive = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, live);
     const unsigned peers = match_partition<BITS>(p, alive);
     uint32_t old = 0;
@@ -268,14 +275,14 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t 
     const uint32_t s = j * THREADS + threadIdx.x;
     if (FULL || s < rows) {
       const K key = s_keys[s];
-      const long long dst = (long long)s + s_delta[part_id<W, BY_BUCKET>(a, key)];
+      const long long dst = (long long)s + s_delta[part_id<W>(a, key)];
       store_stream(a.out_keys + dst, key);
       if (with_vals) store_stream(a.out_vals + dst, s_vals[s]);
     }
   }
 }
 
-template <int W, bool BY_BUCKET, int BITS, int THREADS, int ITEMS, int MINB>
+template <int W, int BITS, int THREADS, int ITEMS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) partition_scatter_many_kernel(PartitionArgs<W> a) {
   constexpr uint32_t TILE = THREADS * ITEMS;
   extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -284,8 +291,8 @@ __global__ void __launch_bounds__(THREADS, MINB) partition_scatter_many_kernel(P
   for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const uint64_t base = tile * TILE;
     const uint32_t rows = (uint32_t)min((uint64_t)TILE, a.n - base);
-    if (rows == TILE) scatter_many_tile<W, BY_BUCKET, BITS, THREADS, ITEMS, true>(a, base, rows, s_dyn, s_scan);
-    else scatter_many_tile<W, BY_BUCKET, BITS, THREADS, ITEMS, false>(a, base, rows, s_dyn, s_scan);
+    if (rows == TILE) scatter_many_tile<W, BITS, THREADS, ITEMS, true>(a, base, rows, s_dyn, s_scan);
+    else scatter_many_tile<W, BITS, THREADS, ITEMS, false>(a, base, rows, s_dyn, s_scan);
     __syncthreads();                                // shared memory is reused by the next tile
   }
 }
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, MINB) partition_scatter_many_kernel(P
 // Per-partition counters are PACKED into one 64-bit register per thread: 8 fields x 8 bits, flushed to shared memory
 // before a field can overflow.  Interior tiles run a FULL = true instantiation of the tile body without any bounds
 // predicate (the 64-bit compares and the per-row branches they cause were most of the instruction stream at first).
-template <int W, bool BY_BUCKET, int HROWS, bool FULL>
+template <int W, int HROWS, bool FULL>
 DWJ_D void hist8_tile(const PartitionArgs<W> &a, uint64_t tile_base, unsigned long long &acc) {
   using K = typename KeyT<W>::type;
   const K *kp = a.keys + tile_base + threadIdx.x;
@@ -304,12 +311,12 @@ DWJ_D void hist8_tile(const PartitionArgs<W> &a, uint64_t tile_base, unsigned lo
   for (int j = 0; j < HROWS; ++j) k[j] = (FULL || j * PART_THREADS + threadIdx.x < rows) ? load_stream(kp + j * PART_THREADS) : (K)0;
 #pragma unroll
   for (int j = 0; j < HROWS; ++j) {
-    const unsigned long long one = 1ull << (8 * part_id<W, BY_BUCKET>(a, k[j]));
+    const unsigned long long one = 1ull << (8 * part_id<W>(a, k[j]));
     acc += (FULL || j * PART_THREADS + threadIdx.x < rows) ? one : 0ull;
   }
 }
 
-template <int W, bool BY_BUCKET, int HROWS>
+template <int W, int HROWS>
 __global__ void __launch_bounds__(PART_THREADS) partition_hist8_kernel(PartitionArgs<W> a) {
   __shared__ unsigned int s_hist[8];
   if (threadIdx.x < 8) s_hist[threadIdx.x] = 0;
@@ -328,8 +335,8 @@ __global__ void __launch_bounds__(PART_THREADS) partition_hist8_kernel(Partition
     pending = 0;
   };
   for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    if (tile * TILE + TILE <= a.n) hist8_tile<W, BY_BUCKET, HROWS, true>(a, tile * TILE, acc);
-    else hist8_tile<W, BY_BUCKET, HROWS, false>(a, tile * TILE, acc);
+    if (tile * TILE + TILE <= a.n) hist8_tile<W, HROWS, true>(a, tile * TILE, acc);
+    else hist8_tile<W, HROWS, false>(a, tile * TILE, acc);
     pending += HROWS;
     if (pending > 255 - HROWS) flush();
   }
@@ -356,7 +363,7 @@ template <int W, int ITEMS> struct Scatter8StagedSmem {
   K *dstv[8];
 };
 
-template <int W, bool BY_BUCKET, int ITEMS, bool FULL, bool WITH_VALS>
+template <int W, int ITEMS, bool FULL, bool WITH_VALS>
 DWJ_D void scatter8_staged_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t rows, Scatter8StagedSmem<W, ITEMS> &sm) {
   using K = typename KeyT<W>::type;
   constexpr int WARPS = PART_THREADS / 32;
@@ -376,7 +383,7 @@ DWJ_D void scatter8_staged_tile(const PartitionArgs<W> &a, uint64_t base, uint32
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const bool live = FULL || j * PART_THREADS + threadIdx.x < rows;
-    const uint32_t p = part_id<W, BY_BUCKET>(a, k[j]);
+    const uint32_t p = part_id<W>(a, k[j]);
     const unsigned alive = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, live);
     const unsigned b0 = __ballot_sync(0xffffffffu, p & 1u), b1 = __ballot_sync(0xffffffffu, p & 2u), b2 = __ballot_sync(0xffffffffu, p & 4u);
     const unsigned m0 = (p & 1u) ? b0 : ~b0, m1 = (p & 2u) ? b1 : ~b1, m2 = (p & 4u) ? b2 : ~b2;
@@ -430,7 +437,7 @@ DWJ_D void scatter8_staged_tile(const PartitionArgs<W> &a, uint64_t base, uint32
   __syncthreads();
 }
 
-template <int W, bool BY_BUCKET, int ITEMS>
+template <int W, int ITEMS>
 __global__ void __launch_bounds__(PART_THREADS, 3) partition_scatter8_staged_kernel(PartitionArgs<W> a) {
   constexpr uint32_t TILE = PART_THREADS * ITEMS;
   __shared__ Scatter8StagedSmem<W, ITEMS> sm;
@@ -445,11 +452,11 @@ __global__ void __launch_bounds__(PART_THREADS, 3) partition_scatter8_staged_ker
     const uint64_t base = tile * TILE;
     const uint32_t rows = (uint32_t)min((uint64_t)TILE, a.n - base);
     if (rows == TILE) {
-      if (with_vals) scatter8_staged_tile<W, BY_BUCKET, ITEMS, true, true>(a, base, rows, sm);
-      else scatter8_staged_tile<W, BY_BUCKET, ITEMS, true, false>(a, base, rows, sm);
+      if (with_vals) scatter8_staged_tile<W, ITEMS, true, true>(a, base, rows, sm);
+      else scatter8_staged_tile<W, ITEMS, true, false>(a, base, rows, sm);
     } else {
-      if (with_vals) scatter8_staged_tile<W, BY_BUCKET, ITEMS, false, true>(a, base, rows, sm);
-      else scatter8_staged_tile<W, BY_BUCKET, ITEMS, false, false>(a, base, rows, sm);
+      if (with_vals) scatter8_staged_tile<W, ITEMS, false, true>(a, base, rows, sm);
+      else scatter8_staged_tile<W, ITEMS, false, false>(a, base, rows, sm);
     }
   }
 }

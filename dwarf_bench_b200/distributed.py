@@ -262,3 +262,177 @@ class PipelinedP2PExchangeJoin(P2PExchangeJoin):
         self.stats.sent_rows += n_build + n_probe
         self.stats.recv_rows += nb + np_
         return nb, np_
+
+
+def plan_folded_exchange(counts, rank: int, regions: int, bounds):
+    """Layout of the folded exchange.  counts[src][batch][dst * regions + region] = rows of `batch` (0 = the build relation,
+    1.. = the probe chunks) that `src` sends to `dst` for table region `region`; bounds[c] = first row of probe chunk c
+    inside the sender's probe relation (len = chunks + 1).
+
+    Receive layout on every rank, per relation: batch-major (probe chunks one after the other), region-major inside a
+    batch, source-minor inside a region -- so a batch is one contiguous, region-grouped segment the local build / probe
+    can take as it is.  Returns a dict of numpy arrays:
+      src_row[b, p]    first row of run (batch b, partition p) inside THIS rank's send buffer of that relation
+      dst_row[b, p]    first row of that run inside the destination's receive buffer of that relation
+      rows[b, p]       its length
+      seg[b]           (first row, rows) of batch b inside THIS rank's receive buffer
+      region_off[b]    regions + 1 row offsets of batch b's regions, relative to seg[b][0]  (build look-ahead)
+    """
+    import numpy as np
+    c = np.asarray(counts, dtype=np.int64)                       # [world, batches, world * regions]
+    world, batches, parts = c.shape
+    assert parts == world * regions and len(bounds) == batches
+    c4 = c.reshape(world, batches, world, regions)               # [src, batch, dst, region]
+    per_region = c4.sum(axis=0)                                  # [batch, dst, region] rows arriving at dst for region
+    total = per_region.sum(axis=2)                               # [batch, dst]
+    seg_start = np.zeros_like(total)                             # batch 0 is its own relation; batches 1.. share one
+    if batches > 2:
+        seg_start[2:] = np.cumsum(total[1:-1], axis=0)
+    region_base = np.cumsum(per_region, axis=2) - per_region     # exclusive over regions
+    src_before = c4[:rank].sum(axis=0)                           # rows of lower-ranked sources, [batch, dst, region]
+    dst_row = (seg_start[:, :, None] + region_base + src_before).reshape(batches, parts)
+    mine = c[rank]                                               # [batch, parts]
+    src_row = np.cumsum(mine, axis=1) - mine
+    src_row[1:] += np.asarray(bounds[:-1], dtype=np.int64)[:, None]     # chunk c is scattered in place of its input rows
+    seg = [(int(seg_start[b, rank]), int(total[b, rank])) for b in range(batches)]
+    roff = np.zeros((batches, regions + 1), dtype=np.int64)
+    roff[:, 1:] = np.cumsum(per_region[:, rank, :], axis=1)
+    return {"src_row": src_row, "dst_row": dst_row, "rows": mine, "seg": seg, "region_off": roff}
+
+
+class FoldedExchangeJoin:
+    """Multi-GPU join whose exchange rides on the copy engines while the SMs partition and join.
+
+    One pass per relation (dwj_xpart_*) groups the rows by (destination rank, table region of the destination's table)
+    into a local send buffer; every (rank, region) run is then pushed into the destination's receive buffer -- peer
+    memory mapped through torch symmetric memory -- by plain device-to-device copies (dwj_copy_many: the copy engines
+    over NVLink, no SM time), laid out region-major.  The receiver therefore gets its rows already grouped by table
+    region and runs dwj_build_grouped / dwj_probe_pairs_grouped without the engine's own partition pass: the one
+    partition pass of the single-GPU join is the only one here too.  The probe relation travels in `chunks` pieces:
+    while the copy engines move piece c+1, the SMs scatter piece c+2 and probe piece c.  One all-gather of the count
+    matrix plans everything (the step's one host sync).
+
+    The result stays sharded and comes out as one segment per probe chunk: `self.segments[c]` = (first output row,
+    capacity) and `self.chunk_counts[c]` = rows written there (device).
+    """
+
+    def __init__(self, engine, device, dtype, cap_build: int, cap_probe: int, max_build: int, max_probe: int, chunks: int = 2,
+                 group=None, stream=None):
+        import numpy as np
+        import torch.distributed._symmetric_memory as symm_mem
+        self.np = np
+        self.e = engine
+        self.device = device
+        self.dtype = dtype
+        self.group = group or dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.regions = engine.xpart_regions(self.world)
+        if self.regions == 0:
+            raise ValueError(f"folded exchange needs a power-of-two world size, got {self.world}")
+        self.parts = self.world * self.regions
+        self.folded = self.regions > 1 and self.regions == engine.info()["radix_parts"]
+        self.chunks = max(1, int(chunks))
+        self.cap_build, self.cap_probe = int(cap_build), int(cap_probe)
+        self.item = torch.empty(0, dtype=dtype).element_size()
+        # receive side (symmetric, peer-mapped): [build keys | build payloads | probe keys | probe payloads]
+        self.buf = symm_mem.empty(2 * (self.cap_build + self.cap_probe), dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        bases = np.array([int(p) for p in self.hdl.buffer_ptrs], dtype=np.uint64)
+        off = [0, self.cap_build, 2 * self.cap_build, 2 * self.cap_build + self.cap_probe]
+        self.recv_ptr = [bases + np.uint64(o * self.item) for o in off]          # [column][rank] -> device pointer
+        self.cols = [self.buf[o:o + n] for o, n in zip(off, (self.cap_build, self.cap_build, self.cap_probe, self.cap_probe))]
+        # send side (local): the relations grouped by (destination, region)
+        self.send = [torch.empty(n, dtype=dtype, device=device) for n in (max_build, max_build, max_probe, max_probe)]
+        self.send_ptr = [np.uint64(t.data_ptr()) for t in self.send]
+        B = 1 + self.chunks
+        self.counts = torch.zeros(B, self.parts, dtype=torch.int64, device=device)
+        self.all_counts = torch.zeros(self.world, B, self.parts, dtype=torch.int64, device=device)
+        self.offsets = torch.zeros(B, self.parts + 1, dtype=torch.int64, device=device)     # scratch of dwj_xpart_scatter
+        self.region_off = torch.zeros(self.regions + 1, dtype=torch.int64, device=device)
+        self.region_off_host = torch.zeros(self.regions + 1, dtype=torch.int64).pin_memory()
+        self.chunk_counts = torch.zeros(self.chunks, dtype=torch.int64, device=device)
+        self.stream = stream
+        self.ps = torch.cuda.Stream(device=device)                        # partition (scatter) stream
+        self.xs = torch.cuda.Stream(device=device)                        # barrier stream
+        self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(self.world)]
+        self.copy_stream_ids = np.array([s.cuda_stream for s in self.copy_streams], dtype=np.uint64)
+        self.ev_plan = torch.cuda.Event()
+        self.ev_scattered = [torch.cuda.Event() for _ in range(B)]
+        self.ev_copied = [[torch.cuda.Event() for _ in range(self.world)] for _ in range(B)]
+        self.ev_arrived = [torch.cuda.Event() for _ in range(B)]
+        self.ev_step_done = torch.cuda.Event()
+        self.segments = []
+        self.stats = ExchangeStats()
+
+    def join(self, build_keys, build_vals, n_build, probe_keys, probe_vals, n_probe, out_key, out_build, out_probe,
+             capacity, d_count):
+        np, e, w, C, B = self.np, self.e, self.world, self.chunks, 1 + self.chunks
+        cs = self.stream if self.stream is not None else torch.cuda.current_stream()
+        bounds = [n_probe * c // C for c in range(C + 1)]
+        rel = [(build_keys, build_vals, 0, n_build, 0)] + [(probe_keys, probe_vals, bounds[c], bounds[c + 1] - bounds[c], 2)
+                                                           for c in range(C)]           # (keys, vals, first row, rows, column)
+        for b, (k, _, r0, n, _) in enumerate(rel):
+            e.xpart_hist(k[r0:], n, w, self.counts[b], stream=cs)
+        with torch.cuda.stream(cs):
+            # Ordered behind this rank's previous local join: once every rank's counts are in, every receive buffer is free.
+            dist.all_gather_into_tensor(self.all_counts.view(-1), self.counts.view(-1), group=self.group)
+            self.ev_plan.record(cs)
+            m = self.all_counts.cpu().numpy()                             # the one host sync of the step
+        plan = plan_folded_exchange(m, self.rank, self.regions, bounds)
+        nb, np_ = plan["seg"][0][1], sum(n for _, n in plan["seg"][1:])
+        if nb > self.cap_build or np_ > self.cap_probe:
+            raise RuntimeError(f"receive buffers too small: {nb}/{self.cap_build} build rows, {np_}/{self.cap_probe} probe rows")
+        if np_ > capacity:
+            raise RuntimeError(f"output capacity {capacity} below the {np_} probe rows this rank receives")
+        self.region_off_host.copy_(torch.from_numpy(plan["region_off"][0]))
+        dest_of_part = np.repeat(np.arange(w), self.regions)
+        item = np.uint64(self.item)
+        # ---- partition stream: one scatter per batch; copy streams: its runs, one stream per destination ----------------
+        self.ps.wait_event(self.ev_plan)
+        for b, (k, v, r0, n, col) in enumerate(rel):
+            e.xpart_scatter(k[r0:], v[r0:], n, w, self.counts[b], self.send[col][r0:], self.send[col + 1][r0:], self.offsets[b],
+                            stream=self.ps)
+            self.ev_scattered[b].record(self.ps)
+            rows = plan["rows"][b].astype(np.uint64)
+            src = plan["src_row"][b].astype(np.uint64) * item
+            dst = plan["dst_row"][b].astype(np.uint64) * item
+            copies_d, copies_s, copies_b, copies_st = [], [], [], []
+            for cc in (col, col + 1):
+                copies_d.append(self.recv_ptr[cc][dest_of_part] + dst)
+                copies_s.append(self.send_ptr[cc] + src)
+                copies_b.append(rows * item)
+                copies_st.append(self.copy_stream_ids[dest_of_part])
+            for st in self.copy_streams:
+                st.wait_event(self.ev_scattered[b])
+            e.copy_many_arrays(np.concatenate(copies_d), np.concatenate(copies_s), np.concatenate(copies_b), np.concatenate(copies_st))
+            for d, st in enumerate(self.copy_streams):
+                self.ev_copied[b][d].record(st)
+                self.xs.wait_event(self.ev_copied[b][d])
+            with torch.cuda.stream(self.xs):
+                self.hdl.barrier(channel=0)                               # every rank's runs of this batch have landed everywhere
+            self.ev_arrived[b].record(self.xs)
+        # ---- compute stream: local build, then one probe per received chunk ---------------------------------------------
+        cs.wait_event(self.ev_arrived[0])
+        with torch.cuda.stream(cs):
+            self.region_off.copy_(self.region_off_host, non_blocking=True)
+        if self.folded:
+            e.build_grouped(self.cols[0], self.cols[1], nb, self.region_off, stream=cs)
+        else:                   # regions not folded into the exchange: the engine groups the received rows itself
+            e.build(self.cols[0], self.cols[1], nb, stream=cs)
+        probe = e.probe_pairs_grouped if self.folded else e.probe_pairs
+        for c, (row0, rows) in enumerate(plan["seg"][1:]):
+            cs.wait_event(self.ev_arrived[1 + c])
+            probe(self.cols[2][row0:], self.cols[3][row0:], rows, None if out_key is None else out_key[row0:],
+                  out_build[row0:], out_probe[row0:], rows, d_n_matches=self.chunk_counts[c:], sync=False, stream=cs)
+        with torch.cuda.stream(cs):
+            torch.sum(self.chunk_counts, dim=0, keepdim=True, out=d_count)
+        # the send buffers may be rewritten once this step's copies are done: the next scatter waits for them
+        for st in self.copy_streams:
+            self.ps.wait_stream(st)
+        self.segments = plan["seg"][1:]
+        sent_local = int(plan["rows"][:, self.rank * self.regions:(self.rank + 1) * self.regions].sum())
+        self.stats.sent_rows += n_build + n_probe
+        self.stats.recv_rows += nb + np_
+        self.stats.sent_bytes_remote += 2 * self.item * (n_build + n_probe - sent_local)
+        return nb, np_

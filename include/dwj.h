@@ -27,8 +27,9 @@
  *                        implicit sycl::buffer H2D/D2H copies made explicit
  *   dwj_timings          HashJoinResult{build_time,probe_time,host_time,
  *                        kernel_time}  common/result.hpp:11-33
- *   dwj_partition        new (no reference counterpart): radix partition on
- *                        the key hash for the multi-GPU exchange
+ *   dwj_partition*, dwj_xpart_*, dwj_*_grouped, dwj_copy_many
+ *                        new (no reference counterpart): radix partition on
+ *                        the key hash and exchange plumbing for the multi-GPU join
  */
 #ifndef DWJ_H
 #define DWJ_H
@@ -193,6 +194,34 @@ DWJ_API int dwj_partition_hist(dwj_engine *e, const void *d_keys, uint64_t n_row
 DWJ_API int dwj_partition_scatter_to(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_parts,
                              void *const *dst_keys, void *const *dst_vals, const uint64_t *dst_row_offsets,
                              void *stream);
+
+/* ---- exchange partition folded with the receiver's region grouping (multi-GPU) ----------------------------------
+ * One pass over a relation that serves BOTH the exchange and the receiver's L2-region grouping: partition id =
+ * destination rank (independent hash, as dwj_partition) x table region of the destination's table (top bits of the
+ * bucket index; every rank's engine must be created with the same table size and hash seed).  Partitions are ordered
+ * rank-major, region-minor.  dwj_xpart_regions() says how many regions are folded in: the engine's region count when
+ * n_ranks x regions <= 512, else 1 (plain rank partition; the receiver then groups by region itself with dwj_build /
+ * dwj_probe_pairs).  Usage: dwj_xpart_hist -> exchange the counts -> dwj_xpart_scatter into a send buffer -> copy
+ * every (rank, region) run into the destination's receive buffer laid out region-major (dwj_copy_many or any
+ * transport) -> dwj_build_grouped / dwj_probe_pairs_grouped on the received rows, which skip the engine's own
+ * partition pass. */
+DWJ_API uint32_t dwj_xpart_regions(const dwj_engine *e, uint32_t n_ranks);
+/* d_counts[n_ranks * regions] (uint64, device). */
+DWJ_API int dwj_xpart_hist(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t n_ranks, uint64_t *d_counts, void *stream);
+/* Second half: d_counts as written by dwj_xpart_hist for the same rows; d_offsets[n_ranks * regions + 1] (device). */
+DWJ_API int dwj_xpart_scatter(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_ranks,
+                      const uint64_t *d_counts, void *d_out_keys, void *d_out_vals, uint64_t *d_offsets, void *stream);
+/* dwj_build / dwj_probe_pairs for rows that are ALREADY grouped by table region (region-major): no partition pass.
+ * d_region_offsets (device, regions + 1 uint64 row offsets, may be NULL) enables the build's L2 look-ahead. */
+DWJ_API int dwj_build_grouped(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows,
+                      const uint64_t *d_region_offsets, void *stream);
+DWJ_API int dwj_probe_pairs_grouped(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *d_out_key,
+                            void *d_out_build_val, void *d_out_probe_val, uint64_t capacity, uint64_t *d_n_matches,
+                            uint64_t *n_matches, void *stream);
+/* n_copies device-to-device copies (local or peer memory mapped into this process), copy i on streams[i]: the copy
+ * engines carry the exchange while the SMs partition and join.  Asynchronous. */
+DWJ_API int dwj_copy_many(dwj_engine *e, uint32_t n_copies, void *const *dsts, const void *const *srcs, const uint64_t *bytes,
+                  void *const *streams);
 
 /* Partition id of one key on the host (same function the kernels use) -- lets callers and tests
  * reason about placement without a device. */

@@ -140,3 +140,43 @@ def test_plan_chunked_exchange_layout():
                 first, rows = plans[d][1][c]
                 mine = [sp for sp in spans if sp[2] == c]
                 assert first == mine[0][0] and first + rows == mine[-1][1] == first + sum(counts[s][c][d] for s in range(world))
+
+
+def test_plan_folded_exchange_layout():
+    """Folded exchange: at every destination each relation's receive buffer is tiled exactly by the (batch, region,
+    source) runs in that order; a batch is one contiguous segment; region offsets are the per-region totals; the
+    sender's runs tile its send buffer chunk by chunk."""
+    from dwarf_bench_b200.distributed import plan_folded_exchange
+    rng = np.random.default_rng(9)
+    for world, regions, chunks in ((2, 4, 1), (8, 8, 2), (4, 1, 3)):
+        parts = world * regions
+        counts = rng.integers(0, 300, (world, 1 + chunks, parts))
+        # rows of every probe chunk at every source (the sender scatters chunk c in place of its input rows)
+        bounds = [[0] + list(np.cumsum(counts[s, 1:].sum(axis=1))) for s in range(world)]      # chunks + 1 entries
+        plans = [plan_folded_exchange(counts, r, regions, bounds[r]) for r in range(world)]
+        for d in range(world):
+            for relation in (range(0, 1), range(1, 1 + chunks)):
+                spans = []
+                for b in relation:
+                    for g in range(regions):
+                        for s in range(world):
+                            p = d * regions + g
+                            spans.append((int(plans[s]["dst_row"][b, p]), int(counts[s, b, p]), b, g, s))
+                pos = 0
+                for start, rows, b, g, s in spans:                    # already in (batch, region, source) order
+                    assert start == pos, (world, regions, chunks, d, b, g, s)
+                    pos += rows
+                for b in relation:
+                    first, rows = plans[d]["seg"][b]
+                    mine = [sp for sp in spans if sp[2] == b]
+                    assert first == mine[0][0] and rows == sum(sp[1] for sp in mine)
+                    roff = plans[d]["region_off"][b]
+                    assert roff[0] == 0 and roff[-1] == rows
+                    for g in range(regions):
+                        assert roff[g + 1] - roff[g] == sum(sp[1] for sp in mine if sp[3] == g)
+        for s in range(world):
+            src = plans[s]["src_row"]
+            assert (src[0] == np.cumsum(counts[s, 0]) - counts[s, 0]).all()
+            for c in range(chunks):
+                assert src[1 + c, 0] == bounds[s][c]
+                assert (np.diff(src[1 + c]) == counts[s, 1 + c, :-1]).all()

@@ -450,3 +450,94 @@ def test_partition_scatter_to_destinations(dwj, wide, parts):
             seen.append(rows)
         np.testing.assert_array_equal(np.sort(np.concatenate(seen)), np.arange(n))
         assert np.bincount(pid, minlength=parts).sum() == 5000
+
+
+@pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("world,chunks", [(4, 2), (8, 1), (2, 3)])
+def test_folded_exchange_single_gpu(dwj, oracle, monkeypatch, wide, world, chunks):
+    """The folded exchange (dwj_xpart_hist / dwj_xpart_scatter / dwj_copy_many / dwj_build_grouped /
+    dwj_probe_pairs_grouped + plan_folded_exchange) with `world` VIRTUAL ranks on one GPU: every virtual rank
+    partitions its own rows, the planned copies fill every destination's receive buffer, every destination joins what
+    it received, and the union of the destinations' results is the oracle's join of the whole input."""
+    from dwarf_bench_b200 import capi
+    from dwarf_bench_b200.distributed import plan_folded_exchange
+    monkeypatch.setenv("DWJ_PARTITION_MIN_MB", "0")
+    monkeypatch.setenv("DWJ_REGION_MB", "0.125")              # force table regions at test size
+    rng = np.random.default_rng(11 + world + chunks + wide)
+    dt = np.uint64 if wide else np.uint32
+    tdt = torch.int64 if wide else torch.int32
+    item = dt().itemsize
+    nb, npr = 40_001, 90_007                                   # rows per virtual rank
+    all_ak = np.unique(rng.integers(1, 2**31, world * nb * 2).astype(dt))[:world * nb]
+    rng.shuffle(all_ak)
+    all_av = rng.integers(0, 2**31, len(all_ak)).astype(dt)
+    all_bk = np.concatenate([all_ak[rng.integers(0, len(all_ak), world * npr - 1000)], rng.integers(2**31, 2**32 - 2, 1000).astype(dt)])
+    rng.shuffle(all_bk)
+    all_bv = np.arange(len(all_bk), dtype=dt)
+    cap = int(len(all_ak) / world * 1.5)
+    with dwj.Engine(cap, key_bytes=item, flags=dwj.FLAG_UNIQUE_BUILD_KEYS, hash_seed=42) as e:
+        regions = e.xpart_regions(world)
+        assert regions == e.info()["radix_parts"] and regions >= 2 and world * regions <= 512
+        parts = world * regions
+        B = 1 + chunks
+        src = []                                               # per virtual rank: inputs, send buffers, counts
+        counts = torch.zeros(world, B, parts, dtype=torch.int64, device="cuda")
+        for s in range(world):
+            ak, av = dev(all_ak[s * nb:(s + 1) * nb]), dev(all_av[s * nb:(s + 1) * nb])
+            bk, bv = dev(all_bk[s * npr:(s + 1) * npr]), dev(all_bv[s * npr:(s + 1) * npr])
+            bounds = [npr * c // chunks for c in range(chunks + 1)]
+            send = [torch.empty(nb, dtype=tdt, device="cuda"), torch.empty(nb, dtype=tdt, device="cuda"),
+                    torch.empty(npr, dtype=tdt, device="cuda"), torch.empty(npr, dtype=tdt, device="cuda")]
+            offs = torch.zeros(parts + 1, dtype=torch.int64, device="cuda")
+            e.xpart_hist(ak, nb, world, counts[s, 0])
+            e.xpart_scatter(ak, av, nb, world, counts[s, 0], send[0], send[1], offs)
+            for c in range(chunks):
+                r0, n = bounds[c], bounds[c + 1] - bounds[c]
+                e.xpart_hist(bk[r0:], n, world, counts[s, 1 + c])
+                e.xpart_scatter(bk[r0:], bv[r0:], n, world, counts[s, 1 + c], send[2][r0:], send[3][r0:], offs)
+            src.append((send, bounds))
+        torch.cuda.synchronize()
+        m = counts.cpu().numpy()
+        assert m[:, 0].sum() == world * nb and m[:, 1:].sum() == world * npr
+        # a sampled key sits in the (rank, region) run its hash says; rank part == dwj_partition_of
+        send0 = host(src[0][0][0], dt)
+        run_start = np.cumsum(m[0, 0]) - m[0, 0]
+        for p in rng.integers(0, parts, 40):
+            if m[0, 0, p]:
+                key = int(send0[run_start[p]])
+                assert capi.partition_of(key, item, world, 42) == p // regions
+        plans = [plan_folded_exchange(m, r, regions, src[r][1]) for r in range(world)]
+        recv_rows_b = [plans[d]["seg"][0][1] for d in range(world)]
+        recv_rows_p = [sum(n for _, n in plans[d]["seg"][1:]) for d in range(world)]
+        recv = [[torch.full((max(n, 1),), -1, dtype=tdt, device="cuda") for n in (recv_rows_b[d], recv_rows_b[d], recv_rows_p[d], recv_rows_p[d])]
+                for d in range(world)]
+        stream = torch.cuda.current_stream()
+        for s in range(world):
+            send, _ = src[s]
+            pl = plans[s]
+            copies = []
+            for b in range(B):
+                col = 0 if b == 0 else 2
+                for p in range(parts):
+                    d = p // regions
+                    for cc in (col, col + 1):
+                        copies.append((recv[d][cc].data_ptr() + int(pl["dst_row"][b, p]) * item,
+                                       send[cc].data_ptr() + int(pl["src_row"][b, p]) * item, int(pl["rows"][b, p]) * item, stream))
+            e.copy_many(copies)
+        torch.cuda.synchronize()
+        got_rows = []
+        for d in range(world):
+            roff = torch.from_numpy(plans[d]["region_off"][0]).cuda()
+            e.build_grouped(recv[d][0], recv[d][1], recv_rows_b[d], roff)
+            ok, oa, ob = (empty_like_dev(recv_rows_p[d], dt) for _ in range(3))
+            total = 0
+            for (row0, rows) in plans[d]["seg"][1:]:
+                mm = e.probe_pairs_grouped(recv[d][2][row0:], recv[d][3][row0:], rows, ok[total:], oa[total:], ob[total:], rows)
+                total += mm
+            torch.cuda.synchronize()
+            got_rows.append(tuple(host(t, dt)[:total] for t in (ok, oa, ob)))
+    got = pyoracle.canonical_rows(*(np.concatenate([g[i] for g in got_rows]) for i in range(3)))
+    want = oracle.sort_join(all_ak, all_av, all_bk, all_bv)
+    assert len(got[0]) == len(want[0]) == world * npr - 1000
+    for w_, g_ in zip(want, got):
+        np.testing.assert_array_equal(w_, g_)
