@@ -61,6 +61,11 @@ def parse_args():
                          "nccl = local partition + NCCL all-to-all-v")
     ap.add_argument("--exchange-chunks", type=int, default=2,
                     help="fold / p2p exchange: the probe relation travels in this many pieces")
+    ap.add_argument("--exchange-transport", default="ce", choices=["sm", "ce"],
+                    help="fold exchange: runs pushed into peer memory by the copy engines (ce) or by a small kernel (sm)")
+    ap.add_argument("--exchange-layout", default="blocked", choices=["blocked", "region"],
+                    help="fold exchange: receive area source-major (one large transfer per peer, segmented build/probe) or region-major")
+    ap.add_argument("--push-ctas", type=int, default=64, help="fold exchange, transport sm: CTAs of the push kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-probe-rows", type=int, default=1 << 26)
@@ -305,8 +310,11 @@ def main():
             try:
                 if args.exchange == "fold":
                     xj = FoldedExchangeJoin(eng, device, tdt, cap_rows, out_cap, n_build, n_probe, chunks=args.exchange_chunks,
-                                            stream=stream)
-                    exchange_used = (f"one (rank x {xj.regions} table regions) partition pass, copy-engine pushes into peer memory "
+                                            stream=stream, transport=args.exchange_transport, push_ctas=args.push_ctas,
+                                            layout=args.exchange_layout)
+                    how = f"a {args.push_ctas}-CTA push kernel" if args.exchange_transport == "sm" else "copy-engine pushes"
+                    how += " (one block per peer, receiver walks the blocks region by region)" if args.exchange_layout == "blocked" else " (one run per peer and region)"
+                    exchange_used = (f"one (rank x {xj.regions} table regions) partition pass, {how} into peer memory "
                                      f"(NVLink), probe relation in {xj.chunks} chunks overlapped with the local probes, counts by one all-gather")
                 elif args.exchange_chunks > 1:
                     xj = PipelinedP2PExchangeJoin(eng, device, tdt, cap_rows, out_cap, chunks=args.exchange_chunks, stream=stream)
@@ -491,7 +499,7 @@ def main():
                        "api": "dwj_join_host (pinned host columns in, compacted rows out)",
                        "pcie_gbs": (h2d + d2h) / (e2e_ms * 1e-3) / 1e9}
         del hb_k, hb_v, hp_k, hp_v, ho_b, ho_p
-    elif world > 1:
+    elif world > 1 and not args.no_e2e:
         # Multi-GPU e2e: per-rank host staging around the same step (inputs H2D, local result D2H).
         hb_k, hb_v = inp.build_keys.cpu().pin_memory(), inp.build_vals.cpu().pin_memory()
         hp_k, hp_v = inp.probe_keys.cpu().pin_memory(), inp.probe_vals.cpu().pin_memory()
@@ -523,6 +531,8 @@ def main():
         except Exception as ex:            # the checker libraries are optional at run time; say so rather than fail
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
 
+    if world > 1 and getattr(xj, "trace", False):
+        print(f"[rank {rank}] exchange timeline (ms from step start): {json.dumps(xj.last_trace)}", file=sys.stderr)
     if rank == 0:
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()

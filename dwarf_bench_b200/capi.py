@@ -26,7 +26,7 @@ SYMBOLS = ("dwj_abi_version", "dwj_last_error", "dwj_create", "dwj_destroy", "dw
            "dwj_probe_aligned", "dwj_probe_contains", "dwj_probe_pairs", "dwj_probe_count", "dwj_timings",
            "dwj_join_host", "dwj_partition", "dwj_partition_hist", "dwj_partition_scatter_to", "dwj_partition_of",
            "dwj_xpart_regions", "dwj_xpart_hist", "dwj_xpart_scatter", "dwj_build_grouped", "dwj_probe_pairs_grouped",
-           "dwj_copy_many")
+           "dwj_copy_many", "dwj_push_runs", "dwj_build_segments", "dwj_probe_pairs_segments")
 
 
 class DwjError(RuntimeError):
@@ -103,10 +103,13 @@ def load_library():
     lib.dwj_xpart_regions.argtypes = [vp, u32]
     lib.dwj_xpart_regions.restype = u32
     lib.dwj_xpart_hist.argtypes = [vp, vp, u64, u32, vp, vp]
-    lib.dwj_xpart_scatter.argtypes = [vp, vp, vp, u64, u32, vp, vp, vp, vp, vp]
+    lib.dwj_xpart_scatter.argtypes = [vp, vp, vp, u64, u32, C.POINTER(u64), vp, vp, vp]
     lib.dwj_build_grouped.argtypes = [vp, vp, vp, u64, vp, vp]
     lib.dwj_probe_pairs_grouped.argtypes = [vp, vp, vp, u64, vp, vp, vp, u64, vp, C.POINTER(u64), vp]
     lib.dwj_copy_many.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(vp)]
+    lib.dwj_push_runs.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), u32, vp]
+    lib.dwj_build_segments.argtypes = [vp, vp, vp, u32, C.POINTER(u64), C.POINTER(u64), u32, vp]
+    lib.dwj_probe_pairs_segments.argtypes = [vp, vp, vp, u32, C.POINTER(u64), C.POINTER(u64), vp, vp, vp, u64, vp, C.POINTER(u64), vp]
     for name in SYMBOLS:
         f = getattr(lib, name)
         if name not in ("dwj_last_error", "dwj_partition_of", "dwj_xpart_regions"):
@@ -239,10 +242,13 @@ class Engine:
     def xpart_hist(self, d_keys, n_rows: int, n_ranks: int, d_counts, stream=None) -> None:
         self._check(self.lib.dwj_xpart_hist(self._h, _ptr(d_keys), n_rows, n_ranks, _ptr(d_counts), _stream(stream)))
 
-    def xpart_scatter(self, d_keys, d_vals, n_rows: int, n_ranks: int, d_counts, d_out_keys, d_out_vals, d_offsets,
-                      stream=None) -> None:
-        self._check(self.lib.dwj_xpart_scatter(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, n_ranks, _ptr(d_counts),
-                                               _ptr(d_out_keys), _ptr(d_out_vals), _ptr(d_offsets), _stream(stream)))
+    def xpart_scatter(self, d_keys, d_vals, n_rows: int, n_ranks: int, start_rows, d_out_keys, d_out_vals, stream=None) -> None:
+        """start_rows: numpy/sequence of n_ranks * regions row offsets relative to d_out_keys / d_out_vals."""
+        import numpy as np
+        st = np.ascontiguousarray(start_rows, dtype=np.uint64)
+        self._check(self.lib.dwj_xpart_scatter(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, n_ranks,
+                                               st.ctypes.data_as(C.POINTER(C.c_uint64)), _ptr(d_out_keys), _ptr(d_out_vals),
+                                               _stream(stream)))
 
     def build_grouped(self, d_keys, d_vals, n_rows: int, d_region_offsets=None, stream=None) -> None:
         self._check(self.lib.dwj_build_grouped(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, _ptr(d_region_offsets),
@@ -257,6 +263,26 @@ class Engine:
         self._check(rc)
         return int(n.value) if sync else None
 
+    def build_segments(self, d_keys, d_vals, seg_first_row, seg_rows, segments_per_region: int = 0, stream=None) -> None:
+        import numpy as np
+        f, r = (np.ascontiguousarray(a, dtype=np.uint64) for a in (seg_first_row, seg_rows))
+        u64p = C.POINTER(C.c_uint64)
+        self._check(self.lib.dwj_build_segments(self._h, _ptr(d_keys), _ptr(d_vals), len(f), f.ctypes.data_as(u64p),
+                                                r.ctypes.data_as(u64p), segments_per_region, _stream(stream)))
+
+    def probe_pairs_segments(self, d_keys, d_vals, seg_first_row, seg_rows, d_out_key, d_out_build_val, d_out_probe_val,
+                             capacity: int, d_n_matches=None, sync: bool = True, stream=None):
+        import numpy as np
+        f, r = (np.ascontiguousarray(a, dtype=np.uint64) for a in (seg_first_row, seg_rows))
+        u64p = C.POINTER(C.c_uint64)
+        n = C.c_uint64(0)
+        rc = self.lib.dwj_probe_pairs_segments(self._h, _ptr(d_keys), _ptr(d_vals), len(f), f.ctypes.data_as(u64p),
+                                               r.ctypes.data_as(u64p), _ptr(d_out_key), _ptr(d_out_build_val),
+                                               _ptr(d_out_probe_val), capacity, _ptr(d_n_matches), C.byref(n) if sync else None,
+                                               _stream(stream))
+        self._check(rc)
+        return int(n.value) if sync else None
+
     def copy_many(self, copies) -> None:
         """copies: list of (dst pointer, src pointer, bytes, stream); device-to-device, possibly to peer memory."""
         n = len(copies)
@@ -268,6 +294,14 @@ class Engine:
         st = (C.c_void_p * n)(*[_stream(c[3]) for c in copies])
         self._check(self.lib.dwj_copy_many(self._h, n, d, s, b, st))
 
+
+    def push_runs(self, dsts, srcs, rows, n_ctas: int = 0, stream=None) -> None:
+        """dwj_push_runs from three equally long numpy uint64 arrays (pointers, pointers, row counts)."""
+        import numpy as np
+        arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in (dsts, srcs, rows)]
+        vpp, u64p = C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)
+        self._check(self.lib.dwj_push_runs(self._h, len(arrs[0]), arrs[0].ctypes.data_as(vpp), arrs[1].ctypes.data_as(vpp),
+                                           arrs[2].ctypes.data_as(u64p), n_ctas, _stream(stream)))
 
     def copy_many_arrays(self, dsts, srcs, nbytes, streams) -> None:
         """dwj_copy_many from four equally long numpy uint64 arrays (no per-copy Python work)."""

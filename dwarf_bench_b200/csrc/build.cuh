@@ -35,6 +35,11 @@ template <int W> struct BuildArgs {
   const unsigned long long *offsets;   // [regions + 1], device
   uint32_t regions;
   uint64_t slice_bytes;
+  // Segmented input (table.cuh): n_segs > 0 => rows come from segs[], `n` is the number of TILES, and segments
+  // [r * segs_per_region, (r+1) * segs_per_region) belong to table region r (look-ahead).
+  const Seg *segs;
+  uint32_t n_segs;
+  uint32_t segs_per_region;
 };
 
 DWJ_D void store_slot(void *table, uint64_t b, uint32_t i, uint32_t k, uint32_t v) {
@@ -67,6 +72,22 @@ DWJ_D void prefetch_next_region(const BuildArgs<W> &a, uint64_t row0, uint64_t t
   for (uint64_t l = (l0 >> 3) + threadIdx.x; l < ((l1 + 7) >> 3); l += blockDim.x) prefetch_l2(fb + (l << 7));
 }
 
+// Same look-ahead for segmented input: tile `tile` of segment `si` lies in region si / segs_per_region, whose tiles are
+// [first_unit of its first segment, first_unit of the next region's first segment).
+template <int W>
+DWJ_D void prefetch_next_region_segs(const BuildArgs<W> &a, uint32_t si, uint64_t tile) {
+  const uint32_t region = si / a.segs_per_region;
+  if (region + 1 >= a.regions) return;
+  const uint64_t t0 = __ldg(&a.segs[region * a.segs_per_region].first_unit);
+  const uint64_t t1 = __ldg(&a.segs[(region + 1) * a.segs_per_region].first_unit);
+  const uint64_t len = max(t1 - t0, (uint64_t)1), lines = a.slice_bytes >> 7;
+  const uint64_t l0 = (tile - t0) * lines / len, l1 = min((tile - t0 + 1) * lines / len, lines);
+  const char *tb = (const char *)a.table + (uint64_t)(region + 1) * a.slice_bytes;
+  const char *fb = (const char *)a.fill + (uint64_t)(region + 1) * (a.slice_bytes >> 3);
+  for (uint64_t l = l0 + threadIdx.x; l < l1; l += blockDim.x) prefetch_l2(tb + (l << 7));
+  for (uint64_t l = (l0 >> 3) + threadIdx.x; l < ((l1 + 7) >> 3); l += blockDim.x) prefetch_l2(fb + (l << 7));
+}
+
 // A CTA takes one tile of 256*ROWS CONSECUTIVE rows, so the rows in flight across the GPU form one contiguous window
 // of the input: when the engine has grouped the input by table region that window touches one L2-resident slice of
 // the table.  The tickets of a thread's ROWS rows are in flight together, and so are the hops of the rows that
@@ -78,17 +99,25 @@ __global__ void __launch_bounds__(256) build_kernel(BuildArgs<W> a) {
   using K = typename KeyT<W>::type;
   constexpr uint32_t SLOTS = Bucket<W>::SLOTS;
   constexpr uint64_t TILE = 256ull * ROWS;
-  const uint64_t tiles = (a.n + TILE - 1) / TILE;
+  const uint64_t tiles = a.n_segs ? a.n : (a.n + TILE - 1) / TILE;
   for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    if (a.regions > 1) prefetch_next_region<W>(a, tile * TILE, TILE);
-    const uint64_t base = tile * TILE + threadIdx.x;
+    uint64_t base = tile * TILE + threadIdx.x, limit = a.n;
+    if (a.n_segs) {
+      const uint32_t si = find_segment(a.segs, a.n_segs, tile);
+      const Seg sg = a.segs[si];
+      base = sg.phys_row + (tile - sg.first_unit) * TILE + threadIdx.x;
+      limit = sg.phys_row + sg.rows;
+      if (a.regions > 1) prefetch_next_region_segs<W>(a, si, tile);
+    } else if (a.regions > 1) {
+      prefetch_next_region<W>(a, tile * TILE, TILE);
+    }
     K k[ROWS], v[ROWS];
     uint64_t b[ROWS];
     uint32_t t[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const uint64_t i = base + (uint64_t)r * 256;
-      const bool live = i < a.n;
+      const bool live = i < limit;
       k[r] = live ? load_stream(a.keys + i) : ~(K)0;       // the reserved key (and a row past the end) is never stored
       v[r] = live ? load_stream(a.vals + i) : ~(K)0;
     }

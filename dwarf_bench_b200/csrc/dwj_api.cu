@@ -83,6 +83,17 @@ struct dwj_engine {
   uint64_t tile_state_cap = 0;                 // in descriptors
   unsigned long long *counter = nullptr;       // device uint64 used when the caller passes no d_n_matches
   unsigned long long *part_scratch = nullptr;  // hist[PART_MAX] + cursor[PART_MAX] + region offsets[PART_MAX + 1]
+  // segmented input (dwj_*_segments): ring of segment tables, and the caller's list while a call is in flight
+  dwj::Seg *seg_tables = nullptr, *seg_tables_host = nullptr;
+  cudaEvent_t seg_done[8]{};
+  uint32_t seg_calls = 0;
+  const uint64_t *pending_seg_first = nullptr, *pending_seg_rows = nullptr;
+  uint32_t pending_segs = 0, pending_segs_per_region = 0;
+  // dwj_push_runs: a ring of PUSH_SLOTS run tables (device + pinned staging), so the host never waits for a table that
+  // is still queued behind earlier work on the stream
+  dwj::PushRun *push_runs = nullptr, *push_runs_host = nullptr;
+  cudaEvent_t push_done[8]{};
+  uint32_t push_calls = 0;
   unsigned long long *xpart_cursor = nullptr;  // PART_MAX cursors of dwj_xpart_scatter (own scratch: may run beside a local join)
   unsigned long long *xchg_cursor = nullptr;   // 8 cursors of dwj_partition_scatter_to: its own scratch, so an exchange
                                                // on one stream can overlap a build/probe (region partition) on another
@@ -243,19 +254,24 @@ template <int W> int partition_hist_impl(dwj_engine *e, const void *keys, uint64
   return hist_launch<W>(e, a, s);
 }
 
-// Scatter with the histogram already known (d_counts from partition_hist_impl, same mode): offsets from the counts,
-// then the scatter -- the second half of a partition whose first half fed the exchange plan.
+// Scatter with the layout planned by the caller: the rows of partition p go to out[h_start_rows[p] ...] (host array).
+// The second half of a partition whose histogram fed an exchange plan; partitions may land anywhere inside the
+// allocation `ok` / `ov` point into (e.g. some in a send buffer, some straight in a receive buffer).
 template <int W>
-int partition_scatter_counted_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, uint32_t log2_parts, uint32_t mode,
-                                   uint32_t rank_bits, const uint64_t *d_counts, void *ok, void *ov, uint64_t *d_offsets, cudaStream_t s) {
+int partition_scatter_planned_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, uint32_t log2_parts, uint32_t mode,
+                                   uint32_t rank_bits, const uint64_t *h_start_rows, void *ok, void *ov, cudaStream_t s) {
   using K = typename dwj::KeyT<W>::type;
   dwj::PartitionArgs<W> a = partition_args<W>(e, keys, vals, n, log2_parts, mode, rank_bits);
   a.out_keys = (K *)ok;
   a.out_vals = (K *)ov;
-  a.hist = (unsigned long long *)d_counts;
   a.cursor = e->xpart_cursor;
-  a.offsets = (unsigned long long *)d_offsets;
-  CU(launch(e, dwj::partition_offsets_kernel<W>, dim3(1), dim3(32), s, a, false));
+  // pageable source: staged before the call returns, so the caller's array may be reused at once
+  CU(cudaMemcpyAsync(a.cursor, h_start_rows, sizeof(uint64_t) << log2_parts, cudaMemcpyHostToDevice, s));
+  if (log2_parts == 0 && n) {       // one partition: a copy to the planned position
+    CU(cudaMemcpyAsync((K *)ok + h_start_rows[0], keys, n * W, cudaMemcpyDeviceToDevice, s));
+    if (vals) CU(cudaMemcpyAsync((K *)ov + h_start_rows[0], vals, n * W, cudaMemcpyDeviceToDevice, s));
+    return DWJ_OK;
+  }
   return scatter_launch<W>(e, a, s);
 }
 
@@ -306,6 +322,32 @@ int ensure_region_buffer(void **buf, uint64_t *cap_rows, uint64_t rows, int W, c
   return DWJ_OK;
 }
 
+// Segment table of the pending dwj_*_segments call for a kernel whose work unit is `unit_rows` rows: uploads
+// {first unit, first row, rows} per segment (+ a closing entry) through a ring of pinned / device tables.  The caller
+// records e->seg_done[slot] after the kernel that reads the table.
+constexpr uint32_t SEG_SLOTS = 8, SEG_MAX = dwj::PART_MAX + 1;
+int upload_segments(dwj_engine *e, uint64_t unit_rows, cudaStream_t s, const dwj::Seg **d_out, uint64_t *total_units, uint32_t *slot_out) {
+  if (!e->seg_tables) {
+    CU(cudaMalloc((void **)&e->seg_tables, SEG_SLOTS * SEG_MAX * sizeof(dwj::Seg)));
+    CU(cudaHostAlloc((void **)&e->seg_tables_host, SEG_SLOTS * SEG_MAX * sizeof(dwj::Seg), cudaHostAllocDefault));
+    for (auto &ev : e->seg_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  const uint32_t slot = e->seg_calls++ % SEG_SLOTS;
+  if (e->seg_calls > SEG_SLOTS) CU(cudaEventSynchronize(e->seg_done[slot]));
+  dwj::Seg *h = e->seg_tables_host + slot * SEG_MAX, *d = e->seg_tables + slot * SEG_MAX;
+  unsigned long long units = 0;
+  for (uint32_t i = 0; i < e->pending_segs; ++i) {
+    h[i] = dwj::Seg{units, e->pending_seg_first[i], e->pending_seg_rows[i]};
+    units += (e->pending_seg_rows[i] + unit_rows - 1) / unit_rows;
+  }
+  h[e->pending_segs] = dwj::Seg{units, 0, 0};
+  CU(cudaMemcpyAsync(d, h, (e->pending_segs + 1) * sizeof(dwj::Seg), cudaMemcpyHostToDevice, s));
+  *d_out = d;
+  *total_units = units;
+  *slot_out = slot;
+  return DWJ_OK;
+}
+
 // grouped: the caller's rows are already grouped by table region (dwj_build_grouped); `grouped_offsets` (device,
 // regions + 1 entries, may be null) are the regions' row ranges for the look-ahead.
 template <int W> int build_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, cudaStream_t s, bool grouped = false,
@@ -341,10 +383,22 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
       a.slice_bytes = e->table_bytes >> e->region_bits;
     }
     constexpr int ROWS = 4;
-    const uint64_t tiles = (n + 256ull * ROWS - 1) / (256ull * ROWS);
+    uint64_t tiles = (n + 256ull * ROWS - 1) / (256ull * ROWS);
+    uint32_t seg_slot = 0;
+    if (e->pending_segs) {              // dwj_build_segments: rows come from a segment list, region by region
+      if (int rc = upload_segments(e, 256ull * ROWS, s, &a.segs, &tiles, &seg_slot)) return rc;
+      a.n = tiles;
+      a.n_segs = e->pending_segs;
+      a.segs_per_region = e->pending_segs_per_region;
+      if (e->region_bits && !no_ahead && a.segs_per_region && a.n_segs == (a.segs_per_region << e->region_bits)) {
+        a.regions = 1u << e->region_bits;
+        a.slice_bytes = e->table_bytes >> e->region_bits;
+      }
+    }
     CU(cudaEventRecord(e->ev_buildk[0], s));
-    CU(launch(e, dwj::build_kernel<W, ROWS>, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(256), s, a, true));
+    if (tiles) CU(launch(e, dwj::build_kernel<W, ROWS>, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(256), s, a, true));
     CU(cudaEventRecord(e->ev_buildk[1], s));
+    if (e->pending_segs) CU(cudaEventRecord(e->seg_done[seg_slot], s));
     e->launches_build += 2;
   }
   CU(cudaEventRecord(e->ev_build[1], s));
@@ -402,7 +456,12 @@ template <int W, bool ORDERED, bool WITH_KEY, int SHAPE>
 int staged_launch_shape(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
   constexpr StagedShape S = W == 4 ? STAGED_SHAPES_4[SHAPE] : STAGED_SHAPES_8[SHAPE];
   constexpr uint64_t CHUNK = (uint64_t)S.warps * 32 * S.items * S.sub;
-  const uint64_t chunks = (a.n + CHUNK - 1) / CHUNK;
+  uint64_t chunks = (a.n + CHUNK - 1) / CHUNK;
+  uint32_t seg_slot = 0;
+  if (e->pending_segs) {                // dwj_probe_pairs_segments
+    if (int rc = upload_segments(e, CHUNK, s, &a.segs, &chunks, &seg_slot)) return rc;
+    a.n_segs = e->pending_segs;
+  }
   a.num_tiles = chunks;
   e->launches_probe = 0;
   if (ORDERED) {
@@ -434,6 +493,7 @@ int staged_launch_shape(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
     CU(cudaLaunchKernelEx(&lc, kern, a));
     e->launches_probe++;
   }
+  if (e->pending_segs) CU(cudaEventRecord(e->seg_done[seg_slot], s));
   return DWJ_OK;
 }
 
@@ -609,6 +669,14 @@ int dwj_destroy(dwj_engine *e) {
   cudaFree(e->part_scratch);
   cudaFree(e->xchg_cursor);
   cudaFree(e->xpart_cursor);
+  cudaFree(e->push_runs);
+  if (e->push_runs_host) cudaFreeHost(e->push_runs_host);
+  cudaFree(e->seg_tables);
+  if (e->seg_tables_host) cudaFreeHost(e->seg_tables_host);
+  for (auto &ev : e->seg_done)
+    if (ev) cudaEventDestroy(ev);
+  for (auto &ev : e->push_done)
+    if (ev) cudaEventDestroy(ev);
   cudaFree(e->region_build);
   cudaFree(e->region_probe);
   cudaFree(e->stage);
@@ -803,18 +871,18 @@ int dwj_xpart_hist(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t 
                    : partition_hist_impl<8>(e, d_keys, n_rows, rb + fb, mode, rb, d_counts, (cudaStream_t)stream);
 }
 
-int dwj_xpart_scatter(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_ranks, const uint64_t *d_counts,
-                      void *d_out_keys, void *d_out_vals, uint64_t *d_offsets, void *stream) {
+int dwj_xpart_scatter(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_ranks, const uint64_t *start_rows,
+                      void *d_out_keys, void *d_out_vals, void *stream) {
   if (int rc = check_engine(e)) return rc;
   uint32_t rb = 0, fb = 0;
   if (int rc = xpart_bits(e, n_ranks, &rb, &fb)) return rc;
-  if (!d_counts || !d_offsets || (n_rows && (!d_keys || !d_out_keys))) return fail(DWJ_ERR_INVALID, "null partition argument");
+  if (!start_rows || (n_rows && (!d_keys || !d_out_keys))) return fail(DWJ_ERR_INVALID, "null partition argument");
   if ((d_vals == nullptr) != (d_out_vals == nullptr)) return fail(DWJ_ERR_INVALID, "d_vals and d_out_vals must both be given or both be null");
   DeviceGuard g(e->cfg.device);
   const uint32_t mode = fb ? dwj::PART_BY_BOTH : dwj::PART_BY_HASH;
   cudaStream_t s = (cudaStream_t)stream;
-  return e->W == 4 ? partition_scatter_counted_impl<4>(e, d_keys, d_vals, n_rows, rb + fb, mode, rb, d_counts, d_out_keys, d_out_vals, d_offsets, s)
-                   : partition_scatter_counted_impl<8>(e, d_keys, d_vals, n_rows, rb + fb, mode, rb, d_counts, d_out_keys, d_out_vals, d_offsets, s);
+  return e->W == 4 ? partition_scatter_planned_impl<4>(e, d_keys, d_vals, n_rows, rb + fb, mode, rb, start_rows, d_out_keys, d_out_vals, s)
+                   : partition_scatter_planned_impl<8>(e, d_keys, d_vals, n_rows, rb + fb, mode, rb, start_rows, d_out_keys, d_out_vals, s);
 }
 
 int dwj_build_grouped(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, const uint64_t *d_region_offsets, void *stream) {
@@ -838,12 +906,100 @@ int dwj_probe_pairs_grouped(dwj_engine *e, const void *d_keys, const void *d_val
                    : probe_impl<8>(e, dwj::PROBE_PAIRS, d_keys, d_vals, n_rows, d_out_key, d_out_build_val, d_out_probe_val, nullptr, capacity, d_n_matches, n_matches, (cudaStream_t)stream, true);
 }
 
+namespace {
+struct PendingSegs {       // scope guard: the segment list is only valid during one call
+  dwj_engine *e;
+  PendingSegs(dwj_engine *e_, uint32_t n, const uint64_t *first, const uint64_t *rows, uint32_t per_region) : e(e_) {
+    e->pending_segs = n;
+    e->pending_seg_first = first;
+    e->pending_seg_rows = rows;
+    e->pending_segs_per_region = per_region;
+  }
+  ~PendingSegs() { e->pending_segs = 0; }
+};
+int check_segments(uint32_t n, const uint64_t *first, const uint64_t *rows, uint64_t *total) {
+  if (n == 0 || n > (uint32_t)dwj::PART_MAX) return fail(DWJ_ERR_INVALID, "between 1 and %d segments, got %u", dwj::PART_MAX, n);
+  if (!first || !rows) return fail(DWJ_ERR_INVALID, "null segment list");
+  *total = 0;
+  for (uint32_t i = 0; i < n; ++i) *total += rows[i];
+  return DWJ_OK;
+}
+}  // namespace
+
+int dwj_build_segments(dwj_engine *e, const void *d_keys, const void *d_vals, uint32_t n_segments, const uint64_t *seg_first_row,
+                       const uint64_t *seg_rows, uint32_t segments_per_region, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  uint64_t total = 0;
+  if (int rc = check_segments(n_segments, seg_first_row, seg_rows, &total)) return rc;
+  if (total && (!d_keys || !d_vals)) return fail(DWJ_ERR_INVALID, "null build column");
+  if (total > e->cfg.max_build_rows && (double)total > 0.9 * (double)e->slots)
+    return fail(DWJ_ERR_CAPACITY, "%llu build rows exceed the table created for %llu", (unsigned long long)total,
+                (unsigned long long)e->cfg.max_build_rows);
+  DeviceGuard g(e->cfg.device);
+  PendingSegs ps(e, total ? n_segments : 0, seg_first_row, seg_rows, segments_per_region);
+  return e->W == 4 ? build_impl<4>(e, d_keys, d_vals, total, (cudaStream_t)stream, true, nullptr)
+                   : build_impl<8>(e, d_keys, d_vals, total, (cudaStream_t)stream, true, nullptr);
+}
+
+int dwj_probe_pairs_segments(dwj_engine *e, const void *d_keys, const void *d_vals, uint32_t n_segments, const uint64_t *seg_first_row,
+                             const uint64_t *seg_rows, void *d_out_key, void *d_out_build_val, void *d_out_probe_val, uint64_t capacity,
+                             uint64_t *d_n_matches, uint64_t *n_matches, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  uint64_t total = 0;
+  if (int rc = check_segments(n_segments, seg_first_row, seg_rows, &total)) return rc;
+  if (!(e->cfg.flags & DWJ_FLAG_UNIQUE_BUILD_KEYS))
+    return fail(DWJ_ERR_INVALID, "segmented probe is implemented for DWJ_FLAG_UNIQUE_BUILD_KEYS engines");
+  if (total && (!d_keys || !d_vals)) return fail(DWJ_ERR_INVALID, "null probe column");
+  if (capacity && (!d_out_build_val || !d_out_probe_val)) return fail(DWJ_ERR_INVALID, "null output column");
+  DeviceGuard g(e->cfg.device);
+  PendingSegs ps(e, total ? n_segments : 0, seg_first_row, seg_rows, 0);
+  return e->W == 4 ? probe_impl<4>(e, dwj::PROBE_PAIRS, d_keys, d_vals, total, d_out_key, d_out_build_val, d_out_probe_val, nullptr, capacity, d_n_matches, n_matches, (cudaStream_t)stream, true)
+                   : probe_impl<8>(e, dwj::PROBE_PAIRS, d_keys, d_vals, total, d_out_key, d_out_build_val, d_out_probe_val, nullptr, capacity, d_n_matches, n_matches, (cudaStream_t)stream, true);
+}
+
 int dwj_copy_many(dwj_engine *e, uint32_t n_copies, void *const *dsts, const void *const *srcs, const uint64_t *bytes, void *const *streams) {
   if (int rc = check_engine(e)) return rc;
   if (n_copies && (!dsts || !srcs || !bytes || !streams)) return fail(DWJ_ERR_INVALID, "null copy list");
   DeviceGuard g(e->cfg.device);
   for (uint32_t i = 0; i < n_copies; ++i)
     if (bytes[i]) CU(cudaMemcpyAsync(dsts[i], srcs[i], bytes[i], cudaMemcpyDeviceToDevice, (cudaStream_t)streams[i]));
+  return DWJ_OK;
+}
+
+int dwj_push_runs(dwj_engine *e, uint32_t n_runs, void *const *dsts, const void *const *srcs, const uint64_t *rows, uint32_t n_ctas,
+                  void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  constexpr uint32_t MAX_RUNS = 4 * dwj::PART_MAX;
+  if (n_runs > MAX_RUNS) return fail(DWJ_ERR_INVALID, "at most %u runs per call, got %u", MAX_RUNS, n_runs);
+  if (n_runs && (!dsts || !srcs || !rows)) return fail(DWJ_ERR_INVALID, "null run list");
+  DeviceGuard g(e->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  constexpr uint32_t PUSH_SLOTS = 8;
+  if (!e->push_runs) {
+    CU(cudaMalloc((void **)&e->push_runs, PUSH_SLOTS * MAX_RUNS * sizeof(dwj::PushRun)));
+    CU(cudaHostAlloc((void **)&e->push_runs_host, PUSH_SLOTS * MAX_RUNS * sizeof(dwj::PushRun), cudaHostAllocDefault));
+    for (auto &ev : e->push_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  const uint32_t slot = e->push_calls++ % PUSH_SLOTS;
+  if (e->push_calls > PUSH_SLOTS) CU(cudaEventSynchronize(e->push_done[slot]));   // the slot's previous kernel (8 calls ago) is done
+  dwj::PushRun *h_runs = e->push_runs_host + slot * MAX_RUNS, *d_runs = e->push_runs + slot * MAX_RUNS;
+  constexpr int ELEMS = 16;
+  const unsigned long long block_rows = 256ull * ELEMS;
+  unsigned long long blocks = 0;
+  uint32_t n = 0;
+  for (uint32_t i = 0; i < n_runs; ++i) {
+    if (!rows[i]) continue;
+    if (!dsts[i] || !srcs[i]) return fail(DWJ_ERR_INVALID, "null pointer in run %u", i);
+    h_runs[n++] = dwj::PushRun{dsts[i], srcs[i], rows[i], blocks};
+    blocks += (rows[i] + block_rows - 1) / block_rows;
+  }
+  if (!n) return DWJ_OK;
+  CU(cudaMemcpyAsync(d_runs, h_runs, n * sizeof(dwj::PushRun), cudaMemcpyHostToDevice, s));
+  const unsigned grid = (unsigned)std::min<unsigned long long>(blocks, n_ctas ? n_ctas : 64u);
+  if (e->W == 4) dwj::push_runs_kernel<4, ELEMS><<<grid, 256, 0, s>>>(d_runs, n, blocks);
+  else dwj::push_runs_kernel<8, ELEMS><<<grid, 256, 0, s>>>(d_runs, n, blocks);
+  CU(cudaEventRecord(e->push_done[slot], s));
+  CU(cudaGetLastError());
   return DWJ_OK;
 }
 

@@ -33,6 +33,8 @@ template <int W> struct ProbeArgs {
   unsigned long long *n_matches;   // PAIRS / COUNT (device)
   unsigned long long *tile_state;  // PAIRS: [0] = ticket counter, [1..] = lookback descriptors
   uint64_t num_tiles;
+  const Seg *segs;                 // segmented input (table.cuh), staged PAIRS kernel only; n_segs == 0: rows [0, n)
+  uint32_t n_segs;
 };
 
 // ---- decoupled look-back ----------------------------------------------------------------------
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeA
 // of the relation: no bounds predicates at all (interior rounds; the 64-bit compares and predicated loads of the
 // guarded version were a third of the instruction stream).
 template <int W, bool WITH_KEY, int ITEMS, bool FULL>
-DWJ_D void staged_round(const ProbeArgs<W> &a, uint64_t base, unsigned lane, unsigned lt,
+DWJ_D void staged_round(const ProbeArgs<W> &a, uint64_t base, uint64_t limit, unsigned lane, unsigned lt,
                         typename KeyT<W>::type *wb, typename KeyT<W>::type *wp, typename KeyT<W>::type *wk, uint32_t &staged) {
   using K = typename KeyT<W>::type;
   constexpr K SENTINEL = ~(K)0;
@@ -326,7 +328,7 @@ DWJ_D void staged_round(const ProbeArgs<W> &a, uint64_t base, unsigned lane, uns
   Bucket<W> bk[ITEMS];
   uint64_t hb[ITEMS];
   const K *kp = a.keys + base + lane, *vp = a.vals + base + lane;
-  const uint32_t rows = FULL ? 0u : (uint32_t)min((uint64_t)(32 * ITEMS), a.n - base);
+  const uint32_t rows = FULL ? 0u : (uint32_t)min((uint64_t)(32 * ITEMS), limit - base);
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const bool live = FULL || j * 32 + lane < rows;
@@ -370,21 +372,27 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) probe_pairs_staged_kernel(Pr
   if (t == 0) s_chunk = ORDERED ? atomicAdd(a.tile_state, 1ull) : (unsigned long long)blockIdx.x;
   __syncthreads();
   const uint64_t chunk = s_chunk;
-  const uint64_t warp_base = chunk * CHUNK + (uint64_t)warp * WROWS;
+  uint64_t chunk_base = chunk * CHUNK, limit = a.n;
+  if (a.n_segs) {                                   // CTA-uniform: the chunk's rows live in one segment of the allocation
+    const Seg sg = a.segs[find_segment(a.segs, a.n_segs, chunk)];
+    chunk_base = sg.phys_row + (chunk - sg.first_unit) * CHUNK;
+    limit = sg.phys_row + sg.rows;
+  }
+  const uint64_t warp_base = chunk_base + (uint64_t)warp * WROWS;
   K *wb = s_build + warp * WROWS, *wp = s_probe + warp * WROWS, *wk = s_key + warp * WROWS;
   const unsigned lt = (1u << lane) - 1u;
   uint32_t staged = 0;                              // warp-uniform running count
 
-  if (warp_base + WROWS <= a.n) {                   // warp-uniform: the whole slice is inside the relation
+  if (warp_base + WROWS <= limit) {                 // warp-uniform: the whole slice is inside the relation / segment
 #pragma unroll 1
     for (int sub = 0; sub < SUB; ++sub)
-      staged_round<W, WITH_KEY, ITEMS, true>(a, warp_base + (uint64_t)sub * (32 * ITEMS), lane, lt, wb, wp, wk, staged);
+      staged_round<W, WITH_KEY, ITEMS, true>(a, warp_base + (uint64_t)sub * (32 * ITEMS), limit, lane, lt, wb, wp, wk, staged);
   } else {
 #pragma unroll 1
     for (int sub = 0; sub < SUB; ++sub) {
       const uint64_t base = warp_base + (uint64_t)sub * (32 * ITEMS);
-      if (base >= a.n) break;
-      staged_round<W, WITH_KEY, ITEMS, false>(a, base, lane, lt, wb, wp, wk, staged);
+      if (base >= limit) break;
+      staged_round<W, WITH_KEY, ITEMS, false>(a, base, limit, lane, lt, wb, wp, wk, staged);
     }
   }
   if (lane == 0) s_wtot[warp] = staged;

@@ -168,6 +168,27 @@ template <int W> DWJ_D Bucket<W> load_bucket_cg(const void *table, uint64_t b) {
   return load_bucket_cg(table, b, (Bucket<W> *)nullptr);
 }
 
+// ---- segmented input ---------------------------------------------------------------------------------------------------
+// A relation may be handed to the build / probe kernels as a LIST OF SEGMENTS of one allocation instead of one
+// contiguous range (dwj_build_segments / dwj_probe_pairs_segments): the multi-GPU exchange delivers every source
+// rank's rows as one block (one large copy-engine transfer per peer), region-grouped inside the block, and the
+// kernels walk the blocks region by region -- segment (region g, source s) after (g, s-1) -- without a regrouping
+// pass.  A kernel's work unit (tile / chunk) never straddles two segments: segment i owns units [first_unit[i],
+// first_unit[i+1]).
+struct Seg {
+  unsigned long long first_unit;   // first tile / chunk of this segment (entry n_segs holds the total)
+  unsigned long long phys_row;     // first row inside the allocation
+  unsigned long long rows;
+};
+DWJ_D uint32_t find_segment(const Seg *segs, uint32_t n_segs, unsigned long long unit) {
+  uint32_t lo = 0, hi = n_segs;                     // segs[lo].first_unit <= unit < segs[hi].first_unit
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&segs[mid].first_unit) <= unit) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 // ---- streaming column access ---------------------------------------------------------------
 template <class T> DWJ_D T load_stream(const T *p) { return __ldcs(p); }   // ld.global.cs: evict-first
 template <class T> DWJ_D void store_stream(T *p, T v) { __stcs(p, v); }    // st.global.cs

@@ -300,24 +300,69 @@ def plan_folded_exchange(counts, rank: int, regions: int, bounds):
     return {"src_row": src_row, "dst_row": dst_row, "rows": mine, "seg": seg, "region_off": roff}
 
 
+def plan_blocked_exchange(counts, rank: int, regions: int, bounds):
+    """Layout of the folded exchange with ONE BLOCK PER SOURCE at the receiver (few, large transfers).  Arguments as
+    plan_folded_exchange.  Receive layout per relation: batch-major, then source-major; inside a source's block the
+    runs are in the sender's own order, i.e. region-major.  The receiver walks a batch region by region through the
+    segment list (region 0 of source 0, region 0 of source 1, ..., region 1 of source 0, ...).  Returns numpy arrays:
+      src_row[b, p]      first row of run (batch b, partition p) inside THIS rank's send area (as plan_folded_exchange)
+      own_row[b, g]      first row, inside this rank's receive area, of its OWN rows of region g (scattered in place)
+      block_src[b, d], block_dst[b, d], block_rows[b, d]   the one transfer to destination d
+      seg[b]             (first row, rows) of batch b inside this rank's receive area
+      seg_first[b], seg_rows[b]   the batch's segment list in walking order (regions * world entries)
+    """
+    import numpy as np
+    c = np.asarray(counts, dtype=np.int64)
+    world, batches, parts = c.shape
+    assert parts == world * regions and len(bounds) == batches
+    c4 = c.reshape(world, batches, world, regions)               # [src, batch, dst, region]
+    blocks = c4.sum(axis=3)                                      # [src, batch, dst] rows of the block src -> dst
+    total = blocks.sum(axis=0)                                   # [batch, dst]
+    seg_start = np.zeros_like(total)
+    if batches > 2:
+        seg_start[2:] = np.cumsum(total[1:-1], axis=0)
+    before = np.cumsum(blocks, axis=0) - blocks                  # [src, batch, dst] rows of lower-ranked sources
+    block_start = seg_start[None, :, :] + before                 # [src, batch, dst] where src's block starts at dst
+    mine = c[rank]
+    src_row = np.cumsum(mine, axis=1) - mine
+    src_row[1:] += np.asarray(bounds[:-1], dtype=np.int64)[:, None]
+    in_block = np.cumsum(c4, axis=3) - c4                        # [src, batch, dst, region] offset of a run in its block
+    own_row = block_start[rank, :, rank][:, None] + in_block[rank, :, rank, :]
+    seg_first = (block_start[:, :, rank][:, :, None] + in_block[:, :, rank, :]).transpose(1, 2, 0).reshape(batches, -1)
+    seg_rows = c4[:, :, rank, :].transpose(1, 2, 0).reshape(batches, -1)       # [batch, region * world + src]
+    return {"src_row": src_row, "own_row": own_row, "block_src": src_row[:, ::regions], "block_dst": block_start[rank],
+            "block_rows": blocks[rank], "rows": mine, "seg": [(int(seg_start[b, rank]), int(total[b, rank])) for b in range(batches)],
+            "seg_first": seg_first, "seg_rows": seg_rows}
+
+
 class FoldedExchangeJoin:
     """Multi-GPU join whose exchange rides on the copy engines while the SMs partition and join.
 
-    One pass per relation (dwj_xpart_*) groups the rows by (destination rank, table region of the destination's table)
-    into a local send buffer; every (rank, region) run is then pushed into the destination's receive buffer -- peer
-    memory mapped through torch symmetric memory -- by plain device-to-device copies (dwj_copy_many: the copy engines
-    over NVLink, no SM time), laid out region-major.  The receiver therefore gets its rows already grouped by table
-    region and runs dwj_build_grouped / dwj_probe_pairs_grouped without the engine's own partition pass: the one
-    partition pass of the single-GPU join is the only one here too.  The probe relation travels in `chunks` pieces:
-    while the copy engines move piece c+1, the SMs scatter piece c+2 and probe piece c.  One all-gather of the count
-    matrix plans everything (the step's one host sync).
+    One pass per relation (dwj_xpart_*) groups the rows by (destination rank, table region of the destination's table).
+    The runs of the OTHER ranks' partitions go to a local send area and are then pushed into the destination's receive
+    area -- peer memory mapped through torch symmetric memory -- by plain device-to-device copies (dwj_copy_many: the
+    copy engines over NVLink, no SM time); this rank's own partitions are scattered straight into its receive area.
+    The receive layout is region-major, so the receiver gets its rows already grouped by table region and runs
+    dwj_build_grouped / dwj_probe_pairs_grouped without the engine's own partition pass: the one partition pass of
+    the single-GPU join is the only one here too.  The probe relation travels in `chunks` pieces: while the copy
+    engines move piece c+1, the SMs scatter piece c+2 and probe piece c.  One all-gather of the count matrix plans
+    everything (the step's one host sync).
 
     The result stays sharded and comes out as one segment per probe chunk: `self.segments[c]` = (first output row,
     capacity) and `self.chunk_counts[c]` = rows written there (device).
     """
 
     def __init__(self, engine, device, dtype, cap_build: int, cap_probe: int, max_build: int, max_probe: int, chunks: int = 2,
-                 group=None, stream=None):
+                 group=None, stream=None, transport: str = "ce", push_ctas: int = 64, layout: str = "blocked"):
+        import os
+        # transport "ce": copy engines (dwj_copy_many); "sm": dwj_push_runs (a few CTAs store into peer memory).
+        # layout "blocked": one block per source at the receiver -> one large transfer per peer and relation, the
+        #   receiver walks the blocks region by region (dwj_*_segments).  The copy engines serialise copies at ~27 us
+        #   each, so this is the layout for them.  Needs an engine with DWJ_FLAG_UNIQUE_BUILD_KEYS.
+        # layout "region": the receive area itself is region-major -> ranks x regions runs per relation.
+        self.transport = transport
+        self.layout = layout
+        self.push_ctas = int(push_ctas)
         import numpy as np
         import torch.distributed._symmetric_memory as symm_mem
         self.np = np
@@ -334,34 +379,46 @@ class FoldedExchangeJoin:
         self.folded = self.regions > 1 and self.regions == engine.info()["radix_parts"]
         self.chunks = max(1, int(chunks))
         self.cap_build, self.cap_probe = int(cap_build), int(cap_probe)
+        self.max_build, self.max_probe = int(max_build), int(max_probe)
         self.item = torch.empty(0, dtype=dtype).element_size()
-        # receive side (symmetric, peer-mapped): [build keys | build payloads | probe keys | probe payloads]
-        self.buf = symm_mem.empty(2 * (self.cap_build + self.cap_probe), dtype=dtype, device=device)
+        # One symmetric (peer-mapped) allocation: a key block and a payload block of identical layout
+        #   [receive build | receive probe | send build | send probe]
+        # so that one scatter can write a partition's keys and payloads at the same row offset of either block: this
+        # rank's own partitions go straight into its receive area, the others into the send area.
+        self.row_off = [0, self.cap_build, self.cap_build + self.cap_probe, self.cap_build + self.cap_probe + self.max_build]
+        self.block_rows = self.row_off[3] + self.max_probe
+        self.buf = symm_mem.empty(2 * self.block_rows, dtype=dtype, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         bases = np.array([int(p) for p in self.hdl.buffer_ptrs], dtype=np.uint64)
-        off = [0, self.cap_build, 2 * self.cap_build, 2 * self.cap_build + self.cap_probe]
-        self.recv_ptr = [bases + np.uint64(o * self.item) for o in off]          # [column][rank] -> device pointer
-        self.cols = [self.buf[o:o + n] for o, n in zip(off, (self.cap_build, self.cap_build, self.cap_probe, self.cap_probe))]
-        # send side (local): the relations grouped by (destination, region)
-        self.send = [torch.empty(n, dtype=dtype, device=device) for n in (max_build, max_build, max_probe, max_probe)]
-        self.send_ptr = [np.uint64(t.data_ptr()) for t in self.send]
+        self.block_ptr = [bases, bases + np.uint64(self.block_rows * self.item)]          # [keys | payloads][rank]
+        self.blocks = [self.buf[:self.block_rows], self.buf[self.block_rows:]]
+        self.recv_build = [blk[self.row_off[0]:self.row_off[1]] for blk in self.blocks]   # [keys, payloads]
+        self.recv_probe = [blk[self.row_off[1]:self.row_off[2]] for blk in self.blocks]
         B = 1 + self.chunks
         self.counts = torch.zeros(B, self.parts, dtype=torch.int64, device=device)
         self.all_counts = torch.zeros(self.world, B, self.parts, dtype=torch.int64, device=device)
-        self.offsets = torch.zeros(B, self.parts + 1, dtype=torch.int64, device=device)     # scratch of dwj_xpart_scatter
         self.region_off = torch.zeros(self.regions + 1, dtype=torch.int64, device=device)
         self.region_off_host = torch.zeros(self.regions + 1, dtype=torch.int64).pin_memory()
         self.chunk_counts = torch.zeros(self.chunks, dtype=torch.int64, device=device)
         self.stream = stream
-        self.ps = torch.cuda.Stream(device=device)                        # partition (scatter) stream
-        self.xs = torch.cuda.Stream(device=device)                        # barrier stream
+        # Priorities: the barrier stream's one-CTA kernels must never queue behind a scatter or probe grid; the scatters
+        # go ahead of the local build / probes, because every later transfer and probe waits for them (measured: with
+        # the probes in front the last chunk left 1.5 ms later and the step grew from 5.3 to 6.1 ms on 2 GPUs).
+        self.ps = torch.cuda.Stream(device=device, priority=-1)           # partition (scatter) stream
+        self.js = torch.cuda.Stream(device=device)                        # local join stream, default priority
+        self.xs = torch.cuda.Stream(device=device, priority=-2)           # barrier stream
+        self.cps = torch.cuda.Stream(device=device, priority=-2)          # push kernel stream (transport "sm")
         self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(self.world)]
         self.copy_stream_ids = np.array([s.cuda_stream for s in self.copy_streams], dtype=np.uint64)
-        self.ev_plan = torch.cuda.Event()
-        self.ev_scattered = [torch.cuda.Event() for _ in range(B)]
-        self.ev_copied = [[torch.cuda.Event() for _ in range(self.world)] for _ in range(B)]
-        self.ev_arrived = [torch.cuda.Event() for _ in range(B)]
-        self.ev_step_done = torch.cuda.Event()
+        self.trace = bool(int(os.environ.get("DWJ_XCHG_TRACE", "0")))     # development: device timeline of every step
+        T = self.trace
+        self.ev_plan = torch.cuda.Event(enable_timing=T)
+        self.ev_scattered = [torch.cuda.Event(enable_timing=T) for _ in range(B)]
+        self.ev_copied = [[torch.cuda.Event(enable_timing=T) for _ in range(self.world)] for _ in range(B)]
+        self.ev_arrived = [torch.cuda.Event(enable_timing=T) for _ in range(B)]
+        self.ev_t0, self.ev_hist, self.ev_built = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        self.ev_probed = [torch.cuda.Event(enable_timing=True) for _ in range(self.chunks)]
+        self.last_trace = None
         self.segments = []
         self.stats = ExchangeStats()
 
@@ -370,68 +427,118 @@ class FoldedExchangeJoin:
         np, e, w, C, B = self.np, self.e, self.world, self.chunks, 1 + self.chunks
         cs = self.stream if self.stream is not None else torch.cuda.current_stream()
         bounds = [n_probe * c // C for c in range(C + 1)]
-        rel = [(build_keys, build_vals, 0, n_build, 0)] + [(probe_keys, probe_vals, bounds[c], bounds[c + 1] - bounds[c], 2)
-                                                           for c in range(C)]           # (keys, vals, first row, rows, column)
-        for b, (k, _, r0, n, _) in enumerate(rel):
+        rel = [(build_keys, build_vals, 0, n_build)] + [(probe_keys, probe_vals, bounds[c], bounds[c + 1] - bounds[c])
+                                                        for c in range(C)]              # (keys, vals, first row, rows)
+        if self.trace:
+            self.ev_t0.record(cs)
+        for b, (k, _, r0, n) in enumerate(rel):
             e.xpart_hist(k[r0:], n, w, self.counts[b], stream=cs)
+        if self.trace:
+            self.ev_hist.record(cs)
         with torch.cuda.stream(cs):
-            # Ordered behind this rank's previous local join: once every rank's counts are in, every receive buffer is free.
+            # Ordered behind this rank's previous local join: once every rank's counts are in, every receive area is free.
             dist.all_gather_into_tensor(self.all_counts.view(-1), self.counts.view(-1), group=self.group)
             self.ev_plan.record(cs)
             m = self.all_counts.cpu().numpy()                             # the one host sync of the step
-        plan = plan_folded_exchange(m, self.rank, self.regions, bounds)
+        blocked = self.layout == "blocked"
+        plan = (plan_blocked_exchange if blocked else plan_folded_exchange)(m, self.rank, self.regions, bounds)
         nb, np_ = plan["seg"][0][1], sum(n for _, n in plan["seg"][1:])
         if nb > self.cap_build or np_ > self.cap_probe:
             raise RuntimeError(f"receive buffers too small: {nb}/{self.cap_build} build rows, {np_}/{self.cap_probe} probe rows")
         if np_ > capacity:
             raise RuntimeError(f"output capacity {capacity} below the {np_} probe rows this rank receives")
-        self.region_off_host.copy_(torch.from_numpy(plan["region_off"][0]))
+        if not blocked:
+            self.region_off_host.copy_(torch.from_numpy(plan["region_off"][0]))
         dest_of_part = np.repeat(np.arange(w), self.regions)
+        own = dest_of_part == self.rank
         item = np.uint64(self.item)
-        # ---- partition stream: one scatter per batch; copy streams: its runs, one stream per destination ----------------
+        remote_streams = [(d, st) for d, st in enumerate(self.copy_streams) if d != self.rank]
+        # ---- partition stream: one scatter per batch; copy streams (one per destination): its runs ---------------------
         self.ps.wait_event(self.ev_plan)
-        for b, (k, v, r0, n, col) in enumerate(rel):
-            e.xpart_scatter(k[r0:], v[r0:], n, w, self.counts[b], self.send[col][r0:], self.send[col + 1][r0:], self.offsets[b],
-                            stream=self.ps)
+        for b, (k, v, r0, n) in enumerate(rel):
+            recv_off, send_off = (self.row_off[0], self.row_off[2]) if b == 0 else (self.row_off[1], self.row_off[3])
+            # own partitions land in this rank's receive area at their final position, the others in the send area
+            if blocked:
+                own_dst = np.zeros(self.parts, dtype=np.int64)
+                own_dst[own] = plan["own_row"][b]
+            else:
+                own_dst = plan["dst_row"][b]
+            start = np.where(own, recv_off + own_dst, send_off + plan["src_row"][b])
+            e.xpart_scatter(k[r0:], v[r0:], n, w, start, self.blocks[0], self.blocks[1], stream=self.ps)
             self.ev_scattered[b].record(self.ps)
-            rows = plan["rows"][b].astype(np.uint64)
-            src = plan["src_row"][b].astype(np.uint64) * item
-            dst = plan["dst_row"][b].astype(np.uint64) * item
-            copies_d, copies_s, copies_b, copies_st = [], [], [], []
-            for cc in (col, col + 1):
-                copies_d.append(self.recv_ptr[cc][dest_of_part] + dst)
-                copies_s.append(self.send_ptr[cc] + src)
-                copies_b.append(rows * item)
-                copies_st.append(self.copy_stream_ids[dest_of_part])
-            for st in self.copy_streams:
-                st.wait_event(self.ev_scattered[b])
-            e.copy_many_arrays(np.concatenate(copies_d), np.concatenate(copies_s), np.concatenate(copies_b), np.concatenate(copies_st))
-            for d, st in enumerate(self.copy_streams):
-                self.ev_copied[b][d].record(st)
-                self.xs.wait_event(self.ev_copied[b][d])
+            if blocked:         # one transfer per destination: the whole (destination, *) stretch of the send area
+                dests = np.arange(w)
+                nbytes = np.where(dests == self.rank, 0, plan["block_rows"][b]).astype(np.uint64) * item
+                src = (send_off + plan["block_src"][b]).astype(np.uint64) * item
+                dst = (recv_off + plan["block_dst"][b]).astype(np.uint64) * item
+            else:
+                dests = dest_of_part
+                nbytes = np.where(own, 0, plan["rows"][b]).astype(np.uint64) * item
+                src = (send_off + plan["src_row"][b]).astype(np.uint64) * item
+                dst = (recv_off + plan["dst_row"][b]).astype(np.uint64) * item
+            dsts = np.concatenate([self.block_ptr[blk][dests] + dst for blk in (0, 1)])
+            srcs = np.concatenate([self.block_ptr[blk][self.rank] + src for blk in (0, 1)])
+            self.xs.wait_event(self.ev_scattered[b])
+            if self.transport == "sm":
+                # every rank starts with a different peer (rank+1, rank+2, ...), so no receiver is everybody's target at once
+                order = np.argsort((np.concatenate([dests, dests]) - self.rank - 1) % w, kind="stable")
+                self.cps.wait_event(self.ev_scattered[b])
+                e.push_runs(dsts[order], srcs[order], np.concatenate([nbytes, nbytes])[order] // item, self.push_ctas, stream=self.cps)
+                self.ev_copied[b][0].record(self.cps)
+                self.xs.wait_event(self.ev_copied[b][0])
+            else:
+                for _, st in remote_streams:
+                    st.wait_event(self.ev_scattered[b])
+                e.copy_many_arrays(dsts, srcs, np.concatenate([nbytes, nbytes]), np.concatenate([self.copy_stream_ids[dests]] * 2))
+                for d, st in remote_streams:
+                    self.ev_copied[b][d].record(st)
+                    self.xs.wait_event(self.ev_copied[b][d])
             with torch.cuda.stream(self.xs):
                 self.hdl.barrier(channel=0)                               # every rank's runs of this batch have landed everywhere
             self.ev_arrived[b].record(self.xs)
-        # ---- compute stream: local build, then one probe per received chunk ---------------------------------------------
+        # ---- join stream: local build, then one probe per received chunk; the caller's stream rejoins at the end ---------
+        caller = cs
+        cs = self.js
+        cs.wait_event(self.ev_plan)
         cs.wait_event(self.ev_arrived[0])
-        with torch.cuda.stream(cs):
-            self.region_off.copy_(self.region_off_host, non_blocking=True)
-        if self.folded:
-            e.build_grouped(self.cols[0], self.cols[1], nb, self.region_off, stream=cs)
+        if self.folded and blocked:
+            e.build_segments(self.recv_build[0], self.recv_build[1], plan["seg_first"][0], plan["seg_rows"][0], w, stream=cs)
+        elif self.folded:
+            with torch.cuda.stream(cs):
+                self.region_off.copy_(self.region_off_host, non_blocking=True)
+            e.build_grouped(self.recv_build[0], self.recv_build[1], nb, self.region_off, stream=cs)
         else:                   # regions not folded into the exchange: the engine groups the received rows itself
-            e.build(self.cols[0], self.cols[1], nb, stream=cs)
+            e.build(self.recv_build[0], self.recv_build[1], nb, stream=cs)
+        if self.trace:
+            self.ev_built.record(cs)
         probe = e.probe_pairs_grouped if self.folded else e.probe_pairs
         for c, (row0, rows) in enumerate(plan["seg"][1:]):
             cs.wait_event(self.ev_arrived[1 + c])
-            probe(self.cols[2][row0:], self.cols[3][row0:], rows, None if out_key is None else out_key[row0:],
-                  out_build[row0:], out_probe[row0:], rows, d_n_matches=self.chunk_counts[c:], sync=False, stream=cs)
+            if self.folded and blocked:
+                e.probe_pairs_segments(self.recv_probe[0], self.recv_probe[1], plan["seg_first"][1 + c], plan["seg_rows"][1 + c],
+                                       None if out_key is None else out_key[row0:], out_build[row0:], out_probe[row0:], rows,
+                                       d_n_matches=self.chunk_counts[c:], sync=False, stream=cs)
+            else:
+                probe(self.recv_probe[0][row0:], self.recv_probe[1][row0:], rows, None if out_key is None else out_key[row0:],
+                      out_build[row0:], out_probe[row0:], rows, d_n_matches=self.chunk_counts[c:], sync=False, stream=cs)
+            if self.trace:
+                self.ev_probed[c].record(cs)
         with torch.cuda.stream(cs):
             torch.sum(self.chunk_counts, dim=0, keepdim=True, out=d_count)
-        # the send buffers may be rewritten once this step's copies are done: the next scatter waits for them
-        for st in self.copy_streams:
+        caller.wait_stream(cs)
+        # the send area may be rewritten once this step's copies are done: the next scatter waits for them
+        for st in ([self.cps] if self.transport == "sm" else [st for _, st in remote_streams]):
             self.ps.wait_stream(st)
         self.segments = plan["seg"][1:]
-        sent_local = int(plan["rows"][:, self.rank * self.regions:(self.rank + 1) * self.regions].sum())
+        if self.trace:
+            torch.cuda.synchronize()
+            t = lambda ev: round(self.ev_t0.elapsed_time(ev), 3)    # noqa: E731
+            self.last_trace = {"hist": t(self.ev_hist), "plan": t(self.ev_plan), "scattered": [t(x) for x in self.ev_scattered],
+                               "copied": [[t(self.ev_copied[b][d]) for d in ([0] if self.transport == "sm" else [d for d, _ in remote_streams])]
+                                          for b in range(B)],
+                               "arrived": [t(x) for x in self.ev_arrived], "built": t(self.ev_built),
+                               "probed": [t(x) for x in self.ev_probed]}
+        sent_local = int(plan["rows"][:, own].sum())
         self.stats.sent_rows += n_build + n_probe
         self.stats.recv_rows += nb + np_
         self.stats.sent_bytes_remote += 2 * self.item * (n_build + n_probe - sent_local)

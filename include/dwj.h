@@ -201,16 +201,19 @@ DWJ_API int dwj_partition_scatter_to(dwj_engine *e, const void *d_keys, const vo
  * bucket index; every rank's engine must be created with the same table size and hash seed).  Partitions are ordered
  * rank-major, region-minor.  dwj_xpart_regions() says how many regions are folded in: the engine's region count when
  * n_ranks x regions <= 512, else 1 (plain rank partition; the receiver then groups by region itself with dwj_build /
- * dwj_probe_pairs).  Usage: dwj_xpart_hist -> exchange the counts -> dwj_xpart_scatter into a send buffer -> copy
+ * dwj_probe_pairs).  Usage: dwj_xpart_hist -> exchange the counts, plan the layout -> dwj_xpart_scatter into a send buffer -> copy
  * every (rank, region) run into the destination's receive buffer laid out region-major (dwj_copy_many or any
  * transport) -> dwj_build_grouped / dwj_probe_pairs_grouped on the received rows, which skip the engine's own
  * partition pass. */
 DWJ_API uint32_t dwj_xpart_regions(const dwj_engine *e, uint32_t n_ranks);
 /* d_counts[n_ranks * regions] (uint64, device). */
 DWJ_API int dwj_xpart_hist(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t n_ranks, uint64_t *d_counts, void *stream);
-/* Second half: d_counts as written by dwj_xpart_hist for the same rows; d_offsets[n_ranks * regions + 1] (device). */
+/* Second half, after the exchange has been planned: the rows of partition p are written to d_out_keys / d_out_vals
+ * [start_rows[p] ...] (HOST array of n_ranks * regions row offsets; runs must not overlap).  The runs may lie anywhere
+ * in the allocation the out pointers address -- typically a send buffer for the other ranks' partitions and this
+ * rank's own receive buffer for its own. */
 DWJ_API int dwj_xpart_scatter(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_ranks,
-                      const uint64_t *d_counts, void *d_out_keys, void *d_out_vals, uint64_t *d_offsets, void *stream);
+                      const uint64_t *start_rows, void *d_out_keys, void *d_out_vals, void *stream);
 /* dwj_build / dwj_probe_pairs for rows that are ALREADY grouped by table region (region-major): no partition pass.
  * d_region_offsets (device, regions + 1 uint64 row offsets, may be NULL) enables the build's L2 look-ahead. */
 DWJ_API int dwj_build_grouped(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows,
@@ -218,10 +221,30 @@ DWJ_API int dwj_build_grouped(dwj_engine *e, const void *d_keys, const void *d_v
 DWJ_API int dwj_probe_pairs_grouped(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *d_out_key,
                             void *d_out_build_val, void *d_out_probe_val, uint64_t capacity, uint64_t *d_n_matches,
                             uint64_t *n_matches, void *stream);
+/* The same for rows that arrive as a LIST OF SEGMENTS of one allocation (d_keys / d_vals address the allocation,
+ * segment i = rows [seg_first_row[i], +seg_rows[i]), host arrays, at most 512 segments) and are to be consumed in list
+ * order: e.g. one block per source rank, region-grouped inside the block, walked region by region -- (region 0, source
+ * 0), (region 0, source 1), ... -- so that every source's rows can be delivered with ONE large copy per peer and still
+ * be built / probed one table region at a time.  segments_per_region (build; 0 = unknown) tells the look-ahead that
+ * segments [r * segments_per_region, (r+1) * segments_per_region) belong to table region r.  The probe variant is
+ * implemented for DWJ_FLAG_UNIQUE_BUILD_KEYS engines. */
+DWJ_API int dwj_build_segments(dwj_engine *e, const void *d_keys, const void *d_vals, uint32_t n_segments,
+                       const uint64_t *seg_first_row, const uint64_t *seg_rows, uint32_t segments_per_region, void *stream);
+DWJ_API int dwj_probe_pairs_segments(dwj_engine *e, const void *d_keys, const void *d_vals, uint32_t n_segments,
+                             const uint64_t *seg_first_row, const uint64_t *seg_rows, void *d_out_key, void *d_out_build_val,
+                             void *d_out_probe_val, uint64_t capacity, uint64_t *d_n_matches, uint64_t *n_matches,
+                             void *stream);
 /* n_copies device-to-device copies (local or peer memory mapped into this process), copy i on streams[i]: the copy
  * engines carry the exchange while the SMs partition and join.  Asynchronous. */
 DWJ_API int dwj_copy_many(dwj_engine *e, uint32_t n_copies, void *const *dsts, const void *const *srcs, const uint64_t *bytes,
                   void *const *streams);
+
+/* The same transfer done by a small kernel instead of the copy engines: run i = rows[i] rows (of key_bytes each) from
+ * srcs[i] to dsts[i] (local or peer memory), all runs pushed by n_ctas CTAs (0 = 64) with coalesced warp stores, on
+ * `stream`.  For many medium-sized runs (ranks x regions per relation) this beats one copy-engine job per run by far
+ * and leaves most SMs free.  Asynchronous; at most 2048 runs per call. */
+DWJ_API int dwj_push_runs(dwj_engine *e, uint32_t n_runs, void *const *dsts, const void *const *srcs, const uint64_t *rows,
+                  uint32_t n_ctas, void *stream);
 
 /* Partition id of one key on the host (same function the kernels use) -- lets callers and tests
  * reason about placement without a device. */

@@ -180,3 +180,42 @@ def test_plan_folded_exchange_layout():
             for c in range(chunks):
                 assert src[1 + c, 0] == bounds[s][c]
                 assert (np.diff(src[1 + c]) == counts[s, 1 + c, :-1]).all()
+
+
+def test_plan_blocked_exchange_layout():
+    """Blocked (source-major) folded exchange: one block per (source, destination, batch); the blocks and the rows a
+    rank scatters in place tile every receive area exactly; the segment list walks a batch region by region, source by
+    source, and names exactly the rows of that (source, region) run."""
+    from dwarf_bench_b200.distributed import plan_blocked_exchange
+    rng = np.random.default_rng(1)
+    for w, G, C in ((2, 4, 1), (8, 8, 2), (4, 2, 3)):
+        cnt = rng.integers(0, 50, (w, 1 + C, w * G))
+        bounds = [[0] + list(np.cumsum(cnt[s, 1:].sum(axis=1))) for s in range(w)]
+        plans = [plan_blocked_exchange(cnt, r, G, bounds[r]) for r in range(w)]
+        tag = lambda s, b, p: (s * 100 + b) * 1000 + p                  # noqa: E731
+        for d in range(w):
+            for rel in (range(0, 1), range(1, 1 + C)):
+                area = np.full(sum(plans[d]["seg"][b][1] for b in rel), -1)
+                for s in range(w):
+                    for b in rel:
+                        if s == d:                                        # scattered in place, run by run
+                            for g in range(G):
+                                r0, n = plans[s]["own_row"][b, g], cnt[s, b, d * G + g]
+                                assert (area[r0:r0 + n] == -1).all()
+                                area[r0:r0 + n] = tag(s, b, d * G + g)
+                        else:                                             # one transfer: the sender's (d, *) stretch
+                            r0, n = plans[s]["block_dst"][b, d], plans[s]["block_rows"][b, d]
+                            assert n == cnt[s, b, d * G:(d + 1) * G].sum()
+                            assert plans[s]["block_src"][b, d] == plans[s]["src_row"][b, d * G]
+                            ids = [np.full(cnt[s, b, d * G + g], tag(s, b, d * G + g)) for g in range(G)]
+                            assert (area[r0:r0 + n] == -1).all()
+                            area[r0:r0 + n] = np.concatenate(ids)
+                assert (area != -1).all()
+                for b in rel:
+                    f, r = plans[d]["seg_first"][b], plans[d]["seg_rows"][b]
+                    i = 0
+                    for g in range(G):
+                        for s in range(w):
+                            assert r[i] == cnt[s, b, d * G + g] and (area[f[i]:f[i] + r[i]] == tag(s, b, d * G + g)).all()
+                            i += 1
+                    assert r.sum() == plans[d]["seg"][b][1]

@@ -453,14 +453,15 @@ def test_partition_scatter_to_destinations(dwj, wide, parts):
 
 
 @pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("layout", ["region", "blocked"])
 @pytest.mark.parametrize("world,chunks", [(4, 2), (8, 1), (2, 3)])
-def test_folded_exchange_single_gpu(dwj, oracle, monkeypatch, wide, world, chunks):
+def test_folded_exchange_single_gpu(dwj, oracle, monkeypatch, wide, world, chunks, layout):
     """The folded exchange (dwj_xpart_hist / dwj_xpart_scatter / dwj_copy_many / dwj_build_grouped /
     dwj_probe_pairs_grouped + plan_folded_exchange) with `world` VIRTUAL ranks on one GPU: every virtual rank
     partitions its own rows, the planned copies fill every destination's receive buffer, every destination joins what
     it received, and the union of the destinations' results is the oracle's join of the whole input."""
     from dwarf_bench_b200 import capi
-    from dwarf_bench_b200.distributed import plan_folded_exchange
+    from dwarf_bench_b200.distributed import plan_blocked_exchange, plan_folded_exchange
     monkeypatch.setenv("DWJ_PARTITION_MIN_MB", "0")
     monkeypatch.setenv("DWJ_REGION_MB", "0.125")              # force table regions at test size
     rng = np.random.default_rng(11 + world + chunks + wide)
@@ -488,13 +489,15 @@ def test_folded_exchange_single_gpu(dwj, oracle, monkeypatch, wide, world, chunk
             bounds = [npr * c // chunks for c in range(chunks + 1)]
             send = [torch.empty(nb, dtype=tdt, device="cuda"), torch.empty(nb, dtype=tdt, device="cuda"),
                     torch.empty(npr, dtype=tdt, device="cuda"), torch.empty(npr, dtype=tdt, device="cuda")]
-            offs = torch.zeros(parts + 1, dtype=torch.int64, device="cuda")
+            def starts(cnt):                                   # compact layout: partition runs one after the other
+                c_ = cnt.cpu().numpy()
+                return np.cumsum(c_) - c_
             e.xpart_hist(ak, nb, world, counts[s, 0])
-            e.xpart_scatter(ak, av, nb, world, counts[s, 0], send[0], send[1], offs)
+            e.xpart_scatter(ak, av, nb, world, starts(counts[s, 0]), send[0], send[1])
             for c in range(chunks):
                 r0, n = bounds[c], bounds[c + 1] - bounds[c]
                 e.xpart_hist(bk[r0:], n, world, counts[s, 1 + c])
-                e.xpart_scatter(bk[r0:], bv[r0:], n, world, counts[s, 1 + c], send[2][r0:], send[3][r0:], offs)
+                e.xpart_scatter(bk[r0:], bv[r0:], n, world, starts(counts[s, 1 + c]), send[2][r0:], send[3][r0:])
             src.append((send, bounds))
         torch.cuda.synchronize()
         m = counts.cpu().numpy()
@@ -506,7 +509,8 @@ def test_folded_exchange_single_gpu(dwj, oracle, monkeypatch, wide, world, chunk
             if m[0, 0, p]:
                 key = int(send0[run_start[p]])
                 assert capi.partition_of(key, item, world, 42) == p // regions
-        plans = [plan_folded_exchange(m, r, regions, src[r][1]) for r in range(world)]
+        blocked = layout == "blocked"
+        plans = [(plan_blocked_exchange if blocked else plan_folded_exchange)(m, r, regions, src[r][1]) for r in range(world)]
         recv_rows_b = [plans[d]["seg"][0][1] for d in range(world)]
         recv_rows_p = [sum(n for _, n in plans[d]["seg"][1:]) for d in range(world)]
         recv = [[torch.full((max(n, 1),), -1, dtype=tdt, device="cuda") for n in (recv_rows_b[d], recv_rows_b[d], recv_rows_p[d], recv_rows_p[d])]
@@ -518,22 +522,40 @@ def test_folded_exchange_single_gpu(dwj, oracle, monkeypatch, wide, world, chunk
             copies = []
             for b in range(B):
                 col = 0 if b == 0 else 2
-                for p in range(parts):
-                    d = p // regions
-                    for cc in (col, col + 1):
-                        copies.append((recv[d][cc].data_ptr() + int(pl["dst_row"][b, p]) * item,
-                                       send[cc].data_ptr() + int(pl["src_row"][b, p]) * item, int(pl["rows"][b, p]) * item, stream))
+                if blocked:                                        # one copy per (destination, column); own rows run by run
+                    for d in range(world):
+                        for cc in (col, col + 1):
+                            if d != s:
+                                copies.append((recv[d][cc].data_ptr() + int(pl["block_dst"][b, d]) * item,
+                                               send[cc].data_ptr() + int(pl["block_src"][b, d]) * item, int(pl["block_rows"][b, d]) * item, stream))
+                            else:
+                                for g in range(regions):
+                                    p = d * regions + g
+                                    copies.append((recv[d][cc].data_ptr() + int(pl["own_row"][b, g]) * item,
+                                                   send[cc].data_ptr() + int(pl["src_row"][b, p]) * item, int(pl["rows"][b, p]) * item, stream))
+                else:
+                    for p in range(parts):
+                        d = p // regions
+                        for cc in (col, col + 1):
+                            copies.append((recv[d][cc].data_ptr() + int(pl["dst_row"][b, p]) * item,
+                                           send[cc].data_ptr() + int(pl["src_row"][b, p]) * item, int(pl["rows"][b, p]) * item, stream))
             e.copy_many(copies)
         torch.cuda.synchronize()
         got_rows = []
         for d in range(world):
-            roff = torch.from_numpy(plans[d]["region_off"][0]).cuda()
-            e.build_grouped(recv[d][0], recv[d][1], recv_rows_b[d], roff)
             ok, oa, ob = (empty_like_dev(recv_rows_p[d], dt) for _ in range(3))
             total = 0
-            for (row0, rows) in plans[d]["seg"][1:]:
-                mm = e.probe_pairs_grouped(recv[d][2][row0:], recv[d][3][row0:], rows, ok[total:], oa[total:], ob[total:], rows)
-                total += mm
+            if blocked:
+                e.build_segments(recv[d][0], recv[d][1], plans[d]["seg_first"][0], plans[d]["seg_rows"][0], world)
+                for c in range(chunks):
+                    rows = plans[d]["seg"][1 + c][1]
+                    total += e.probe_pairs_segments(recv[d][2], recv[d][3], plans[d]["seg_first"][1 + c], plans[d]["seg_rows"][1 + c],
+                                                    ok[total:], oa[total:], ob[total:], rows)
+            else:
+                roff = torch.from_numpy(plans[d]["region_off"][0]).cuda()
+                e.build_grouped(recv[d][0], recv[d][1], recv_rows_b[d], roff)
+                for (row0, rows) in plans[d]["seg"][1:]:
+                    total += e.probe_pairs_grouped(recv[d][2][row0:], recv[d][3][row0:], rows, ok[total:], oa[total:], ob[total:], rows)
             torch.cuda.synchronize()
             got_rows.append(tuple(host(t, dt)[:total] for t in (ok, oa, ob)))
     got = pyoracle.canonical_rows(*(np.concatenate([g[i] for g in got_rows]) for i in range(3)))
