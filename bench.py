@@ -59,8 +59,8 @@ def parse_args():
                     help="multi-GPU exchange: fold = one (rank x table region) partition pass + copy-engine pushes into peer "
                          "memory, overlapped with the local probes (default); p2p = fused partition + SM stores into peer memory; "
                          "nccl = local partition + NCCL all-to-all-v")
-    ap.add_argument("--exchange-chunks", type=int, default=2,
-                    help="fold / p2p exchange: the probe relation travels in this many pieces")
+    ap.add_argument("--exchange-chunks", type=int, default=0,
+                    help="fold / p2p exchange: the probe relation travels in this many pieces (0 = 2 on two GPUs, 4 on more: measured)")
     ap.add_argument("--exchange-transport", default="ce", choices=["sm", "ce"],
                     help="fold exchange: runs pushed into peer memory by the copy engines (ce) or by a small kernel (sm)")
     ap.add_argument("--exchange-layout", default="blocked", choices=["blocked", "region"],
@@ -267,6 +267,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+        if args.exchange_chunks <= 0:
+            args.exchange_chunks = 2 if world <= 2 else 4
     dwj.load_library()
     tdt = torch.int32 if key_bytes == 4 else torch.int64
     dtype_name = "u32" if key_bytes == 4 else "u64"

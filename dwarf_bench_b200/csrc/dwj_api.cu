@@ -552,12 +552,18 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
     rc = unique ? simple_launch<W, dwj::PROBE_COUNT, true>(e, a, s) : simple_launch<W, dwj::PROBE_COUNT, false>(e, a, s);
     break;
   default:
-    if (unique) {      // one look-back (or one atomic) per chunk, rows staged in shared memory
-      const bool ordered = !(e->cfg.flags & DWJ_FLAG_UNORDERED_OUTPUT);
-      if (ordered) rc = ok ? staged_launch<W, true, true>(e, a, s) : staged_launch<W, true, false>(e, a, s);
-      else rc = ok ? staged_launch<W, false, true>(e, a, s) : staged_launch<W, false, false>(e, a, s);
-    } else {
-      rc = (e->cfg.flags & DWJ_FLAG_UNORDERED_OUTPUT) ? multi_launch<W, false>(e, a, s) : multi_launch<W, true>(e, a, s);
+    {
+      // Probe-row order only exists when the kernel sees the caller's rows in the caller's order: a region-partitioned,
+      // grouped or segmented input is already permuted, so the order-preserving look-back would buy nothing.
+      static const bool keep_lookback = getenv("DWJ_KEEP_LOOKBACK") && atoi(getenv("DWJ_KEEP_LOOKBACK"));   // A/B switch (development)
+      const bool permuted = extra_launches || grouped;
+      const bool ordered = !(e->cfg.flags & DWJ_FLAG_UNORDERED_OUTPUT) && (!permuted || keep_lookback);
+      if (unique) {      // rows staged in shared memory; one look-back per chunk (ordered) or one atomic per warp
+        if (ordered) rc = ok ? staged_launch<W, true, true>(e, a, s) : staged_launch<W, true, false>(e, a, s);
+        else rc = ok ? staged_launch<W, false, true>(e, a, s) : staged_launch<W, false, false>(e, a, s);
+      } else {
+        rc = ordered ? multi_launch<W, true>(e, a, s) : multi_launch<W, false>(e, a, s);
+      }
     }
   }
   if (rc) return rc;

@@ -1,15 +1,13 @@
-N=${1:-2}
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-DWJ_XCHG_TRACE=1 $TR bench.py --gpus $N --steps 3 --warmup 2 --exchange fold --exchange-chunks 2 --no-e2e > gpurun_out/mg${N}_trace.json 2> gpurun_out/mg${N}_trace.err
-grep -o "rank 0\] exchange timeline.*" gpurun_out/mg${N}_trace.err | cut -c1-700 || tail -20 gpurun_out/mg${N}_trace.err
-for ch in 2 4; do
-  $TR bench.py --gpus $N --steps 10 --warmup 3 --exchange fold --exchange-chunks $ch --no-e2e > gpurun_out/mg${N}_blk_$ch.json 2> gpurun_out/mg${N}_blk_$ch.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for wl in join_16Mx256M_u32_unique join_256Mx256M_u32_unique join_512Mx1G_u64_unique join_16Mx256M_u32_dup4_zipf; do
+  python bench.py --workload $wl --steps 4 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/ld_$wl.json 2> gpurun_out/ld.err
 done
-$TR bench.py --gpus $N --steps 10 --warmup 3 --exchange fold --exchange-chunks 2 --exchange-layout region --no-e2e > gpurun_out/mg${N}_blk_region2.json 2> gpurun_out/mg${N}_blk_region2.err
+DWJ_KEEP_LOOKBACK=1 python bench.py --workload join_16Mx256M_u32_unique --steps 4 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/ld_lookback_join_16Mx256M_u32_unique.json 2> gpurun_out/ld.err
 python - <<'PY'
 import json,glob
-for f in sorted(glob.glob("gpurun_out/mg*_blk_*.json")):
+for f in sorted(glob.glob("gpurun_out/ld_*.json")):
     try:
-        d=json.load(open(f)); print(f, round(d["value"]/1e9,1), "G/s", round(d["ms_per_step"],3), "ms")
+        d=json.load(open(f)); print(f, round(d["ms_per_step"],3), {k:round(v,3) for k,v in d["phases_ms"].items()}, round(d["roofline"]["kernel_ms"],3), d["config"]["table_regions"])
     except Exception as ex: print(f, "ERR", ex)
 PY
+tail -3 gpurun_out/ld.err
