@@ -151,10 +151,10 @@ int ensure_tile_state(dwj_engine *e, uint64_t tiles, cudaStream_t s) {
 }
 
 // Thread-private byte counters (histogram, > 8 partitions) and the ballot-ranked, shared-memory-staged scatter.
-template <int W, int THREADS>
+template <int W, uint32_t MODE, int THREADS>
 int hist_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
   constexpr int HROWS = 8;
-  auto kern = dwj::partition_hist_private_kernel<W, THREADS, HROWS>;
+  auto kern = dwj::partition_hist_private_kernel<W, MODE, THREADS, HROWS>;
   const size_t smem = (size_t)THREADS << a.log2_parts;
   if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
@@ -164,17 +164,22 @@ int hist_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t
   CU(launch(e, kern, dim3(grid), dim3(THREADS), s, a, false, smem));
   return DWJ_OK;
 }
-// Histogram of a.keys into a.hist (zeroed by the caller).
-template <int W> int hist_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
-  if (!a.n) return DWJ_OK;
+template <int W, uint32_t MODE> int hist_launch_mode(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
   if (a.log2_parts <= 3) {      // <= 8 partitions: packed-register counters
     constexpr int HROWS = 8;
     const uint64_t htiles = (a.n + 256ull * HROWS - 1) / (256ull * HROWS);
     const dim3 hgrid((unsigned)std::min<uint64_t>(htiles, (uint64_t)e->prop.multiProcessorCount * 8));
-    CU(launch(e, dwj::partition_hist8_kernel<W, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
+    CU(launch(e, dwj::partition_hist8_kernel<W, MODE, HROWS>, hgrid, dim3(dwj::PART_THREADS), s, a, false));
     return DWJ_OK;
   }
-  return a.log2_parts <= 8 ? hist_many_launch<W, 256>(e, a, s) : hist_many_launch<W, 128>(e, a, s);
+  return a.log2_parts <= 8 ? hist_many_launch<W, MODE, 256>(e, a, s) : hist_many_launch<W, MODE, 128>(e, a, s);
+}
+// Histogram of a.keys into a.hist (zeroed by the caller).
+template <int W> int hist_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
+  if (!a.n) return DWJ_OK;
+  if (a.mode == dwj::PART_BY_BUCKET) return hist_launch_mode<W, dwj::PART_BY_BUCKET>(e, a, s);
+  if (a.mode == dwj::PART_BY_HASH) return hist_launch_mode<W, dwj::PART_BY_HASH>(e, a, s);
+  return hist_launch_mode<W, dwj::PART_BY_BOTH>(e, a, s);
 }
 
 template <int W, int BITS>

@@ -61,11 +61,18 @@ template <int W> struct PartitionArgs {
 //   PART_BY_BOTH   : destination rank (rank_bits) in the high bits, table region of the DESTINATION's table in the low
 //                    bits -- one pass that serves the exchange and the receiver's region grouping (dwj_xpart_*)
 enum PartMode : uint32_t { PART_BY_HASH = 0, PART_BY_BUCKET = 1, PART_BY_BOTH = 2 };
-template <int W> DWJ_D uint32_t part_id(const PartitionArgs<W> &a, typename KeyT<W>::type key) {
-  if (a.mode == PART_BY_BUCKET) return (uint32_t)((slot_hash(key, a.seed) & a.bucket_mask) >> a.bucket_shift);
-  if (a.mode == PART_BY_HASH) return partition_of(key, a.log2_parts, a.seed);
+template <int W, uint32_t MODE> DWJ_D uint32_t part_id_of(const PartitionArgs<W> &a, typename KeyT<W>::type key) {
+  if constexpr (MODE == PART_BY_BUCKET) return (uint32_t)((slot_hash(key, a.seed) & a.bucket_mask) >> a.bucket_shift);
+  if constexpr (MODE == PART_BY_HASH) return partition_of(key, a.log2_parts, a.seed);
   const uint32_t region_bits = a.log2_parts - a.rank_bits;
   return partition_of(key, a.rank_bits, a.seed) << region_bits | (uint32_t)((slot_hash(key, a.seed) & a.bucket_mask) >> a.bucket_shift);
+}
+// Run-time mode (the scatter: one id per row beside ~100 other instructions); the histograms, which do little else,
+// are compiled per mode.
+template <int W> DWJ_D uint32_t part_id(const PartitionArgs<W> &a, typename KeyT<W>::type key) {
+  if (a.mode == PART_BY_BUCKET) return part_id_of<W, PART_BY_BUCKET>(a, key);
+  if (a.mode == PART_BY_HASH) return part_id_of<W, PART_BY_HASH>(a, key);
+  return part_id_of<W, PART_BY_BOTH>(a, key);
 }
 
 constexpr uint32_t PART_DEAD = 0xFFFFFFFFu;   // partition id of a lane past the end of the input
@@ -95,7 +102,7 @@ template <int BITS> DWJ_D unsigned match_partition(uint32_t p, unsigned alive) {
   return peers;
 }
 
-template <int W, int THREADS, int HROWS>
+template <int W, uint32_t MODE, int THREADS, int HROWS>
 __global__ void __launch_bounds__(THREADS) partition_hist_private_kernel(PartitionArgs<W> a) {
   using K = typename KeyT<W>::type;
   extern __shared__ __align__(16) unsigned char s_cnt[];      // [parts][THREADS] bytes
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(THREADS) partition_hist_private_kernel(Partiti
       for (int j = 0; j < HROWS; ++j) k[j] = load_stream(a.keys + base + (uint64_t)j * THREADS);
 #pragma unroll
       for (int j = 0; j < HROWS; ++j) {
-        unsigned char *c = mine + part_id<W>(a, k[j]) * THREADS;
+        unsigned char *c = mine + part_id_of<W, MODE>(a, k[j]) * THREADS;
         *c = (unsigned char)(*c + 1);
       }
     } else {
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(THREADS) partition_hist_private_kernel(Partiti
       for (int j = 0; j < HROWS; ++j) {
         const uint64_t i = base + (uint64_t)j * THREADS;
         if (i < a.n) {
-          unsigned char *c = mine + part_id<W>(a, load_stream(a.keys + i)) * THREADS;
+          unsigned char *c = mine + part_id_of<W, MODE>(a, load_stream(a.keys + i)) * THREADS;
           *c = (unsigned char)(*c + 1);
         }
       }
@@ -169,8 +176,8 @@ template <int W, int THREADS, int ITEMS> struct ScatterManySmem {
   using K = typename KeyT<W>::type;
   static constexpr uint32_t TILE = THREADS * ITEMS;
   static constexpr int WARPS = THREADS / 32;
-  // dynamic shared memory: keys[TILE] | vals[TILE] | delta[parts] (int64) | wc[WARPS][parts] (uint32)
-  static size_t bytes(uint32_t parts) { return (size_t)TILE * 2 * sizeof(K) + (size_t)parts * (8 + 4 * WARPS); }
+  // dynamic shared memory: keys[TILE] | vals[TILE] | delta[parts] (int64) | wc[WARPS][parts] (uint32) | part[TILE] (uint16)
+  static size_t bytes(uint32_t parts) { return (size_t)TILE * (2 * sizeof(K) + 2) + (size_t)parts * (8 + 4 * WARPS); }
 };
 
 template <int W, int BITS, int THREADS, int ITEMS, bool FULL>
@@ -184,7 +191,8 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t 
   K *s_vals = s_keys + TILE;
   long long *s_delta = reinterpret_cast<long long *>(s_vals + TILE);
   unsigned int *s_wc = reinterpret_cast<unsigned int *>(s_delta + PARTS);
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned short *s_part = reinterpret_cast<unsigned short *>(s_wc + WARPS * PARTS);   // partition of every staged row: two
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                     // shared-memory ops instead of a re-hash
   const unsigned lt = (1u << lane) - 1u;
   const bool with_vals = a.vals != nullptr;
   unsigned int *mywc = s_wc + warp * PARTS;
@@ -267,6 +275,7 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t 
       const uint32_t s = mywc[pr[j] >> 16] + (pr[j] & 0xFFFFu);
       s_keys[s] = k[j];
       s_vals[s] = v[j];
+      s_part[s] = (unsigned short)(pr[j] >> 16);
     }
   }
   __syncthreads();
@@ -274,9 +283,8 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t 
   for (int j = 0; j < ITEMS; ++j) {
     const uint32_t s = j * THREADS + threadIdx.x;
     if (FULL || s < rows) {
-      const K key = s_keys[s];
-      const long long dst = (long long)s + s_delta[part_id<W>(a, key)];
-      store_stream(a.out_keys + dst, key);
+      const long long dst = (long long)s + s_delta[s_part[s]];
+      store_stream(a.out_keys + dst, s_keys[s]);
       if (with_vals) store_stream(a.out_vals + dst, s_vals[s]);
     }
   }
@@ -301,7 +309,7 @@ __global__ void __launch_bounds__(THREADS, MINB) partition_scatter_many_kernel(P
 // Per-partition counters are PACKED into one 64-bit register per thread: 8 fields x 8 bits, flushed to shared memory
 // before a field can overflow.  Interior tiles run a FULL = true instantiation of the tile body without any bounds
 // predicate (the 64-bit compares and the per-row branches they cause were most of the instruction stream at first).
-template <int W, int HROWS, bool FULL>
+template <int W, uint32_t MODE, int HROWS, bool FULL>
 DWJ_D void hist8_tile(const PartitionArgs<W> &a, uint64_t tile_base, unsigned long long &acc) {
   using K = typename KeyT<W>::type;
   const K *kp = a.keys + tile_base + threadIdx.x;
@@ -311,12 +319,12 @@ DWJ_D void hist8_tile(const PartitionArgs<W> &a, uint64_t tile_base, unsigned lo
   for (int j = 0; j < HROWS; ++j) k[j] = (FULL || j * PART_THREADS + threadIdx.x < rows) ? load_stream(kp + j * PART_THREADS) : (K)0;
 #pragma unroll
   for (int j = 0; j < HROWS; ++j) {
-    const unsigned long long one = 1ull << (8 * part_id<W>(a, k[j]));
+    const unsigned long long one = 1ull << (8 * part_id_of<W, MODE>(a, k[j]));
     acc += (FULL || j * PART_THREADS + threadIdx.x < rows) ? one : 0ull;
   }
 }
 
-template <int W, int HROWS>
+template <int W, uint32_t MODE, int HROWS>
 __global__ void __launch_bounds__(PART_THREADS) partition_hist8_kernel(PartitionArgs<W> a) {
   __shared__ unsigned int s_hist[8];
   if (threadIdx.x < 8) s_hist[threadIdx.x] = 0;
@@ -335,8 +343,8 @@ __global__ void __launch_bounds__(PART_THREADS) partition_hist8_kernel(Partition
     pending = 0;
   };
   for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    if (tile * TILE + TILE <= a.n) hist8_tile<W, HROWS, true>(a, tile * TILE, acc);
-    else hist8_tile<W, HROWS, false>(a, tile * TILE, acc);
+    if (tile * TILE + TILE <= a.n) hist8_tile<W, MODE, HROWS, true>(a, tile * TILE, acc);
+    else hist8_tile<W, MODE, HROWS, false>(a, tile * TILE, acc);
     pending += HROWS;
     if (pending > 255 - HROWS) flush();
   }
