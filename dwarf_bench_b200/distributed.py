@@ -353,9 +353,12 @@ class FoldedExchangeJoin:
     """
 
     def __init__(self, engine, device, dtype, cap_build: int, cap_probe: int, max_build: int, max_probe: int, chunks: int = 2,
-                 group=None, stream=None, transport: str = "ce", push_ctas: int = 64, layout: str = "blocked"):
+                 group=None, stream=None, transport: str = "ce1", push_ctas: int = 64, layout: str = "blocked"):
         import os
-        # transport "ce": copy engines (dwj_copy_many); "sm": dwj_push_runs (a few CTAs store into peer memory).
+        # transport "ce1": copy engines (dwj_copy_many), ONE copy stream, peers in the order rank+1, rank+2, ... so that
+        #   every receiver is one sender's target at a time (the classic all-to-all schedule): ~600 GB/s per GPU.
+        #   "ce": one copy stream per peer -- concurrent copies to several peers share ~400 GB/s and finish together.
+        #   "sm": dwj_push_runs (a few CTAs store into peer memory), ~430 GB/s.
         # layout "blocked": one block per source at the receiver -> one large transfer per peer and relation, the
         #   receiver walks the blocks region by region (dwj_*_segments).  The copy engines serialise copies at ~27 us
         #   each, so this is the layout for them.  Needs an engine with DWJ_FLAG_UNIQUE_BUILD_KEYS.
@@ -486,6 +489,15 @@ class FoldedExchangeJoin:
                 e.push_runs(dsts[order], srcs[order], np.concatenate([nbytes, nbytes])[order] // item, self.push_ctas, stream=self.cps)
                 self.ev_copied[b][0].record(self.cps)
                 self.xs.wait_event(self.ev_copied[b][0])
+            elif self.transport == "ce1":
+                # one copy stream, peers in the order rank+1, rank+2, ...: at any time every receiver is the target of one sender
+                order = np.argsort((np.concatenate([dests, dests]) - self.rank - 1) % w, kind="stable")
+                st = self.copy_streams[0]
+                st.wait_event(self.ev_scattered[b])
+                e.copy_many_arrays(dsts[order], srcs[order], np.concatenate([nbytes, nbytes])[order],
+                                   np.full(len(order), self.copy_stream_ids[0], dtype=np.uint64))
+                self.ev_copied[b][0].record(st)
+                self.xs.wait_event(self.ev_copied[b][0])
             else:
                 for _, st in remote_streams:
                     st.wait_event(self.ev_scattered[b])
@@ -527,14 +539,14 @@ class FoldedExchangeJoin:
             torch.sum(self.chunk_counts, dim=0, keepdim=True, out=d_count)
         caller.wait_stream(cs)
         # the send area may be rewritten once this step's copies are done: the next scatter waits for them
-        for st in ([self.cps] if self.transport == "sm" else [st for _, st in remote_streams]):
+        for st in {"sm": [self.cps], "ce1": [self.copy_streams[0]]}.get(self.transport, [st for _, st in remote_streams]):
             self.ps.wait_stream(st)
         self.segments = plan["seg"][1:]
         if self.trace:
             torch.cuda.synchronize()
             t = lambda ev: round(self.ev_t0.elapsed_time(ev), 3)    # noqa: E731
             self.last_trace = {"hist": t(self.ev_hist), "plan": t(self.ev_plan), "scattered": [t(x) for x in self.ev_scattered],
-                               "copied": [[t(self.ev_copied[b][d]) for d in ([0] if self.transport == "sm" else [d for d, _ in remote_streams])]
+                               "copied": [[t(self.ev_copied[b][d]) for d in ([0] if self.transport in ("sm", "ce1") else [d for d, _ in remote_streams])]
                                           for b in range(B)],
                                "arrived": [t(x) for x in self.ev_arrived], "built": t(self.ev_built),
                                "probed": [t(x) for x in self.ev_probed]}
