@@ -8,8 +8,10 @@ followed by dwj_probe_pairs of the probe relation with compacted (build payload,
 
 N == 1 (default): BASELINE.json configs[1] -- build 16 Mi / probe 256 Mi uint32 rows, unique build keys, every
 probe row matches once.  N > 1 (under torchrun): every rank holds that same amount of both relations of an
-N-times larger global join (weak scaling); rows are hash-partitioned, exchanged with NCCL all-to-all-v and
-joined locally (dwarf_bench_b200/distributed.py).
+N-times larger global join (weak scaling); rows are partitioned by (destination rank, table region) in one pass,
+pushed into the peers' memory by the copy engines over NVLink while the SMs scatter and probe other chunks, and
+joined locally without a second partition pass (dwarf_bench_b200/distributed.py: FoldedExchangeJoin; --exchange
+p2p / nccl select the fused SM-store exchange or the NCCL all-to-all-v baseline).
 
 One JSON line on stdout (rank 0).  `--impl reference` times the reference's own table code (oracle/_ref, or the
 oracle port when that was not built) on the host cores over a bounded sample of the same workload.
