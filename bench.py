@@ -62,7 +62,7 @@ def parse_args():
                          "memory, overlapped with the local probes (default); p2p = fused partition + SM stores into peer memory; "
                          "nccl = local partition + NCCL all-to-all-v")
     ap.add_argument("--exchange-chunks", type=int, default=0,
-                    help="fold / p2p exchange: the probe relation travels in this many pieces (0 = 2 on two GPUs, 4 on more: measured)")
+                    help="fold exchange: the probe relation travels in this many pieces (0 = 2 on two GPUs, 4 on more: measured)")
     ap.add_argument("--exchange-transport", default="ce1", choices=["sm", "ce", "ce1"],
                     help="fold exchange: runs pushed into peer memory by the copy engines -- ce1: one copy stream, peers in "
                          "rotated order (default; 4 GPUs: 4.9 ms/step against 7.0 ms with one stream per peer), ce: one stream per "
@@ -308,8 +308,7 @@ def main():
                             sync=False, stream=stream)
         launches_per_step = None
     else:
-        from dwarf_bench_b200.distributed import (CudaJoinOps, ExchangeJoin, FoldedExchangeJoin, P2PExchangeJoin,
-                                                  PipelinedP2PExchangeJoin)
+        from dwarf_bench_b200.distributed import CudaJoinOps, ExchangeJoin, FoldedExchangeJoin, P2PExchangeJoin
         exchange_used = "nccl all-to-all-v"
         xj = None
         if args.exchange in ("fold", "p2p"):
@@ -323,10 +322,6 @@ def main():
                     how += " (one block per peer, receiver walks the blocks region by region)" if args.exchange_layout == "blocked" else " (one run per peer and region)"
                     exchange_used = (f"one (rank x {xj.regions} table regions) partition pass, {how} into peer memory "
                                      f"(NVLink), probe relation in {xj.chunks} chunks overlapped with the local probes, counts by one all-gather")
-                elif args.exchange_chunks > 1:
-                    xj = PipelinedP2PExchangeJoin(eng, device, tdt, cap_rows, out_cap, chunks=args.exchange_chunks, stream=stream)
-                    exchange_used = (f"fused partition + P2P stores into peer memory (NVLink), probe relation in {args.exchange_chunks} "
-                                     "chunks overlapped with the local probes, counts by one all-gather")
                 else:
                     xj = P2PExchangeJoin(eng, device, tdt, cap_rows, out_cap, stream=stream)
                     exchange_used = "fused partition + P2P stores into peer memory (NVLink), counts by all-gather"

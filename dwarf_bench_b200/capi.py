@@ -148,6 +148,8 @@ class Engine:
         self._h = C.c_void_p()
         cfg = Config(device, key_bytes, key_bytes, flags, max_build_rows, load_factor, hash_seed)
         self._check(self.lib.dwj_create(C.byref(cfg), C.byref(self._h)))
+        self.flags = int(cfg.flags)
+        self.key_bytes = int(cfg.key_bytes)
 
     def _check(self, rc: int) -> None:
         if rc != 0:

@@ -1,26 +1,24 @@
 """Multi-GPU join: radix partition on the key hash -> exchange over NVLink -> local build + probe.
 
-Two exchange implementations:
-  P2PExchangeJoin  the partition kernel stores every row straight into the destination rank's receive buffer
-                   (peer memory mapped through torch symmetric memory): partition and transfer are ONE kernel, there
-                   is no intermediate partitioned copy and no collective on the data path -- only a tiny all-gather of
-                   the per-destination counts to plan the layout, and a symmetric-memory barrier before the local join.
+Three exchange implementations (profiles/r1_exchange.md):
+  FoldedExchangeJoin  (default) ONE partition pass groups the rows by (destination rank, table region of the
+                   destination's table); the copy engines push every rank's block into the peers' receive areas (peer
+                   memory mapped through torch symmetric memory) on one stream in rotated peer order while the SMs
+                   scatter and probe other chunks; the receiver builds / probes the blocks region by region through a
+                   segment list, without a partition pass of its own.
+  P2PExchangeJoin  the partition kernel stores every row straight into the destination rank's receive buffer: partition
+                   and transfer are ONE kernel (SM stores over NVLink), then the normal local join.
   ExchangeJoin     partition locally, then NCCL all-to-all-v (the baseline, and the fallback when peer mapping is
                    unavailable).
 
+No reference counterpart (the reference is single-device).  One process per GPU; the plumbing
+is torch.distributed.  Every rank holds an arbitrary (arrival-order) slice of both relations; equal keys must meet on
+one GPU, so there is one real exchange step per relation.  Only tiny count matrices travel through collectives.
 
-No reference counterpart (the reference is single-device).  One process per GPU; the
-plumbing is torch.distributed.  Every rank holds an arbitrary (arrival-order) slice of both relations; equal
-keys must meet on one GPU, so there is one real exchange step per relation:
-
-    dwj_partition (CUDA)          rows grouped by destination rank, per-destination offsets
-    all_to_all_single (counts)    G x G count matrix row/column for this rank (one tiny collective, one host sync)
-    all_to_all_single (columns)   keys and payloads, variable split sizes
-    dwj_build / dwj_probe_pairs   local join on the received rows (output stays sharded)
-
-The device work is delegated to a `JoinOps` object so that the host-side logic (split sizes, buffer sizing,
-ordering of collectives) can be exercised on CPU with gloo in tests, where a numpy stand-in supplied BY THE TEST
-plays the device.  The product only ever constructs `CudaJoinOps`, which calls the C ABI and nothing else.
+The device work of ExchangeJoin is delegated to a `JoinOps` object so that the host-side logic (split sizes, buffer
+sizing, ordering of collectives) can be exercised on CPU with gloo in tests, where a numpy stand-in supplied BY THE
+TEST plays the device; the layout planners (plan_*) are pure numpy / Python and tested on CPU as well.  The product
+only ever calls the C ABI.
 """
 from __future__ import annotations
 
@@ -190,80 +188,6 @@ class P2PExchangeJoin:
         return nb, np_
 
 
-def plan_chunked_exchange(counts, rank: int):
-    """counts[src][chunk][dst] = rows of `chunk` that src sends to dst.  Receive layout on every rank: chunk-major,
-    source-major inside a chunk.  Returns (offsets[chunk][dst] = row offset of THIS rank's rows of that chunk inside
-    dst's receive buffer, segments[chunk] = (first row, rows) of the chunk inside THIS rank's receive buffer)."""
-    world, chunks = len(counts), len(counts[0])
-    total = [[sum(int(counts[s][c][d]) for s in range(world)) for d in range(world)] for c in range(chunks)]
-    seg_start = [[sum(total[c2][d] for c2 in range(c)) for d in range(world)] for c in range(chunks)]
-    offsets = [[seg_start[c][d] + sum(int(counts[s][c][d]) for s in range(rank)) for d in range(world)] for c in range(chunks)]
-    segments = [(seg_start[c][rank], total[c][rank]) for c in range(chunks)]
-    return offsets, segments
-
-
-class PipelinedP2PExchangeJoin(P2PExchangeJoin):
-    """P2PExchangeJoin with the probe relation exchanged in `chunks` pieces on a second stream: while chunk c is probed,
-    chunk c+1 is already travelling over NVLink.  One all-gather plans every chunk up front (still one host sync)."""
-
-    def __init__(self, engine, device, dtype, cap_build: int, cap_probe: int, chunks: int = 4, group=None, stream=None):
-        super().__init__(engine, device, dtype, cap_build, cap_probe, group=group, stream=stream)
-        self.chunks = int(chunks)
-        self.xs = torch.cuda.Stream(device=device)                       # exchange stream
-        self.counts = torch.zeros(1 + self.chunks, self.world, dtype=torch.int64, device=device)
-        self.all_counts = torch.zeros(self.world, 1 + self.chunks, self.world, dtype=torch.int64, device=device)
-        self.chunk_counts = torch.zeros(self.chunks, dtype=torch.int64, device=device)
-        self.ev_plan = torch.cuda.Event()
-        self.ev_build = torch.cuda.Event()
-        self.ev_chunk = [torch.cuda.Event() for _ in range(self.chunks)]
-
-    def join(self, build_keys, build_vals, n_build, probe_keys, probe_vals, n_probe, out_key, out_build, out_probe,
-             capacity, d_count):
-        e, w, C = self.e, self.world, self.chunks
-        cs = self.stream if self.stream is not None else torch.cuda.current_stream()
-        bounds = [n_probe * c // C for c in range(C + 1)]
-        e.partition_hist(build_keys, n_build, w, self.counts[0], stream=cs)
-        for c in range(C):
-            e.partition_hist(probe_keys[bounds[c]:], bounds[c + 1] - bounds[c], w, self.counts[1 + c], stream=cs)
-        with torch.cuda.stream(cs):
-            dist.all_gather_into_tensor(self.all_counts.view(-1), self.counts.view(-1), group=self.group)
-            self.ev_plan.record(cs)                                    # every rank's previous join is finished
-            m = self.all_counts.cpu().tolist()                          # the one host sync of the step
-        boff, nb = plan_exchange([[m[s][0][d] for d in range(w)] for s in range(w)], self.rank)
-        poffs, segs = plan_chunked_exchange([[m[s][1 + c] for c in range(C)] for s in range(w)], self.rank)
-        np_ = sum(n for _, n in segs)
-        if nb > self.cap_build or np_ > self.cap_probe:
-            raise RuntimeError(f"receive buffers too small: {nb}/{self.cap_build} build rows, {np_}/{self.cap_probe} probe rows")
-        if np_ > capacity:
-            raise RuntimeError(f"output capacity {capacity} below the {np_} probe rows this rank receives")
-        # ---- exchange stream: build side, then the probe chunks, a barrier after each piece -------------------------
-        with torch.cuda.stream(self.xs):
-            self.xs.wait_event(self.ev_plan)
-            e.partition_scatter_to(build_keys, build_vals, n_build, w, self.dst[0], self.dst[1], boff, stream=self.xs)
-            self.hdl.barrier(channel=0)
-            self.ev_build.record(self.xs)
-            for c in range(C):
-                rows = bounds[c + 1] - bounds[c]
-                e.partition_scatter_to(probe_keys[bounds[c]:], probe_vals[bounds[c]:], rows, w, self.dst[2], self.dst[3], poffs[c],
-                                       stream=self.xs)
-                self.hdl.barrier(channel=0)
-                self.ev_chunk[c].record(self.xs)
-        # ---- compute stream: local build, then one probe per received chunk (output segment = receive segment) -------
-        cs.wait_event(self.ev_build)
-        e.build(self.cols[0], self.cols[1], nb, stream=cs)
-        for c, (row0, rows) in enumerate(segs):
-            cs.wait_event(self.ev_chunk[c])
-            e.probe_pairs(self.cols[2][row0:], self.cols[3][row0:], rows, None if out_key is None else out_key[row0:],
-                          out_build[row0:], out_probe[row0:], rows, d_n_matches=self.chunk_counts[c:], sync=False, stream=cs)
-        with torch.cuda.stream(cs):
-            torch.sum(self.chunk_counts, dim=0, keepdim=True, out=d_count)
-        self.segments = segs                                            # (first output row, rows) per chunk; chunk_counts holds the matches
-        item = self.buf.element_size()
-        self.stats.sent_rows += n_build + n_probe
-        self.stats.recv_rows += nb + np_
-        return nb, np_
-
-
 def plan_folded_exchange(counts, rank: int, regions: int, bounds):
     """Layout of the folded exchange.  counts[src][batch][dst * regions + region] = rows of `batch` (0 = the build relation,
     1.. = the probe chunks) that `src` sends to `dst` for table region `region`; bounds[c] = first row of probe chunk c
@@ -364,6 +288,8 @@ class FoldedExchangeJoin:
         #   each, so this is the layout for them.  Needs an engine with DWJ_FLAG_UNIQUE_BUILD_KEYS.
         # layout "region": the receive area itself is region-major -> ranks x regions runs per relation.
         self.transport = transport
+        if layout == "blocked" and not getattr(engine, "flags", 1) & 1:     # DWJ_FLAG_UNIQUE_BUILD_KEYS
+            layout = "region"                   # the segmented probe exists for unique build keys only
         self.layout = layout
         self.push_ctas = int(push_ctas)
         import numpy as np

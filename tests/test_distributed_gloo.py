@@ -123,25 +123,6 @@ def test_plan_exchange_layout():
             assert spans[-1][1] == plans[d][1] == sum(counts[s][d] for s in range(world))
 
 
-def test_plan_chunked_exchange_layout():
-    """Chunk-major, source-major receive layout of the pipelined exchange: every (chunk, source) range is disjoint,
-    chunks are contiguous segments, nothing lost."""
-    from dwarf_bench_b200.distributed import plan_chunked_exchange
-    rng = np.random.default_rng(4)
-    for world, chunks in ((2, 4), (8, 3), (4, 1)):
-        counts = rng.integers(0, 500, (world, chunks, world)).tolist()
-        plans = [plan_chunked_exchange(counts, r) for r in range(world)]
-        for d in range(world):
-            spans = sorted((plans[s][0][c][d], plans[s][0][c][d] + counts[s][c][d], c) for s in range(world) for c in range(chunks))
-            assert spans[0][0] == 0
-            for (a0, a1, ca), (b0, b1, cb) in zip(spans, spans[1:]):
-                assert a1 == b0 and ca <= cb                      # tiles the buffer, chunk-major
-            for c in range(chunks):
-                first, rows = plans[d][1][c]
-                mine = [sp for sp in spans if sp[2] == c]
-                assert first == mine[0][0] and first + rows == mine[-1][1] == first + sum(counts[s][c][d] for s in range(world))
-
-
 def test_plan_folded_exchange_layout():
     """Folded exchange: at every destination each relation's receive buffer is tiled exactly by the (batch, region,
     source) runs in that order; a batch is one contiguous segment; region offsets are the per-region totals; the
