@@ -140,7 +140,9 @@ DWJ_API int dwj_probe_aligned(dwj_engine *e, const void *d_keys, const void *d_v
 DWJ_API int dwj_probe_contains(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t *d_out_flags,
                        void *stream);
 
-/* Compacted join output in probe-row order: row r of the result is
+/* Compacted join output -- in probe-row order while the table is small enough to be probed directly
+ * (dwj_info.radix_parts == 1), else region by region in no particular order (same multiset; DWJ_FLAG_NO_PARTITION
+ * keeps probe-row order at any size).  Row r of the result is
  * (d_out_key[r], d_out_build_val[r], d_out_probe_val[r]); d_out_key may be NULL to skip the key
  * column.  At most `capacity` rows are written; the total match count is stored to *d_n_matches
  * (device, uint64) and, when n_matches != NULL, the call synchronises the stream and returns it
@@ -215,7 +217,9 @@ DWJ_API int dwj_xpart_hist(dwj_engine *e, const void *d_keys, uint64_t n_rows, u
 DWJ_API int dwj_xpart_scatter(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_ranks,
                       const uint64_t *start_rows, void *d_out_keys, void *d_out_vals, void *stream);
 /* dwj_build / dwj_probe_pairs for rows that are ALREADY grouped by table region (region-major): no partition pass.
- * d_region_offsets (device, regions + 1 uint64 row offsets, may be NULL) enables the build's L2 look-ahead. */
+ * d_region_offsets (device, regions + 1 uint64 row offsets, may be NULL) enables the build's L2 look-ahead.  The
+ * caller's row order carries no meaning here, so the result rows are emitted in no particular order (same multiset;
+ * one atomicAdd per warp instead of the order-preserving scan) -- as for any probe of a region-partitioned table. */
 DWJ_API int dwj_build_grouped(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows,
                       const uint64_t *d_region_offsets, void *stream);
 DWJ_API int dwj_probe_pairs_grouped(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *d_out_key,
