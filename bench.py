@@ -190,6 +190,10 @@ def main_reference(args, kind, n_build, n_probe, key_bytes, workload_name, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun pins every worker to OMP_NUM_THREADS=1; this arm is the reference's CPU path on ALL host threads and
+        # only rank 0 runs it, so undo that before the OpenMP runtime of the checker library starts.
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     if key_bytes != 4:
         out.write(json.dumps({"impl": "reference", "unavailable": "the reference Join path is uint32-only (SURVEY fact 5)"}) + "\n")
         out.flush()
