@@ -39,6 +39,24 @@ def test_c_abi_exports_every_declared_symbol(built):
     assert capi.partition_of(12345, 4, 8) in range(8) and capi.partition_of(12345, 8, 1) == 0
 
 
+def test_ctypes_binding_matches_header(built):
+    """The ctypes binding (dwarf_bench_b200/capi.py) declares, for every entry point of include/dwj.h, exactly as many
+    arguments as the prototype has -- a drifted binding would corrupt the stack silently."""
+    from dwarf_bench_b200 import capi
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "dwj.h")).read(), flags=re.S)
+    protos = dict(re.findall(r"DWJ_API [\w \*]*?\b(dwj_\w+)\(([^;]*?)\);", header, flags=re.S))
+    assert set(protos) == set(capi.SYMBOLS)
+    lib = capi.load_library()
+    for name, args in protos.items():
+        args = " ".join(args.split())
+        n_args = 0 if args in ("", "void") else args.count(",") + 1
+        argtypes = getattr(lib, name).argtypes
+        if n_args == 0:
+            assert not argtypes, name
+        else:
+            assert argtypes is not None and len(argtypes) == n_args, (name, n_args, argtypes)
+
+
 def test_no_gpu_fails_loudly(built):
     import torch
     if torch.cuda.is_available():
