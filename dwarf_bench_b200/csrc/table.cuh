@@ -143,31 +143,6 @@ DWJ_D Bucket<8> load_bucket_stream(const void *table, uint64_t b, Bucket<8> *) {
 template <int W> DWJ_D Bucket<W> load_bucket_stream(const void *table, uint64_t b) {
   return load_bucket_stream(table, b, (Bucket<W> *)nullptr);
 }
-// Coherent variant for the build kernel (other CTAs are inserting concurrently): L2 is the point of
-// coherence, so skip L1 (.cg).  A stale view can only show a slot as still empty, and the CAS that
-// follows corrects that.
-DWJ_D Bucket<4> load_bucket_cg(const void *table, uint64_t b, Bucket<4> *) {
-  Bucket<4> r;
-  const char *p = (const char *)table + (b << 5);
-  asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r.f[0]), "=r"(r.f[1]), "=r"(r.f[2]), "=r"(r.f[3]), "=r"(r.f[4]), "=r"(r.f[5]), "=r"(r.f[6]), "=r"(r.f[7])
-               : "l"(p)
-               : "memory");
-  return r;
-}
-DWJ_D Bucket<8> load_bucket_cg(const void *table, uint64_t b, Bucket<8> *) {
-  Bucket<8> r;
-  const char *p = (const char *)table + (b << 5);
-  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
-               : "=l"(r.f[0]), "=l"(r.f[1]), "=l"(r.f[2]), "=l"(r.f[3])
-               : "l"(p)
-               : "memory");
-  return r;
-}
-template <int W> DWJ_D Bucket<W> load_bucket_cg(const void *table, uint64_t b) {
-  return load_bucket_cg(table, b, (Bucket<W> *)nullptr);
-}
-
 // ---- segmented input ---------------------------------------------------------------------------------------------------
 // A relation may be handed to the build / probe kernels as a LIST OF SEGMENTS of one allocation instead of one
 // contiguous range (dwj_build_segments / dwj_probe_pairs_segments): the multi-GPU exchange delivers every source
