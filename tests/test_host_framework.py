@@ -14,8 +14,8 @@ LIB = os.path.join(ROOT, "dwarf_bench_b200", "lib")
 @pytest.fixture(scope="module")
 def built():
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-    if not os.path.exists(os.path.join(LIB, "libdwj_b200.so")):
-        subprocess.run(["make", "-C", os.path.join(ROOT, "dwarf_bench_b200", "csrc")], check=True, env=env, stdout=subprocess.DEVNULL)
+    # always through make (it knows what is up to date): a stale library must never be what gets tested
+    subprocess.run(["make", "-C", os.path.join(ROOT, "dwarf_bench_b200", "csrc")], check=True, env=env, stdout=subprocess.DEVNULL)
     subprocess.run(["make", "-C", os.path.join(ROOT, "dwarf_bench_b200", "host")], check=True, env=env, stdout=subprocess.DEVNULL)
     return LIB
 
