@@ -6,8 +6,8 @@ RunOptions / makeMeasurements surface and the `dwarf_bench` CLI).  This Python p
 ctypes binding used by tests and bench.py, plus the torch.distributed plumbing of the multi-GPU join.
 There is no CPU fallback: importing works anywhere, creating an engine needs a B200.
 """
-from .capi import (DwjError, Engine, JoinTiming, lib_path, load_library,  # noqa: F401
+from .capi import (DwjError, Engine, ExchangeJoinRank, JoinTiming, MultiGpuJoin, lib_path, load_library,  # noqa: F401
                    FLAG_L2_PERSIST, FLAG_NO_PARTITION, FLAG_UNIQUE_BUILD_KEYS, FLAG_UNORDERED_OUTPUT, OUT_ALIGNED, OUT_COUNT, OUT_PAIRS)
 
-__all__ = ["DwjError", "Engine", "JoinTiming", "lib_path", "load_library", "FLAG_L2_PERSIST",
+__all__ = ["DwjError", "Engine", "ExchangeJoinRank", "MultiGpuJoin", "JoinTiming", "lib_path", "load_library", "FLAG_L2_PERSIST",
            "FLAG_NO_PARTITION", "FLAG_UNIQUE_BUILD_KEYS", "FLAG_UNORDERED_OUTPUT", "OUT_ALIGNED", "OUT_COUNT", "OUT_PAIRS"]

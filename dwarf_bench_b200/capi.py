@@ -24,9 +24,13 @@ ERR_NAMES = {0: "DWJ_OK", -1: "DWJ_ERR_INVALID", -2: "DWJ_ERR_CUDA", -3: "DWJ_ER
 # Every symbol include/dwj.h declares (tests check the library exports exactly these).
 SYMBOLS = ("dwj_abi_version", "dwj_last_error", "dwj_create", "dwj_destroy", "dwj_get_info", "dwj_build",
            "dwj_probe_aligned", "dwj_probe_contains", "dwj_probe_pairs", "dwj_probe_count", "dwj_timings",
-           "dwj_join_host", "dwj_partition", "dwj_partition_hist", "dwj_partition_scatter_to", "dwj_partition_of",
-           "dwj_xpart_regions", "dwj_xpart_hist", "dwj_xpart_scatter", "dwj_build_grouped", "dwj_probe_pairs_grouped",
-           "dwj_copy_many", "dwj_push_runs", "dwj_build_segments", "dwj_probe_pairs_segments")
+           "dwj_join_host", "dwj_partition", "dwj_partition_hist", "dwj_partition_of",
+           "dwj_xpart_regions", "dwj_xpart_hist", "dwj_xpart_hist2", "dwj_xpart_scatter", "dwj_build_grouped",
+           "dwj_probe_pairs_grouped", "dwj_build_segments", "dwj_probe_pairs_segments", "dwj_region_scatter_segments",
+           "dwj_set_option", "dwj_xj_block_bytes", "dwj_xj_create", "dwj_xj_destroy", "dwj_xj_describe", "dwj_xj_join",
+           "dwj_xj_sync_timings", "dwj_xj_plan_send", "dwj_xj_plan_recv", "dwj_region_of", "dwj_mg_create", "dwj_mg_destroy", "dwj_mg_describe", "dwj_mg_join", "dwj_mg_join_host")
+ABI_VERSION = 2
+OPT_APPEND_OUTPUT, OPT_PASS_FILTER = 1, 2
 
 
 class DwjError(RuntimeError):
@@ -49,7 +53,36 @@ class Info(C.Structure):
     _fields_ = [("slots", C.c_uint64), ("table_bytes", C.c_uint64), ("build_rows", C.c_uint64), ("slot_bytes", C.c_uint32),
                 ("slots_per_bucket", C.c_uint32), ("l2_persist", C.c_uint32), ("sm_count", C.c_uint32),
                 ("l2_bytes", C.c_uint64), ("launches_build", C.c_uint32), ("launches_probe", C.c_uint32),
-                ("radix_parts", C.c_uint32), ("probe_passes", C.c_uint32)]
+                ("radix_parts", C.c_uint32), ("probe_passes", C.c_uint32), ("flags", C.c_uint32), ("device", C.c_int32),
+                ("hash_seed", C.c_uint64), ("max_build_rows", C.c_uint64)]
+
+
+class XjConfig(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("max_build_rows", C.c_uint64), ("max_probe_rows", C.c_uint64),
+                ("chunk_rows", C.c_uint64), ("passes", C.c_uint32), ("force_scatter_pull", C.c_uint32), ("recv_slack", C.c_double)]
+
+
+class XjInfo(C.Structure):
+    _fields_ = [("regions", C.c_uint32), ("fold_regions", C.c_uint32), ("chunks", C.c_uint32), ("ring", C.c_uint32),
+                ("passes", C.c_uint32), ("direct_pull", C.c_uint32), ("chunk_rows", C.c_uint64), ("block_bytes", C.c_uint64),
+                ("landing_bytes", C.c_uint64)]
+
+
+class XjTiming(C.Structure):
+    _fields_ = [("counts_ms", C.c_float), ("scattered_ms", C.c_float), ("built_ms", C.c_float), ("total_ms", C.c_float),
+                ("remote_bytes", C.c_uint64)]
+
+
+class MgConfig(C.Structure):
+    _fields_ = [("n_gpus", C.c_int32), ("devices", C.c_int32 * 8), ("key_bytes", C.c_int32), ("flags", C.c_uint32),
+                ("max_build_rows_per_gpu", C.c_uint64), ("max_probe_rows_per_gpu", C.c_uint64), ("load_factor", C.c_double),
+                ("hash_seed", C.c_uint64), ("chunk_rows", C.c_uint64), ("passes", C.c_uint32), ("force_scatter_pull", C.c_uint32),
+                ("recv_slack", C.c_double)]
+
+
+class MgTiming(C.Structure):
+    _fields_ = [("counts_ms", C.c_float), ("partition_ms", C.c_float), ("build_ms", C.c_float), ("total_ms", C.c_float),
+                ("remote_bytes", C.c_uint64)]
 
 
 @dataclass
@@ -97,7 +130,6 @@ def load_library():
                                   C.POINTER(Timing)]
     lib.dwj_partition.argtypes = [vp, vp, vp, u64, u32, vp, vp, vp, vp]
     lib.dwj_partition_hist.argtypes = [vp, vp, u64, u32, vp, vp]
-    lib.dwj_partition_scatter_to.argtypes = [vp, vp, vp, u64, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), vp]
     lib.dwj_partition_of.argtypes = [u64, C.c_int32, u32, u64]
     lib.dwj_partition_of.restype = u32
     lib.dwj_xpart_regions.argtypes = [vp, u32]
@@ -106,13 +138,30 @@ def load_library():
     lib.dwj_xpart_scatter.argtypes = [vp, vp, vp, u64, u32, C.POINTER(u64), vp, vp, vp]
     lib.dwj_build_grouped.argtypes = [vp, vp, vp, u64, vp, vp]
     lib.dwj_probe_pairs_grouped.argtypes = [vp, vp, vp, u64, vp, vp, vp, u64, vp, C.POINTER(u64), vp]
-    lib.dwj_copy_many.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(vp)]
-    lib.dwj_push_runs.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), u32, vp]
-    lib.dwj_build_segments.argtypes = [vp, vp, vp, u32, C.POINTER(u64), C.POINTER(u64), u32, vp]
-    lib.dwj_probe_pairs_segments.argtypes = [vp, vp, vp, u32, C.POINTER(u64), C.POINTER(u64), vp, vp, vp, u64, vp, C.POINTER(u64), vp]
+    vpp, u64p = C.POINTER(vp), C.POINTER(u64)
+    lib.dwj_xpart_hist2.argtypes = [vp, vp, u64, u32, vp, vp]
+    lib.dwj_build_segments.argtypes = [vp, u32, vpp, vpp, u64p, u32, vp]
+    lib.dwj_probe_pairs_segments.argtypes = [vp, u32, vpp, vpp, u64p, vp, vp, vp, u64, vp, u64p, vp]
+    lib.dwj_region_scatter_segments.argtypes = [vp, u32, vpp, vpp, u64p, u64p, vp, vp, vp]
+    lib.dwj_set_option.argtypes = [vp, C.c_int, u64]
+    lib.dwj_xj_block_bytes.argtypes = [vp, C.POINTER(XjConfig), u64p]
+    lib.dwj_xj_create.argtypes = [vp, C.POINTER(XjConfig), vpp, C.POINTER(vp)]
+    lib.dwj_xj_destroy.argtypes = [vp]
+    lib.dwj_xj_describe.argtypes = [vp, C.POINTER(XjInfo)]
+    lib.dwj_xj_join.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp, vp, vp, u64, vp, vp]
+    lib.dwj_xj_sync_timings.argtypes = [vp, C.POINTER(XjTiming)]
+    lib.dwj_xj_plan_send.argtypes = [u32, u32, u32, u64, u64p, u64p]
+    lib.dwj_xj_plan_recv.argtypes = [u32, u32, u32, u64, u64p, u64p, C.c_int, u64p, u64p, u64p, u64p]
+    lib.dwj_region_of.argtypes = [u64, C.c_int32, u64, u32, u64]
+    lib.dwj_region_of.restype = u32
+    lib.dwj_mg_create.argtypes = [C.POINTER(MgConfig), C.POINTER(vp)]
+    lib.dwj_mg_destroy.argtypes = [vp]
+    lib.dwj_mg_describe.argtypes = [vp, u32, C.POINTER(XjInfo)]
+    lib.dwj_mg_join.argtypes = [vp, vpp, vpp, u64p, vpp, vpp, u64p, vpp, vpp, vpp, u64p, u64p, C.POINTER(MgTiming)]
+    lib.dwj_mg_join_host.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp, vp, vp, u64, u64p, C.POINTER(MgTiming)]
     for name in SYMBOLS:
         f = getattr(lib, name)
-        if name not in ("dwj_last_error", "dwj_partition_of", "dwj_xpart_regions"):
+        if name not in ("dwj_last_error", "dwj_partition_of", "dwj_xpart_regions", "dwj_region_of"):
             f.restype = C.c_int
     _lib = lib
     return lib
@@ -227,16 +276,6 @@ class Engine:
     def partition_hist(self, d_keys, n_rows: int, n_parts: int, d_counts, stream=None) -> None:
         self._check(self.lib.dwj_partition_hist(self._h, _ptr(d_keys), n_rows, n_parts, _ptr(d_counts), _stream(stream)))
 
-    def partition_scatter_to(self, d_keys, d_vals, n_rows: int, n_parts: int, dst_keys, dst_vals, dst_row_offsets,
-                             stream=None) -> None:
-        """dst_keys / dst_vals: sequences of device pointers (ints), possibly peer memory; dst_row_offsets: ints."""
-        pk = (C.c_void_p * n_parts)(*[int(x) for x in dst_keys])
-        pv = (C.c_void_p * n_parts)(*[int(x) for x in dst_vals]) if d_vals is not None else None
-        off = (C.c_uint64 * n_parts)(*[int(x) for x in dst_row_offsets])
-        self._check(self.lib.dwj_partition_scatter_to(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, n_parts, pk, pv, off,
-                                                      _stream(stream)))
-
-
     # ---- exchange partition folded with the receiver's region grouping (include/dwj.h, dwj_xpart_*) -------------------
     def xpart_regions(self, n_ranks: int) -> int:
         return int(self.lib.dwj_xpart_regions(self._h, n_ranks))
@@ -265,56 +304,148 @@ class Engine:
         self._check(rc)
         return int(n.value) if sync else None
 
-    def build_segments(self, d_keys, d_vals, seg_first_row, seg_rows, segments_per_region: int = 0, stream=None) -> None:
+    @staticmethod
+    def _seg_arrays(seg_keys, seg_vals, seg_rows):
         import numpy as np
-        f, r = (np.ascontiguousarray(a, dtype=np.uint64) for a in (seg_first_row, seg_rows))
-        u64p = C.POINTER(C.c_uint64)
-        self._check(self.lib.dwj_build_segments(self._h, _ptr(d_keys), _ptr(d_vals), len(f), f.ctypes.data_as(u64p),
-                                                r.ctypes.data_as(u64p), segments_per_region, _stream(stream)))
+        k, r = np.ascontiguousarray(seg_keys, dtype=np.uint64), np.ascontiguousarray(seg_rows, dtype=np.uint64)
+        v = None if seg_vals is None else np.ascontiguousarray(seg_vals, dtype=np.uint64)
+        vpp, u64p = C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)
+        return (k, v, r), len(k), k.ctypes.data_as(vpp), None if v is None else v.ctypes.data_as(vpp), r.ctypes.data_as(u64p)
 
-    def probe_pairs_segments(self, d_keys, d_vals, seg_first_row, seg_rows, d_out_key, d_out_build_val, d_out_probe_val,
+    def build_segments(self, seg_keys, seg_vals, seg_rows, segments_per_region: int = 0, stream=None) -> None:
+        """seg_keys / seg_vals: device pointers (ints) of each segment's first key / payload -- local or peer memory."""
+        keep, n, k, v, r = self._seg_arrays(seg_keys, seg_vals, seg_rows)
+        self._check(self.lib.dwj_build_segments(self._h, n, k, v, r, segments_per_region, _stream(stream)))
+
+    def probe_pairs_segments(self, seg_keys, seg_vals, seg_rows, d_out_key, d_out_build_val, d_out_probe_val,
                              capacity: int, d_n_matches=None, sync: bool = True, stream=None):
-        import numpy as np
-        f, r = (np.ascontiguousarray(a, dtype=np.uint64) for a in (seg_first_row, seg_rows))
-        u64p = C.POINTER(C.c_uint64)
-        n = C.c_uint64(0)
-        rc = self.lib.dwj_probe_pairs_segments(self._h, _ptr(d_keys), _ptr(d_vals), len(f), f.ctypes.data_as(u64p),
-                                               r.ctypes.data_as(u64p), _ptr(d_out_key), _ptr(d_out_build_val),
-                                               _ptr(d_out_probe_val), capacity, _ptr(d_n_matches), C.byref(n) if sync else None,
-                                               _stream(stream))
+        keep, n, k, v, r = self._seg_arrays(seg_keys, seg_vals, seg_rows)
+        cnt = C.c_uint64(0)
+        rc = self.lib.dwj_probe_pairs_segments(self._h, n, k, v, r, _ptr(d_out_key), _ptr(d_out_build_val), _ptr(d_out_probe_val),
+                                               capacity, _ptr(d_n_matches), C.byref(cnt) if sync else None, _stream(stream))
         self._check(rc)
-        return int(n.value) if sync else None
+        return int(cnt.value) if sync else None
 
-    def copy_many(self, copies) -> None:
-        """copies: list of (dst pointer, src pointer, bytes, stream); device-to-device, possibly to peer memory."""
-        n = len(copies)
-        if not n:
-            return
-        d = (C.c_void_p * n)(*[int(c[0]) for c in copies])
-        s = (C.c_void_p * n)(*[int(c[1]) for c in copies])
-        b = (C.c_uint64 * n)(*[int(c[2]) for c in copies])
-        st = (C.c_void_p * n)(*[_stream(c[3]) for c in copies])
-        self._check(self.lib.dwj_copy_many(self._h, n, d, s, b, st))
-
-
-    def push_runs(self, dsts, srcs, rows, n_ctas: int = 0, stream=None) -> None:
-        """dwj_push_runs from three equally long numpy uint64 arrays (pointers, pointers, row counts)."""
+    def region_scatter_segments(self, seg_keys, seg_vals, seg_rows, start_rows, d_out_keys, d_out_vals, stream=None) -> None:
         import numpy as np
-        arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in (dsts, srcs, rows)]
-        vpp, u64p = C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)
-        self._check(self.lib.dwj_push_runs(self._h, len(arrs[0]), arrs[0].ctypes.data_as(vpp), arrs[1].ctypes.data_as(vpp),
-                                           arrs[2].ctypes.data_as(u64p), n_ctas, _stream(stream)))
+        keep, n, k, v, r = self._seg_arrays(seg_keys, seg_vals, seg_rows)
+        st = np.ascontiguousarray(start_rows, dtype=np.uint64)
+        self._check(self.lib.dwj_region_scatter_segments(self._h, n, k, v, r, st.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                         _ptr(d_out_keys), _ptr(d_out_vals), _stream(stream)))
 
-    def copy_many_arrays(self, dsts, srcs, nbytes, streams) -> None:
-        """dwj_copy_many from four equally long numpy uint64 arrays (no per-copy Python work)."""
-        import numpy as np
-        arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in (dsts, srcs, nbytes, streams)]
-        n = len(arrs[0])
-        if not n:
-            return
-        vpp, u64p = C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)
-        self._check(self.lib.dwj_copy_many(self._h, n, arrs[0].ctypes.data_as(vpp), arrs[1].ctypes.data_as(vpp),
-                                           arrs[2].ctypes.data_as(u64p), arrs[3].ctypes.data_as(vpp)))
+    def xpart_hist2(self, d_keys, n_rows: int, n_ranks: int, d_counts, stream=None) -> None:
+        self._check(self.lib.dwj_xpart_hist2(self._h, _ptr(d_keys), n_rows, n_ranks, _ptr(d_counts), _stream(stream)))
+
+    def set_option(self, option: int, value: int) -> None:
+        self._check(self.lib.dwj_set_option(self._h, option, value))
+
+    def set_pass_filter(self, rank_bits: int, pass_bits: int, pass_id: int) -> None:
+        self.set_option(OPT_PASS_FILTER, rank_bits | pass_bits << 8 | pass_id << 16)
+
+
+class ExchangeJoinRank:
+    """dwj_xj: this rank's end of the multi-GPU pull-exchange join (include/dwj.h).  `blocks`: this process's pointers to
+    every rank's block (each `block_bytes(...)` bytes, peer-mapped)."""
+
+    def __init__(self, engine: Engine, rank: int, world: int, max_build_rows: int, max_probe_rows: int, blocks,
+                 chunk_rows: int = 0, passes: int = 1, recv_slack: float = 0.0, force_scatter_pull: bool = False):
+        self.lib = engine.lib
+        self.engine = engine
+        self.cfg = XjConfig(rank, world, max_build_rows, max_probe_rows, chunk_rows, passes, 1 if force_scatter_pull else 0, recv_slack)
+        self._h = C.c_void_p()
+        arr = (C.c_void_p * world)(*[int(b) for b in blocks])
+        engine._check(self.lib.dwj_xj_create(engine._h, C.byref(self.cfg), arr, C.byref(self._h)))
+
+    @staticmethod
+    def block_bytes(engine: Engine, rank: int, world: int, max_build_rows: int, max_probe_rows: int, chunk_rows: int = 0,
+                    passes: int = 1, recv_slack: float = 0.0, force_scatter_pull: bool = False) -> int:
+        cfg = XjConfig(rank, world, max_build_rows, max_probe_rows, chunk_rows, passes, 1 if force_scatter_pull else 0, recv_slack)
+        n = C.c_uint64(0)
+        engine._check(engine.lib.dwj_xj_block_bytes(engine._h, C.byref(cfg), C.byref(n)))
+        return int(n.value)
+
+    def describe(self) -> dict:
+        i = XjInfo()
+        self.engine._check(self.lib.dwj_xj_describe(self._h, C.byref(i)))
+        return {f: getattr(i, f) for f, _ in XjInfo._fields_}
+
+    def join(self, build_keys, build_vals, n_build, probe_keys, probe_vals, n_probe, out_key, out_build, out_probe, capacity,
+             d_count, stream=None) -> None:
+        self.engine._check(self.lib.dwj_xj_join(self._h, _ptr(build_keys), _ptr(build_vals), n_build, _ptr(probe_keys), _ptr(probe_vals),
+                                                n_probe, _ptr(out_key), _ptr(out_build), _ptr(out_probe), capacity, _ptr(d_count),
+                                                _stream(stream)))
+
+    def sync_timings(self) -> dict:
+        t = XjTiming()
+        self.engine._check(self.lib.dwj_xj_sync_timings(self._h, C.byref(t)))
+        return {f: getattr(t, f) for f, _ in XjTiming._fields_}
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.dwj_xj_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiGpuJoin:
+    """dwj_mg: all GPUs of the box from this one process (what `dwarf_bench Join --gpus N` calls)."""
+
+    def __init__(self, devices, key_bytes: int, max_build_rows_per_gpu: int, max_probe_rows_per_gpu: int, flags: int = FLAG_UNIQUE_BUILD_KEYS,
+                 load_factor: float = 0.0, hash_seed: int = 42, chunk_rows: int = 0, passes: int = 1, recv_slack: float = 0.0,
+                 force_scatter_pull: bool = False):
+        self.lib = load_library()
+        self.n = len(devices)
+        self.key_bytes = key_bytes
+        cfg = MgConfig()
+        cfg.n_gpus = self.n
+        for i, d in enumerate(devices):
+            cfg.devices[i] = d
+        cfg.key_bytes, cfg.flags = key_bytes, flags
+        cfg.max_build_rows_per_gpu, cfg.max_probe_rows_per_gpu = max_build_rows_per_gpu, max_probe_rows_per_gpu
+        cfg.load_factor, cfg.hash_seed, cfg.chunk_rows, cfg.passes = load_factor, hash_seed, chunk_rows, passes
+        cfg.force_scatter_pull, cfg.recv_slack = (1 if force_scatter_pull else 0), recv_slack
+        self._h = C.c_void_p()
+        self._check(self.lib.dwj_mg_create(C.byref(cfg), C.byref(self._h)))
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise DwjError(rc, self.lib.dwj_last_error().decode())
+
+    def describe(self, rank: int = 0) -> dict:
+        i = XjInfo()
+        self._check(self.lib.dwj_mg_describe(self._h, rank, C.byref(i)))
+        return {f: getattr(i, f) for f, _ in XjInfo._fields_}
+
+    def join_host(self, build_keys, build_vals, probe_keys, probe_vals, out_key, out_build, out_probe):
+        """numpy columns in, numpy columns out (out_key may be None).  Returns (rows, timing dict)."""
+        n = C.c_uint64(0)
+        t = MgTiming()
+        self._check(self.lib.dwj_mg_join_host(self._h, _ptr(build_keys), _ptr(build_vals), len(build_keys), _ptr(probe_keys),
+                                              _ptr(probe_vals), len(probe_keys), _ptr(out_key), _ptr(out_build), _ptr(out_probe),
+                                              len(out_build), C.byref(n), C.byref(t)))
+        return int(n.value), {f: getattr(t, f) for f, _ in MgTiming._fields_}
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.dwj_mg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def partition_of(key: int, key_bytes: int, n_parts: int, hash_seed: int = 42) -> int:

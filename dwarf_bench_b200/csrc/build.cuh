@@ -40,6 +40,9 @@ template <int W> struct BuildArgs {
   const Seg *segs;
   uint32_t n_segs;
   uint32_t segs_per_region;
+  PassFilter filter;                   // rows of other key classes are skipped (table.cuh)
+  const unsigned long long *n_dev;     // non-null: the row count lives on the device (a filtered partition pass produced
+                                       // the input); `n` is then only an upper bound that sizes the grid
 };
 
 DWJ_D void store_slot(void *table, uint64_t b, uint32_t i, uint32_t k, uint32_t v) {
@@ -99,14 +102,18 @@ __global__ void __launch_bounds__(256) build_kernel(BuildArgs<W> a) {
   using K = typename KeyT<W>::type;
   constexpr uint32_t SLOTS = Bucket<W>::SLOTS;
   constexpr uint64_t TILE = 256ull * ROWS;
-  const uint64_t tiles = a.n_segs ? a.n : (a.n + TILE - 1) / TILE;
+  const uint64_t n_rows = a.n_dev ? min((uint64_t)__ldg(a.n_dev), a.n) : a.n;
+  const uint64_t tiles = a.n_segs ? a.n : (n_rows + TILE - 1) / TILE;
   for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    uint64_t base = tile * TILE + threadIdx.x, limit = a.n;
-    if (a.n_segs) {
+    uint64_t base = tile * TILE + threadIdx.x, limit = n_rows;
+    const K *kp = a.keys, *vp = a.vals;
+    if (a.n_segs) {                                        // the tile's rows live in one segment (possibly peer memory)
       const uint32_t si = find_segment(a.segs, a.n_segs, tile);
       const Seg sg = a.segs[si];
-      base = sg.phys_row + (tile - sg.first_unit) * TILE + threadIdx.x;
-      limit = sg.phys_row + sg.rows;
+      kp = (const K *)sg.keys;
+      vp = (const K *)sg.vals;
+      base = (tile - sg.first_unit) * TILE + threadIdx.x;
+      limit = sg.rows;
       if (a.regions > 1) prefetch_next_region_segs<W>(a, si, tile);
     } else if (a.regions > 1) {
       prefetch_next_region<W>(a, tile * TILE, TILE);
@@ -118,8 +125,12 @@ __global__ void __launch_bounds__(256) build_kernel(BuildArgs<W> a) {
     for (int r = 0; r < ROWS; ++r) {
       const uint64_t i = base + (uint64_t)r * 256;
       const bool live = i < limit;
-      k[r] = live ? load_stream(a.keys + i) : ~(K)0;       // the reserved key (and a row past the end) is never stored
-      v[r] = live ? load_stream(a.vals + i) : ~(K)0;
+      k[r] = live ? load_stream(kp + i) : ~(K)0;           // the reserved key (and a row past the end) is never stored
+      v[r] = live ? load_stream(vp + i) : ~(K)0;
+    }
+    if (a.filter.mask) {                                   // grid-uniform: rows of other key classes count as absent
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) k[r] = pass_ok(k[r], a.seed, a.filter) ? k[r] : ~(K)0;
     }
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {

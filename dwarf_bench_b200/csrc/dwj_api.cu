@@ -85,18 +85,22 @@ struct dwj_engine {
   unsigned long long *part_scratch = nullptr;  // hist[PART_MAX] + cursor[PART_MAX] + region offsets[PART_MAX + 1]
   // segmented input (dwj_*_segments): ring of segment tables, and the caller's list while a call is in flight
   dwj::Seg *seg_tables = nullptr, *seg_tables_host = nullptr;
-  cudaEvent_t seg_done[8]{};
+  cudaEvent_t seg_done[32]{};
   uint32_t seg_calls = 0;
-  const uint64_t *pending_seg_first = nullptr, *pending_seg_rows = nullptr;
+  const void *const *pending_seg_keys = nullptr, *const *pending_seg_vals = nullptr;
+  const uint64_t *pending_seg_rows = nullptr;
   uint32_t pending_segs = 0, pending_segs_per_region = 0;
-  // dwj_push_runs: a ring of PUSH_SLOTS run tables (device + pinned staging), so the host never waits for a table that
-  // is still queued behind earlier work on the stream
-  dwj::PushRun *push_runs = nullptr, *push_runs_host = nullptr;
-  cudaEvent_t push_done[8]{};
-  uint32_t push_calls = 0;
+  // Small host arrays (scatter start rows) travel through a ring of PINNED staging slots: an asynchronous copy from
+  // pageable memory synchronises the stream first, and a stream of the multi-GPU join may be parked behind a kernel that
+  // waits for work this very host thread has yet to enqueue.
+  unsigned long long *pin_ring = nullptr;
+  cudaEvent_t pin_done[64]{};
+  uint32_t pin_calls = 0;
+  dwj::PassFilter filter{};                    // DWJ_OPT_PASS_FILTER
+  bool append_output = false;                  // DWJ_OPT_APPEND_OUTPUT
   unsigned long long *xpart_cursor = nullptr;  // PART_MAX cursors of dwj_xpart_scatter (own scratch: may run beside a local join)
-  unsigned long long *xchg_cursor = nullptr;   // 8 cursors of dwj_partition_scatter_to: its own scratch, so an exchange
-                                               // on one stream can overlap a build/probe (region partition) on another
+  unsigned long long *pull_cursor = nullptr;   // PART_MAX cursors of dwj_region_scatter_segments: its own scratch, so the
+                                               // receiving scatter on one stream can overlap a sending one on another
   // L2-locality regions: inputs are radix-partitioned on the top `region_bits` bits of the bucket index first
   uint32_t region_bits = 0;
   void *region_build = nullptr, *region_probe = nullptr;   // partitioned copies (keys then payloads)
@@ -150,6 +154,32 @@ int ensure_tile_state(dwj_engine *e, uint64_t tiles, cudaStream_t s) {
   return DWJ_OK;
 }
 
+// Small host arrays (scatter start rows, segment tables) reach the device through a KERNEL that reads a pinned, mapped
+// staging slot -- not through cudaMemcpyAsync.  Two reasons, both met on hardware: an asynchronous copy from pageable
+// memory synchronises the stream first; and copy-engine jobs of different streams share hardware queues, so a copy
+// that waits behind a flag-polling kernel of the multi-GPU join (dwj_xj.cu) holds up another stream's copy that the
+// polled flag depends on -- a dependency cycle the streams themselves do not contain.  Kernels have their own queues.
+__global__ void stage_words_kernel(unsigned long long *dst, const unsigned long long *src, uint32_t words) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+int stage_words(unsigned long long *dst, const unsigned long long *pinned_src, uint32_t words, cudaStream_t s) {
+  if (!words) return DWJ_OK;
+  stage_words_kernel<<<(words + 255) / 256 > 8 ? 8 : (words + 255) / 256, 256, 0, s>>>(dst, pinned_src, words);
+  CU(cudaGetLastError());
+  return DWJ_OK;
+}
+// dst[0 .. words) = src[0 .. words) (words <= PART_MAX) on stream s; src may be reused at once.
+constexpr uint32_t PIN_SLOTS = 64;
+int upload_words(dwj_engine *e, unsigned long long *dst, const uint64_t *src, uint32_t words, cudaStream_t s) {
+  const uint32_t slot = e->pin_calls++ % PIN_SLOTS;
+  if (e->pin_calls > PIN_SLOTS) CU(cudaEventSynchronize(e->pin_done[slot]));     // the copy PIN_SLOTS calls ago has left the slot
+  unsigned long long *h = e->pin_ring + (size_t)slot * dwj::PART_MAX;
+  memcpy(h, src, words * sizeof(unsigned long long));
+  if (int rc = stage_words(dst, h, words, s)) return rc;
+  CU(cudaEventRecord(e->pin_done[slot], s));
+  return DWJ_OK;
+}
+
 // Thread-private byte counters (histogram, > 8 partitions) and the ballot-ranked, shared-memory-staged scatter.
 template <int W, uint32_t MODE, int THREADS>
 int hist_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
@@ -174,9 +204,22 @@ template <int W, uint32_t MODE> int hist_launch_mode(dwj_engine *e, const dwj::P
   }
   return a.log2_parts <= 8 ? hist_many_launch<W, MODE, 256>(e, a, s) : hist_many_launch<W, MODE, 128>(e, a, s);
 }
+// Shared-memory RED histogram: any partition count up to 4096 and the only one that honours the pass filter.
+template <int W, uint32_t MODE> int hist_red_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
+  constexpr int HROWS = 8;
+  const uint64_t htiles = (a.n + 256ull * HROWS - 1) / (256ull * HROWS);
+  const unsigned grid = (unsigned)std::min<uint64_t>(htiles, (uint64_t)e->prop.multiProcessorCount * 8);
+  CU(launch(e, dwj::partition_hist_red_kernel<W, MODE, HROWS>, dim3(grid), dim3(dwj::PART_THREADS), s, a, false, sizeof(unsigned int) << a.log2_parts));
+  return DWJ_OK;
+}
 // Histogram of a.keys into a.hist (zeroed by the caller).
 template <int W> int hist_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
   if (!a.n) return DWJ_OK;
+  if (a.filter.mask || a.log2_parts > 9) {
+    if (a.mode == dwj::PART_BY_BUCKET) return hist_red_launch<W, dwj::PART_BY_BUCKET>(e, a, s);
+    if (a.mode == dwj::PART_BY_HASH) return hist_red_launch<W, dwj::PART_BY_HASH>(e, a, s);
+    return hist_red_launch<W, dwj::PART_BY_BOTH>(e, a, s);
+  }
   if (a.mode == dwj::PART_BY_BUCKET) return hist_launch_mode<W, dwj::PART_BY_BUCKET>(e, a, s);
   if (a.mode == dwj::PART_BY_HASH) return hist_launch_mode<W, dwj::PART_BY_HASH>(e, a, s);
   return hist_launch_mode<W, dwj::PART_BY_BOTH>(e, a, s);
@@ -186,7 +229,7 @@ template <int W, int BITS>
 int scatter_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
   constexpr int THREADS = 256, ITEMS = W == 4 ? 16 : 8, MINB = 3;
   using SM = dwj::ScatterManySmem<W, THREADS, ITEMS>;
-  const uint64_t tiles = (a.n + SM::TILE - 1) / SM::TILE;
+  const uint64_t tiles = a.n_segs ? a.n : (a.n + SM::TILE - 1) / SM::TILE;
   auto kern = dwj::partition_scatter_many_kernel<W, BITS, THREADS, ITEMS, MINB>;
   CU(launch(e, kern, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(THREADS), s, a, false, SM::bytes(1u << BITS)));
   return DWJ_OK;
@@ -195,7 +238,8 @@ int scatter_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStrea
 template <int W> int scatter_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
   if (!a.n) return DWJ_OK;
   switch (a.log2_parts) {
-  case 0:                         // one partition: a copy
+  case 0:                         // one partition: a copy -- unless rows are filtered or gathered from segments
+    if (a.filter.mask || a.n_segs) return scatter_many_launch<W, 1>(e, a, s);     // every row has partition id 0
     CU(cudaMemcpyAsync(a.out_keys, a.keys, a.n * W, cudaMemcpyDeviceToDevice, s));
     if (a.vals) CU(cudaMemcpyAsync(a.out_vals, a.vals, a.n * W, cudaMemcpyDeviceToDevice, s));
     return DWJ_OK;
@@ -224,6 +268,7 @@ dwj::PartitionArgs<W> partition_args(const dwj_engine *e, const void *keys, cons
   a.mode = mode;
   a.rank_bits = rank_bits;
   a.bucket_mask = e->buckets - 1;
+  a.filter = e->filter;
   uint32_t lgb = 0;
   while ((1ull << lgb) < e->buckets) ++lgb;
   const uint32_t region_bits = mode == dwj::PART_BY_BOTH ? log2_parts - rank_bits : log2_parts;
@@ -270,47 +315,13 @@ int partition_scatter_planned_impl(dwj_engine *e, const void *keys, const void *
   a.out_keys = (K *)ok;
   a.out_vals = (K *)ov;
   a.cursor = e->xpart_cursor;
-  // pageable source: staged before the call returns, so the caller's array may be reused at once
-  CU(cudaMemcpyAsync(a.cursor, h_start_rows, sizeof(uint64_t) << log2_parts, cudaMemcpyHostToDevice, s));
-  if (log2_parts == 0 && n) {       // one partition: a copy to the planned position
+  if (int rc = upload_words(e, a.cursor, h_start_rows, 1u << log2_parts, s)) return rc;     // the caller's array may be reused at once
+  if (log2_parts == 0 && n && !a.filter.mask) {       // one partition: a copy to the planned position
     CU(cudaMemcpyAsync((K *)ok + h_start_rows[0], keys, n * W, cudaMemcpyDeviceToDevice, s));
     if (vals) CU(cudaMemcpyAsync((K *)ov + h_start_rows[0], vals, n * W, cudaMemcpyDeviceToDevice, s));
     return DWJ_OK;
   }
   return scatter_launch<W>(e, a, s);
-}
-
-// Scatter straight into per-partition destinations (local or peer memory); <= 8 partitions.  The caller has planned
-// the layout: rows of partition p go to dst_keys[p][row_offsets[p] ...].
-template <int W>
-int partition_scatter_to_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, uint32_t log2_parts, void *const *dst_keys,
-                              void *const *dst_vals, const uint64_t *row_offsets, cudaStream_t s) {
-  using K = typename dwj::KeyT<W>::type;
-  dwj::PartitionArgs<W> a{};
-  a.keys = (const K *)keys;
-  a.vals = (const K *)vals;
-  a.n = n;
-  a.log2_parts = log2_parts;
-  a.seed = e->cfg.hash_seed;
-  a.mode = dwj::PART_BY_HASH;
-  a.use_dst = 1;
-  a.cursor = e->xchg_cursor;
-  unsigned long long start[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (uint32_t p = 0; p < (1u << log2_parts); ++p) {
-    a.dst_keys[p] = (K *)dst_keys[p];
-    a.dst_vals[p] = vals ? (K *)dst_vals[p] : nullptr;
-    start[p] = row_offsets[p];
-  }
-  // The cursors start at the planned offsets; cudaMemcpyAsync from a stack array is safe because pageable H2D copies
-  // are staged before the call returns.
-  CU(cudaMemcpyAsync(a.cursor, start, sizeof(start), cudaMemcpyHostToDevice, s));
-  if (!n) return DWJ_OK;
-  // Staged variant: destinations may sit behind NVLink, which wants 128-byte pieces (partition.cuh).
-  constexpr int ITEMS8 = W == 4 ? 16 : 8;
-  const uint64_t tiles8 = (n + 256ull * ITEMS8 - 1) / (256ull * ITEMS8);
-  const dim3 grid((unsigned)std::min<uint64_t>(tiles8, 0x7fffffffull));
-  CU(launch(e, dwj::partition_scatter8_staged_kernel<W, ITEMS8>, grid, dim3(dwj::PART_THREADS), s, a, false));
-  return DWJ_OK;
 }
 
 // Grow-only scratch for the region-partitioned copy of a relation: [keys | payloads], rows each.
@@ -330,27 +341,44 @@ int ensure_region_buffer(void **buf, uint64_t *cap_rows, uint64_t rows, int W, c
 // Segment table of the pending dwj_*_segments call for a kernel whose work unit is `unit_rows` rows: uploads
 // {first unit, first row, rows} per segment (+ a closing entry) through a ring of pinned / device tables.  The caller
 // records e->seg_done[slot] after the kernel that reads the table.
-constexpr uint32_t SEG_SLOTS = 8, SEG_MAX = dwj::PART_MAX + 1;
+constexpr uint32_t SEG_SLOTS = 32, SEG_MAX = dwj::PART_MAX + 1;
 int upload_segments(dwj_engine *e, uint64_t unit_rows, cudaStream_t s, const dwj::Seg **d_out, uint64_t *total_units, uint32_t *slot_out) {
-  if (!e->seg_tables) {
-    CU(cudaMalloc((void **)&e->seg_tables, SEG_SLOTS * SEG_MAX * sizeof(dwj::Seg)));
-    CU(cudaHostAlloc((void **)&e->seg_tables_host, SEG_SLOTS * SEG_MAX * sizeof(dwj::Seg), cudaHostAllocDefault));
-    for (auto &ev : e->seg_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  }
   const uint32_t slot = e->seg_calls++ % SEG_SLOTS;
   if (e->seg_calls > SEG_SLOTS) CU(cudaEventSynchronize(e->seg_done[slot]));
   dwj::Seg *h = e->seg_tables_host + slot * SEG_MAX, *d = e->seg_tables + slot * SEG_MAX;
   unsigned long long units = 0;
   for (uint32_t i = 0; i < e->pending_segs; ++i) {
-    h[i] = dwj::Seg{units, e->pending_seg_first[i], e->pending_seg_rows[i]};
+    h[i] = dwj::Seg{units, e->pending_seg_keys[i], e->pending_seg_vals ? e->pending_seg_vals[i] : nullptr, e->pending_seg_rows[i]};
     units += (e->pending_seg_rows[i] + unit_rows - 1) / unit_rows;
   }
-  h[e->pending_segs] = dwj::Seg{units, 0, 0};
-  CU(cudaMemcpyAsync(d, h, (e->pending_segs + 1) * sizeof(dwj::Seg), cudaMemcpyHostToDevice, s));
+  h[e->pending_segs] = dwj::Seg{units, nullptr, nullptr, 0};
+  static_assert(sizeof(dwj::Seg) % sizeof(unsigned long long) == 0, "Seg is staged word by word");
+  if (int rc = stage_words((unsigned long long *)d, (const unsigned long long *)h, (e->pending_segs + 1) * (uint32_t)(sizeof(dwj::Seg) / 8), s)) return rc;
   *d_out = d;
   *total_units = units;
   *slot_out = slot;
   return DWJ_OK;
+}
+
+template <int W>
+int region_scatter_segments_impl(dwj_engine *e, const uint64_t *h_start_rows, void *ok, void *ov, bool with_vals, cudaStream_t s) {
+  using K = typename dwj::KeyT<W>::type;
+  dwj::PartitionArgs<W> a = partition_args<W>(e, nullptr, nullptr, 0, e->region_bits, dwj::PART_BY_BUCKET, 0);
+  a.filter = dwj::PassFilter{};                 // the sender already dropped the rows of other key classes
+  a.out_keys = (K *)ok;
+  a.out_vals = (K *)ov;
+  a.cursor = e->pull_cursor;
+  if (int rc = upload_words(e, a.cursor, h_start_rows, 1u << e->region_bits, s)) return rc;
+  constexpr uint64_t TILE = dwj::ScatterManySmem<W, 256, W == 4 ? 16 : 8>::TILE;
+  uint64_t tiles = 0;
+  uint32_t slot = 0;
+  if (int rc = upload_segments(e, TILE, s, &a.segs, &tiles, &slot)) return rc;
+  a.n = tiles;
+  a.n_segs = e->pending_segs;
+  if (with_vals) a.vals = (const K *)(uintptr_t)1;      // non-null: the kernel takes the payload pointers from the segments
+  const int rc = scatter_launch<W>(e, a, s);
+  CU(cudaEventRecord(e->seg_done[slot], s));
+  return rc;
 }
 
 // grouped: the caller's rows are already grouped by table region (dwj_build_grouped); `grouped_offsets` (device,
@@ -381,6 +409,8 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
     a.fill = e->fill;
     a.bucket_mask = e->buckets - 1;
     a.seed = e->cfg.hash_seed;
+    if (partitioned && e->filter.mask) a.n_dev = e->part_scratch + 2 * dwj::PART_MAX + (1u << e->region_bits);   // rows that passed the filter
+    else a.filter = e->filter;          // unpartitioned input: the insert kernel filters
     static const bool no_ahead = getenv("DWJ_BUILD_NO_AHEAD") && atoi(getenv("DWJ_BUILD_NO_AHEAD"));   // A/B switch (development)
     if ((partitioned || (grouped && grouped_offsets && e->region_bits)) && !no_ahead) {   // region look-ahead: offsets stay on the device
       a.offsets = partitioned ? e->part_scratch + 2 * dwj::PART_MAX : (const unsigned long long *)grouped_offsets;
@@ -447,8 +477,10 @@ int multi_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
     CU(cudaMemsetAsync(e->tile_state, 0, (tiles + 1) * sizeof(unsigned long long), s));
     e->launches_probe++;
   }
-  CU(cudaMemsetAsync(a.n_matches, 0, sizeof(unsigned long long), s));
-  e->launches_probe++;
+  if (!e->append_output) {
+    CU(cudaMemsetAsync(a.n_matches, 0, sizeof(unsigned long long), s));
+    e->launches_probe++;
+  }
   if (tiles) {
     if (tiles > 0x7fffffffull) return fail(DWJ_ERR_INVALID, "probe of %llu rows needs more than 2^31 tiles", (unsigned long long)a.n);
     CU(launch(e, dwj::probe_pairs_multi_kernel<W, ORDERED, THREADS, ITEMS, MINB>, dim3((unsigned)tiles), dim3(THREADS), s, a, true));
@@ -476,8 +508,10 @@ int staged_launch_shape(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
     CU(cudaMemsetAsync(e->tile_state, 0, (chunks + 1) * sizeof(unsigned long long), s));
     e->launches_probe++;
   }
-  CU(cudaMemsetAsync(a.n_matches, 0, sizeof(unsigned long long), s));
-  e->launches_probe++;
+  if (!e->append_output) {
+    CU(cudaMemsetAsync(a.n_matches, 0, sizeof(unsigned long long), s));
+    e->launches_probe++;
+  }
   if (chunks) {
     if (chunks > 0x7fffffffull) return fail(DWJ_ERR_INVALID, "probe of %llu rows needs more than 2^31 chunks", (unsigned long long)a.n);
     auto kern = dwj::probe_pairs_staged_kernel<W, ORDERED, WITH_KEY, S.warps, S.items, S.sub, S.minb>;
@@ -519,6 +553,7 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
                uint32_t *flags, uint64_t capacity, uint64_t *d_n, uint64_t *h_n, cudaStream_t s, bool grouped = false) {
   using K = typename dwj::KeyT<W>::type;
   if (!e->built) return fail(DWJ_ERR_STATE, "probe before dwj_build");
+  if (e->append_output && mode == dwj::PROBE_PAIRS && !d_n) return fail(DWJ_ERR_INVALID, "DWJ_OPT_APPEND_OUTPUT needs the device counter d_n_matches");
   dwj::ProbeArgs<W> a{};
   a.keys = (const K *)keys;
   a.vals = (const K *)vals;
@@ -547,6 +582,7 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
       return rc;
     a.keys = pk;
     a.vals = pv;
+    if (e->filter.mask) a.n_dev = e->part_scratch + 2 * dwj::PART_MAX + (1u << e->region_bits);   // rows that passed the filter
     extra_launches = 4;
   }
   CU(cudaEventRecord(e->ev_probek[0], s));
@@ -562,7 +598,9 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
       // grouped or segmented input is already permuted, so the order-preserving look-back would buy nothing.
       static const bool keep_lookback = getenv("DWJ_KEEP_LOOKBACK") && atoi(getenv("DWJ_KEEP_LOOKBACK"));   // A/B switch (development)
       const bool permuted = extra_launches || grouped;
-      const bool ordered = !(e->cfg.flags & DWJ_FLAG_UNORDERED_OUTPUT) && (!permuted || keep_lookback);
+      // Appending (DWJ_OPT_APPEND_OUTPUT) continues at the running count in *d_n_matches: the atomic variants do that by
+      // construction, the look-back variants start from zero.
+      const bool ordered = !(e->cfg.flags & DWJ_FLAG_UNORDERED_OUTPUT) && (!permuted || keep_lookback) && !e->append_output;
       if (unique) {      // rows staged in shared memory; one look-back per chunk (ordered) or one atomic per warp
         if (ordered) rc = ok ? staged_launch<W, true, true>(e, a, s) : staged_launch<W, true, false>(e, a, s);
         else rc = ok ? staged_launch<W, false, true>(e, a, s) : staged_launch<W, false, false>(e, a, s);
@@ -594,6 +632,8 @@ int check_engine(const dwj_engine *e) { return e ? DWJ_OK : fail(DWJ_ERR_INVALID
 extern "C" {
 
 int dwj_abi_version(void) { return DWJ_ABI_VERSION; }
+// dwj_xj.cu reports through the same per-thread buffer (hidden visibility: not part of the ABI)
+void dwj_internal_set_error(const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
 const char *dwj_last_error(void) { return g_err; }
 
 int dwj_create(const dwj_config *cfg, dwj_engine **out) {
@@ -629,13 +669,24 @@ int dwj_create(const dwj_config *cfg, dwj_engine **out) {
   if (me != cudaSuccess) return bail(fail(DWJ_ERR_OOM, "cudaMalloc of a %llu-byte table failed: %s", (unsigned long long)e->table_bytes, cudaGetErrorString(me)));
   if (cudaMalloc((void **)&e->fill, e->buckets * sizeof(unsigned int)) != cudaSuccess)
     return bail(fail(DWJ_ERR_OOM, "cudaMalloc of the %llu-byte ticket array failed", (unsigned long long)(e->buckets * sizeof(unsigned int))));
-  if (cudaMalloc(&e->xpart_cursor, dwj::PART_MAX * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&e->xchg_cursor, 64) != cudaSuccess || cudaMalloc(&e->counter, 64) != cudaSuccess || cudaMalloc(&e->part_scratch, (3 * dwj::PART_MAX + 1) * sizeof(unsigned long long)) != cudaSuccess)
+  if (cudaMalloc(&e->xpart_cursor, dwj::PART_MAX * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&e->pull_cursor, dwj::PART_MAX * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&e->counter, 64) != cudaSuccess || cudaMalloc(&e->part_scratch, (3 * dwj::PART_MAX + 1) * sizeof(unsigned long long)) != cudaSuccess)
     return bail(fail(DWJ_ERR_OOM, "scratch allocation failed"));
   for (int i = 0; i < 2; ++i)
     if (cudaEventCreate(&e->ev_build[i]) != cudaSuccess || cudaEventCreate(&e->ev_probe[i]) != cudaSuccess ||
         cudaEventCreate(&e->ev_part[i]) != cudaSuccess || cudaEventCreate(&e->ev_probek[i]) != cudaSuccess ||
         cudaEventCreate(&e->ev_buildk[i]) != cudaSuccess)
       return bail(fail(DWJ_ERR_CUDA, "cudaEventCreate failed"));
+
+  // staging rings of the segment / start-row uploads: allocated here, never inside a join (an allocation may synchronise
+  // the device, and a multi-GPU join has kernels parked on flags only later host work will raise)
+  if (cudaMalloc((void **)&e->seg_tables, SEG_SLOTS * SEG_MAX * sizeof(dwj::Seg)) != cudaSuccess ||
+      cudaHostAlloc((void **)&e->seg_tables_host, SEG_SLOTS * SEG_MAX * sizeof(dwj::Seg), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+      cudaHostAlloc((void **)&e->pin_ring, (size_t)PIN_SLOTS * dwj::PART_MAX * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
+    return bail(fail(DWJ_ERR_OOM, "staging ring allocation failed"));
+  for (auto &ev : e->seg_done)
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail(fail(DWJ_ERR_CUDA, "cudaEventCreate failed"));
+  for (auto &ev : e->pin_done)
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail(fail(DWJ_ERR_CUDA, "cudaEventCreate failed"));
 
   {   // L2-locality regions (see partition.cuh).  DWJ_REGION_MB / DWJ_PARTITION_MIN_MB are tuning overrides.
     double region_mb = 32.0, min_mb = 192.0;
@@ -678,15 +729,14 @@ int dwj_destroy(dwj_engine *e) {
   cudaFree(e->tile_state);
   cudaFree(e->counter);
   cudaFree(e->part_scratch);
-  cudaFree(e->xchg_cursor);
+  cudaFree(e->pull_cursor);
   cudaFree(e->xpart_cursor);
-  cudaFree(e->push_runs);
-  if (e->push_runs_host) cudaFreeHost(e->push_runs_host);
   cudaFree(e->seg_tables);
   if (e->seg_tables_host) cudaFreeHost(e->seg_tables_host);
-  for (auto &ev : e->seg_done)
+  if (e->pin_ring) cudaFreeHost(e->pin_ring);
+  for (auto &ev : e->pin_done)
     if (ev) cudaEventDestroy(ev);
-  for (auto &ev : e->push_done)
+  for (auto &ev : e->seg_done)
     if (ev) cudaEventDestroy(ev);
   cudaFree(e->region_build);
   cudaFree(e->region_probe);
@@ -724,14 +774,20 @@ int dwj_get_info(const dwj_engine *e, dwj_info *info) {
   info->launches_probe = e->launches_probe;
   info->radix_parts = 1u << e->region_bits;
   info->probe_passes = 1u;
+  info->flags = e->cfg.flags;
+  info->device = e->cfg.device;
+  info->hash_seed = e->cfg.hash_seed;
+  info->max_build_rows = e->cfg.max_build_rows;
   return DWJ_OK;
 }
 
 int dwj_build(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *stream) {
   if (int rc = check_engine(e)) return rc;
   if (n_rows && (!d_keys || !d_vals)) return fail(DWJ_ERR_INVALID, "null build column");
-  if (n_rows > e->cfg.max_build_rows && (double)n_rows > 0.9 * (double)e->slots)
-    return fail(DWJ_ERR_CAPACITY, "%llu build rows exceed the table created for %llu", (unsigned long long)n_rows,
+  // under a pass filter only one key class in 2^pass_bits is inserted (classes are hash bits: an even split)
+  const uint64_t expect = e->filter.mask ? n_rows / ((uint64_t)e->filter.mask + 1) : n_rows;
+  if (expect > e->cfg.max_build_rows && (double)expect > 0.9 * (double)e->slots)
+    return fail(DWJ_ERR_CAPACITY, "%llu build rows exceed the table created for %llu", (unsigned long long)expect,
                 (unsigned long long)e->cfg.max_build_rows);
   DeviceGuard g(e->cfg.device);
   return e->W == 4 ? build_impl<4>(e, d_keys, d_vals, n_rows, (cudaStream_t)stream)
@@ -830,27 +886,6 @@ int dwj_partition_hist(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint3
                    : partition_hist_impl<8>(e, d_keys, n_rows, lg, dwj::PART_BY_HASH, 0, d_counts, (cudaStream_t)stream);
 }
 
-int dwj_partition_scatter_to(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_parts,
-                             void *const *dst_keys, void *const *dst_vals, const uint64_t *dst_row_offsets, void *stream) {
-  if (int rc = check_engine(e)) return rc;
-  if (n_parts == 0 || n_parts > 8 || (n_parts & (n_parts - 1)))
-    return fail(DWJ_ERR_INVALID, "dwj_partition_scatter_to supports 1, 2, 4 or 8 partitions, got %u", n_parts);
-  if (!dst_keys || !dst_row_offsets || (d_vals && !dst_vals) || (n_rows && !d_keys)) return fail(DWJ_ERR_INVALID, "null partition argument");
-  for (uint32_t p = 0; p < n_parts; ++p)
-    if (!dst_keys[p] || (d_vals && !dst_vals[p])) return fail(DWJ_ERR_INVALID, "null destination for partition %u", p);
-  uint32_t lg = 0;
-  while ((1u << lg) < n_parts) ++lg;
-  DeviceGuard g(e->cfg.device);
-  cudaStream_t s = (cudaStream_t)stream;
-  CU(cudaEventRecord(e->ev_part[0], s));
-  const int rc = e->W == 4 ? partition_scatter_to_impl<4>(e, d_keys, d_vals, n_rows, lg, dst_keys, dst_vals, dst_row_offsets, s)
-                           : partition_scatter_to_impl<8>(e, d_keys, d_vals, n_rows, lg, dst_keys, dst_vals, dst_row_offsets, s);
-  if (rc) return rc;
-  CU(cudaEventRecord(e->ev_part[1], s));
-  e->have_part = true;
-  return DWJ_OK;
-}
-
 // ---- exchange partition folded with the receiver's region grouping ------------------------------------------------------
 namespace {
 int xpart_bits(const dwj_engine *e, uint32_t n_ranks, uint32_t *rank_bits, uint32_t *fold_bits) {
@@ -892,8 +927,13 @@ int dwj_xpart_scatter(dwj_engine *e, const void *d_keys, const void *d_vals, uin
   DeviceGuard g(e->cfg.device);
   const uint32_t mode = fb ? dwj::PART_BY_BOTH : dwj::PART_BY_HASH;
   cudaStream_t s = (cudaStream_t)stream;
-  return e->W == 4 ? partition_scatter_planned_impl<4>(e, d_keys, d_vals, n_rows, rb + fb, mode, rb, start_rows, d_out_keys, d_out_vals, s)
-                   : partition_scatter_planned_impl<8>(e, d_keys, d_vals, n_rows, rb + fb, mode, rb, start_rows, d_out_keys, d_out_vals, s);
+  CU(cudaEventRecord(e->ev_part[0], s));
+  const int rc = e->W == 4 ? partition_scatter_planned_impl<4>(e, d_keys, d_vals, n_rows, rb + fb, mode, rb, start_rows, d_out_keys, d_out_vals, s)
+                           : partition_scatter_planned_impl<8>(e, d_keys, d_vals, n_rows, rb + fb, mode, rb, start_rows, d_out_keys, d_out_vals, s);
+  if (rc) return rc;
+  CU(cudaEventRecord(e->ev_part[1], s));
+  e->have_part = true;
+  return DWJ_OK;
 }
 
 int dwj_build_grouped(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, const uint64_t *d_region_offsets, void *stream) {
@@ -920,15 +960,16 @@ int dwj_probe_pairs_grouped(dwj_engine *e, const void *d_keys, const void *d_val
 namespace {
 struct PendingSegs {       // scope guard: the segment list is only valid during one call
   dwj_engine *e;
-  PendingSegs(dwj_engine *e_, uint32_t n, const uint64_t *first, const uint64_t *rows, uint32_t per_region) : e(e_) {
+  PendingSegs(dwj_engine *e_, uint32_t n, const void *const *keys, const void *const *vals, const uint64_t *rows, uint32_t per_region) : e(e_) {
     e->pending_segs = n;
-    e->pending_seg_first = first;
+    e->pending_seg_keys = keys;
+    e->pending_seg_vals = vals;
     e->pending_seg_rows = rows;
     e->pending_segs_per_region = per_region;
   }
   ~PendingSegs() { e->pending_segs = 0; }
 };
-int check_segments(uint32_t n, const uint64_t *first, const uint64_t *rows, uint64_t *total) {
+int check_segments(uint32_t n, const void *first, const uint64_t *rows, uint64_t *total) {
   if (n == 0 || n > (uint32_t)dwj::PART_MAX) return fail(DWJ_ERR_INVALID, "between 1 and %d segments, got %u", dwj::PART_MAX, n);
   if (!first || !rows) return fail(DWJ_ERR_INVALID, "null segment list");
   *total = 0;
@@ -937,87 +978,95 @@ int check_segments(uint32_t n, const uint64_t *first, const uint64_t *rows, uint
 }
 }  // namespace
 
-int dwj_build_segments(dwj_engine *e, const void *d_keys, const void *d_vals, uint32_t n_segments, const uint64_t *seg_first_row,
-                       const uint64_t *seg_rows, uint32_t segments_per_region, void *stream) {
+int dwj_build_segments(dwj_engine *e, uint32_t n_segments, const void *const *seg_keys, const void *const *seg_vals, const uint64_t *seg_rows,
+                       uint32_t segments_per_region, void *stream) {
   if (int rc = check_engine(e)) return rc;
   uint64_t total = 0;
-  if (int rc = check_segments(n_segments, seg_first_row, seg_rows, &total)) return rc;
-  if (total && (!d_keys || !d_vals)) return fail(DWJ_ERR_INVALID, "null build column");
+  if (int rc = check_segments(n_segments, seg_keys, seg_rows, &total)) return rc;
+  if (!seg_vals) return fail(DWJ_ERR_INVALID, "null build payload segments");
   if (total > e->cfg.max_build_rows && (double)total > 0.9 * (double)e->slots)
     return fail(DWJ_ERR_CAPACITY, "%llu build rows exceed the table created for %llu", (unsigned long long)total,
                 (unsigned long long)e->cfg.max_build_rows);
   DeviceGuard g(e->cfg.device);
-  PendingSegs ps(e, total ? n_segments : 0, seg_first_row, seg_rows, segments_per_region);
-  return e->W == 4 ? build_impl<4>(e, d_keys, d_vals, total, (cudaStream_t)stream, true, nullptr)
-                   : build_impl<8>(e, d_keys, d_vals, total, (cudaStream_t)stream, true, nullptr);
+  PendingSegs ps(e, total ? n_segments : 0, seg_keys, seg_vals, seg_rows, segments_per_region);
+  return e->W == 4 ? build_impl<4>(e, nullptr, nullptr, total, (cudaStream_t)stream, true, nullptr)
+                   : build_impl<8>(e, nullptr, nullptr, total, (cudaStream_t)stream, true, nullptr);
 }
 
-int dwj_probe_pairs_segments(dwj_engine *e, const void *d_keys, const void *d_vals, uint32_t n_segments, const uint64_t *seg_first_row,
+int dwj_probe_pairs_segments(dwj_engine *e, uint32_t n_segments, const void *const *seg_keys, const void *const *seg_vals,
                              const uint64_t *seg_rows, void *d_out_key, void *d_out_build_val, void *d_out_probe_val, uint64_t capacity,
                              uint64_t *d_n_matches, uint64_t *n_matches, void *stream) {
   if (int rc = check_engine(e)) return rc;
   uint64_t total = 0;
-  if (int rc = check_segments(n_segments, seg_first_row, seg_rows, &total)) return rc;
+  if (int rc = check_segments(n_segments, seg_keys, seg_rows, &total)) return rc;
+  if (!seg_vals) return fail(DWJ_ERR_INVALID, "null probe payload segments");
   if (!(e->cfg.flags & DWJ_FLAG_UNIQUE_BUILD_KEYS))
     return fail(DWJ_ERR_INVALID, "segmented probe is implemented for DWJ_FLAG_UNIQUE_BUILD_KEYS engines");
-  if (total && (!d_keys || !d_vals)) return fail(DWJ_ERR_INVALID, "null probe column");
   if (capacity && (!d_out_build_val || !d_out_probe_val)) return fail(DWJ_ERR_INVALID, "null output column");
   DeviceGuard g(e->cfg.device);
-  PendingSegs ps(e, total ? n_segments : 0, seg_first_row, seg_rows, 0);
-  return e->W == 4 ? probe_impl<4>(e, dwj::PROBE_PAIRS, d_keys, d_vals, total, d_out_key, d_out_build_val, d_out_probe_val, nullptr, capacity, d_n_matches, n_matches, (cudaStream_t)stream, true)
-                   : probe_impl<8>(e, dwj::PROBE_PAIRS, d_keys, d_vals, total, d_out_key, d_out_build_val, d_out_probe_val, nullptr, capacity, d_n_matches, n_matches, (cudaStream_t)stream, true);
+  PendingSegs ps(e, total ? n_segments : 0, seg_keys, seg_vals, seg_rows, 0);
+  return e->W == 4 ? probe_impl<4>(e, dwj::PROBE_PAIRS, nullptr, nullptr, total, d_out_key, d_out_build_val, d_out_probe_val, nullptr, capacity, d_n_matches, n_matches, (cudaStream_t)stream, true)
+                   : probe_impl<8>(e, dwj::PROBE_PAIRS, nullptr, nullptr, total, d_out_key, d_out_build_val, d_out_probe_val, nullptr, capacity, d_n_matches, n_matches, (cudaStream_t)stream, true);
 }
 
-int dwj_copy_many(dwj_engine *e, uint32_t n_copies, void *const *dsts, const void *const *srcs, const uint64_t *bytes, void *const *streams) {
+int dwj_region_scatter_segments(dwj_engine *e, uint32_t n_segments, const void *const *seg_keys, const void *const *seg_vals,
+                                const uint64_t *seg_rows, const uint64_t *start_rows, void *d_out_keys, void *d_out_vals, void *stream) {
   if (int rc = check_engine(e)) return rc;
-  if (n_copies && (!dsts || !srcs || !bytes || !streams)) return fail(DWJ_ERR_INVALID, "null copy list");
+  uint64_t total = 0;
+  if (int rc = check_segments(n_segments, seg_keys, seg_rows, &total)) return rc;
+  if (!start_rows || (total && !d_out_keys)) return fail(DWJ_ERR_INVALID, "null scatter argument");
+  if ((seg_vals == nullptr) != (d_out_vals == nullptr)) return fail(DWJ_ERR_INVALID, "seg_vals and d_out_vals must both be given or both be null");
+  if (!total) return DWJ_OK;
   DeviceGuard g(e->cfg.device);
-  for (uint32_t i = 0; i < n_copies; ++i)
-    if (bytes[i]) CU(cudaMemcpyAsync(dsts[i], srcs[i], bytes[i], cudaMemcpyDeviceToDevice, (cudaStream_t)streams[i]));
-  return DWJ_OK;
+  PendingSegs ps(e, n_segments, seg_keys, seg_vals, seg_rows, 0);
+  return e->W == 4 ? region_scatter_segments_impl<4>(e, start_rows, d_out_keys, d_out_vals, seg_vals != nullptr, (cudaStream_t)stream)
+                   : region_scatter_segments_impl<8>(e, start_rows, d_out_keys, d_out_vals, seg_vals != nullptr, (cudaStream_t)stream);
 }
 
-int dwj_push_runs(dwj_engine *e, uint32_t n_runs, void *const *dsts, const void *const *srcs, const uint64_t *rows, uint32_t n_ctas,
-                  void *stream) {
+int dwj_xpart_hist2(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t n_ranks, uint64_t *d_counts, void *stream) {
   if (int rc = check_engine(e)) return rc;
-  constexpr uint32_t MAX_RUNS = 4 * dwj::PART_MAX;
-  if (n_runs > MAX_RUNS) return fail(DWJ_ERR_INVALID, "at most %u runs per call, got %u", MAX_RUNS, n_runs);
-  if (n_runs && (!dsts || !srcs || !rows)) return fail(DWJ_ERR_INVALID, "null run list");
+  if (n_ranks == 0 || (n_ranks & (n_ranks - 1)) || n_ranks > 8) return fail(DWJ_ERR_INVALID, "n_ranks must be 1, 2, 4 or 8, got %u", n_ranks);
+  if (!d_counts || (n_rows && !d_keys)) return fail(DWJ_ERR_INVALID, "null partition argument");
+  uint32_t rb = 0;
+  while ((1u << rb) < n_ranks) ++rb;
   DeviceGuard g(e->cfg.device);
-  cudaStream_t s = (cudaStream_t)stream;
-  constexpr uint32_t PUSH_SLOTS = 8;
-  if (!e->push_runs) {
-    CU(cudaMalloc((void **)&e->push_runs, PUSH_SLOTS * MAX_RUNS * sizeof(dwj::PushRun)));
-    CU(cudaHostAlloc((void **)&e->push_runs_host, PUSH_SLOTS * MAX_RUNS * sizeof(dwj::PushRun), cudaHostAllocDefault));
-    for (auto &ev : e->push_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  const uint32_t bits = rb + e->region_bits;
+  const uint32_t mode = e->region_bits ? dwj::PART_BY_BOTH : dwj::PART_BY_HASH;
+  return e->W == 4 ? partition_hist_impl<4>(e, d_keys, n_rows, bits, mode, rb, d_counts, (cudaStream_t)stream)
+                   : partition_hist_impl<8>(e, d_keys, n_rows, bits, mode, rb, d_counts, (cudaStream_t)stream);
+}
+
+int dwj_set_option(dwj_engine *e, int option, uint64_t value) {
+  if (int rc = check_engine(e)) return rc;
+  switch (option) {
+  case DWJ_OPT_APPEND_OUTPUT: e->append_output = value != 0; return DWJ_OK;
+  case DWJ_OPT_PASS_FILTER: {
+    // value = rank_bits | pass_bits << 8 | pass_id << 16: the class of a key is the pass_bits bits of its partition
+    // hash right below the rank_bits destination-rank bits; pass_bits == 0 switches the filter off.
+    const uint32_t rank_bits = value & 0xff, pass_bits = (value >> 8) & 0xff, pass_id = (uint32_t)(value >> 16);
+    if (pass_bits == 0) { e->filter = dwj::PassFilter{}; return DWJ_OK; }
+    if (rank_bits + pass_bits > 16 || pass_id >= (1u << pass_bits)) return fail(DWJ_ERR_INVALID, "bad pass filter %llx", (unsigned long long)value);
+    e->filter.shift = (e->W == 4 ? 32u : 64u) - rank_bits - pass_bits;
+    e->filter.mask = (1u << pass_bits) - 1u;
+    e->filter.want = pass_id;
+    return DWJ_OK;
   }
-  const uint32_t slot = e->push_calls++ % PUSH_SLOTS;
-  if (e->push_calls > PUSH_SLOTS) CU(cudaEventSynchronize(e->push_done[slot]));   // the slot's previous kernel (8 calls ago) is done
-  dwj::PushRun *h_runs = e->push_runs_host + slot * MAX_RUNS, *d_runs = e->push_runs + slot * MAX_RUNS;
-  constexpr int ELEMS = 16;
-  const unsigned long long block_rows = 256ull * ELEMS;
-  unsigned long long blocks = 0;
-  uint32_t n = 0;
-  for (uint32_t i = 0; i < n_runs; ++i) {
-    if (!rows[i]) continue;
-    if (!dsts[i] || !srcs[i]) return fail(DWJ_ERR_INVALID, "null pointer in run %u", i);
-    h_runs[n++] = dwj::PushRun{dsts[i], srcs[i], rows[i], blocks};
-    blocks += (rows[i] + block_rows - 1) / block_rows;
+  default: return fail(DWJ_ERR_INVALID, "unknown option %d", option);
   }
-  if (!n) return DWJ_OK;
-  CU(cudaMemcpyAsync(d_runs, h_runs, n * sizeof(dwj::PushRun), cudaMemcpyHostToDevice, s));
-  const unsigned grid = (unsigned)std::min<unsigned long long>(blocks, n_ctas ? n_ctas : 64u);
-  if (e->W == 4) dwj::push_runs_kernel<4, ELEMS><<<grid, 256, 0, s>>>(d_runs, n, blocks);
-  else dwj::push_runs_kernel<8, ELEMS><<<grid, 256, 0, s>>>(d_runs, n, blocks);
-  CU(cudaEventRecord(e->push_done[slot], s));
-  CU(cudaGetLastError());
-  return DWJ_OK;
 }
 
 uint32_t dwj_partition_of(uint64_t key, int32_t key_bytes, uint32_t n_parts, uint64_t hash_seed) {
   uint32_t lg = 0;
   while ((1u << lg) < n_parts) ++lg;
   return key_bytes == 4 ? dwj::partition_of((uint32_t)key, lg, hash_seed) : dwj::partition_of((uint64_t)key, lg, hash_seed);
+}
+
+uint32_t dwj_region_of(uint64_t key, int32_t key_bytes, uint64_t buckets, uint32_t region_bits, uint64_t hash_seed) {
+  uint32_t lgb = 0;
+  while ((1ull << lgb) < buckets) ++lgb;
+  if (!region_bits || region_bits > lgb) return 0;
+  const uint64_t h = key_bytes == 4 ? dwj::slot_hash((uint32_t)key, hash_seed) : dwj::slot_hash((uint64_t)key, hash_seed);
+  return (uint32_t)((h & (buckets - 1)) >> (lgb - region_bits));
 }
 
 // ---- host-buffer join ---------------------------------------------------------------------------------

@@ -45,14 +45,14 @@ template <int W> struct PartitionArgs {
   uint64_t bucket_mask;
   K *out_keys;
   K *out_vals;         // may be null
-  // Per-partition destinations (<= 8 partitions, dwj_partition_scatter_to): partition p is written to
-  // dst_keys[p] / dst_vals[p] -- which may be PEER GPU memory mapped over NVLink -- instead of out_keys/out_vals.
-  uint32_t use_dst;
-  K *dst_keys[8];
-  K *dst_vals[8];
   unsigned long long *hist;     // [PART_MAX] zeroed before the histogram kernel
   unsigned long long *cursor;   // [PART_MAX] running write positions
   unsigned long long *offsets;  // [parts + 1] result
+  // Segmented input (table.cuh; the many-way scatter only): n_segs > 0 => the rows come from segs[] -- possibly peer
+  // memory, which makes the scatter the receiving end of the multi-GPU exchange -- and `n` is the number of TILES.
+  const Seg *segs;
+  uint32_t n_segs;
+  PassFilter filter;            // rows of other key classes are dropped (histograms do not count them)
 };
 
 // Partition id of a key.  `mode` is uniform across the grid, so the branch costs one predicate.
@@ -181,7 +181,8 @@ template <int W, int THREADS, int ITEMS> struct ScatterManySmem {
 };
 
 template <int W, int BITS, int THREADS, int ITEMS, bool FULL>
-DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t rows, unsigned char *smem, unsigned int *s_scan) {
+DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, const typename KeyT<W>::type *kp, const typename KeyT<W>::type *vp, uint32_t rows,
+                             unsigned char *smem, unsigned int *s_scan) {
   using K = typename KeyT<W>::type;
   constexpr uint32_t TILE = THREADS * ITEMS;
   constexpr int WARPS = THREADS / 32;
@@ -201,17 +202,21 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t 
 
   K k[ITEMS], v[ITEMS];
   uint32_t pr[ITEMS];                               // partition << 16 | rank inside (warp, partition); PART_DEAD = dead row
-  const K *kp = a.keys + base + threadIdx.x, *vp = a.vals + base + threadIdx.x;
+  uint32_t livemask = 0;                            // FULL = false: rows inside the relation AND of the current key class
+  kp += threadIdx.x;
+  vp += threadIdx.x;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
-    const bool live = FULL || j * THREADS + threadIdx.x < rows;
-    k[j] = live ? load_stream(kp + j * THREADS) : (K)0;
+    const bool in = FULL || j * THREADS + threadIdx.x < rows;
+    k[j] = in ? load_stream(kp + j * THREADS) : (K)0;
+    const bool live = FULL || (in && pass_ok(k[j], a.seed, a.filter));
+    livemask |= (live ? 1u : 0u) << j;
     v[j] = live && with_vals ? load_stream(vp + j * THREADS) : (K)0;
   }
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
-    const bool live = FULL || j * THREADS + threadIdx.x < rows;
+    const bool live = FULL || (livemask >> j & 1u);
     const uint32_t p = part_id<W>(a, k[j]);
     const unsigned alive = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, live);
     const unsigned peers = match_partition<BITS>(p, alive);
@@ -250,6 +255,7 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t 
     unsigned before = 0;
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) before += w < (int)warp ? s_scan[w] : 0u;
+    if (!FULL && threadIdx.x == THREADS - 1) s_scan[WARPS] = before + incl;      // rows of the tile that are staged at all
     unsigned run = before + incl - sum;
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
@@ -279,10 +285,11 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t 
     }
   }
   __syncthreads();
+  const uint32_t staged_rows = FULL ? (uint32_t)TILE : s_scan[WARPS];
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const uint32_t s = j * THREADS + threadIdx.x;
-    if (FULL || s < rows) {
+    if (FULL || s < staged_rows) {
       const long long dst = (long long)s + s_delta[s_part[s]];
       store_stream(a.out_keys + dst, s_keys[s]);
       if (with_vals) store_stream(a.out_vals + dst, s_vals[s]);
@@ -293,16 +300,59 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t 
 template <int W, int BITS, int THREADS, int ITEMS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) partition_scatter_many_kernel(PartitionArgs<W> a) {
   constexpr uint32_t TILE = THREADS * ITEMS;
+  using K = typename KeyT<W>::type;
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  __shared__ unsigned int s_scan[THREADS / 32];
-  const uint64_t num_tiles = (a.n + TILE - 1) / TILE;
+  __shared__ unsigned int s_scan[THREADS / 32 + 1];
+  const uint64_t num_tiles = a.n_segs ? a.n : (a.n + TILE - 1) / TILE;
   for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const uint64_t base = tile * TILE;
-    const uint32_t rows = (uint32_t)min((uint64_t)TILE, a.n - base);
-    if (rows == TILE) scatter_many_tile<W, BITS, THREADS, ITEMS, true>(a, base, rows, s_dyn, s_scan);
-    else scatter_many_tile<W, BITS, THREADS, ITEMS, false>(a, base, rows, s_dyn, s_scan);
+    const K *kp = a.keys, *vp = a.vals;
+    uint64_t base = tile * TILE, limit = a.n;
+    if (a.n_segs) {                                 // CTA-uniform: the tile's rows live in one segment (possibly peer memory)
+      const Seg sg = a.segs[find_segment(a.segs, a.n_segs, tile)];
+      kp = (const K *)sg.keys;
+      vp = (const K *)sg.vals;
+      base = (tile - sg.first_unit) * TILE;
+      limit = sg.rows;
+    }
+    const uint32_t rows = (uint32_t)min((uint64_t)TILE, limit - base);
+    if (rows == TILE && !a.filter.mask) scatter_many_tile<W, BITS, THREADS, ITEMS, true>(a, kp + base, vp + base, rows, s_dyn, s_scan);
+    else scatter_many_tile<W, BITS, THREADS, ITEMS, false>(a, kp + base, vp + base, rows, s_dyn, s_scan);
     __syncthreads();                                // shared memory is reused by the next tile
   }
+}
+
+// ---- histogram with shared-memory reductions (any partition count up to 4096, pass filter) -----------------------------
+// One 32-bit counter per partition in shared memory, bumped with RED.shared (no result: the cost that rules ATOMS out of
+// the scatter does not apply).  Used where the private-counter kernels do not reach: the (destination rank x table
+// region) histogram of the multi-GPU exchange when ranks x regions exceeds 512 -- the senders count for the receivers,
+// so that a receiver can lay out its region-grouped buffer before it pulls a single row -- and every histogram under a
+// pass filter.
+template <int W, uint32_t MODE, int HROWS>
+__global__ void __launch_bounds__(PART_THREADS) partition_hist_red_kernel(PartitionArgs<W> a) {
+  using K = typename KeyT<W>::type;
+  extern __shared__ unsigned int s_bins[];
+  const uint32_t parts = 1u << a.log2_parts;
+  for (uint32_t i = threadIdx.x; i < parts; i += PART_THREADS) s_bins[i] = 0;
+  __syncthreads();
+  constexpr uint64_t TILE = (uint64_t)PART_THREADS * HROWS;
+  const uint64_t tiles = (a.n + TILE - 1) / TILE;
+  for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const uint64_t base = tile * TILE + threadIdx.x;
+    K k[HROWS];
+#pragma unroll
+    for (int j = 0; j < HROWS; ++j) {
+      const uint64_t i = base + (uint64_t)j * PART_THREADS;
+      k[j] = i < a.n ? load_stream(a.keys + i) : (K)0;
+    }
+#pragma unroll
+    for (int j = 0; j < HROWS; ++j) {
+      const uint64_t i = base + (uint64_t)j * PART_THREADS;
+      if (i < a.n && pass_ok(k[j], a.seed, a.filter)) atomicAdd(&s_bins[part_id_of<W, MODE>(a, k[j])], 1u);
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < parts; i += PART_THREADS)
+    if (s_bins[i]) atomicAdd(a.hist + i, (unsigned long long)s_bins[i]);
 }
 
 // ---- histogram for at most 8 partitions ------------------------------------------------------------------------
@@ -351,165 +401,6 @@ __global__ void __launch_bounds__(PART_THREADS) partition_hist8_kernel(Partition
   flush();
   __syncthreads();
   if (threadIdx.x < 8 && s_hist[threadIdx.x]) atomicAdd(a.hist + threadIdx.x, (unsigned long long)s_hist[threadIdx.x]);
-}
-
-// Scatter for <= 8 partitions with one DESTINATION POINTER per partition, for destinations on the far side of NVLink
-// (dwj_partition_scatter_to): three ballots per 32 rows and warp-distributed counters (lane q keeps the warp's running
-// count of partition q) rank the rows; the tile is first grouped by partition in shared memory and then
-// streamed out so that every warp-level store is one contiguous 128-byte (4-byte keys) / 256-byte (8-byte keys)
-// piece of ONE destination.  Storing straight from registers hands each peer ~16-byte pieces per instruction, which
-// NVLink moves at a fraction of its bandwidth (8 GPUs: 26.8 ms per step against a 2.6 ms transfer floor).
-template <int W, int ITEMS> struct Scatter8StagedSmem {
-  using K = typename KeyT<W>::type;
-  K keys[PART_THREADS * ITEMS];
-  K vals[PART_THREADS * ITEMS];
-  unsigned char part[PART_THREADS * ITEMS];
-  unsigned int wcnt[PART_THREADS / 32][8];    // per-warp rows per partition, then per-warp prefix
-  unsigned int start[8];                      // staging offset of each partition inside the tile
-  long long delta[8];                         // global row of the partition's run minus its staging offset
-  K *dstk[8];
-  K *dstv[8];
-};
-
-template <int W, int ITEMS, bool FULL, bool WITH_VALS>
-DWJ_D void scatter8_staged_tile(const PartitionArgs<W> &a, uint64_t base, uint32_t rows, Scatter8StagedSmem<W, ITEMS> &sm) {
-  using K = typename KeyT<W>::type;
-  constexpr int WARPS = PART_THREADS / 32;
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt = (1u << lane) - 1u;
-  const unsigned q0 = (lane & 1) ? 0xffffffffu : 0u, q1 = (lane & 2) ? 0xffffffffu : 0u, q2 = (lane & 4) ? 0xffffffffu : 0u;
-  K k[ITEMS], v[ITEMS];
-  uint32_t pr[ITEMS];                              // rank inside the warp << 4 | partition (8 = dead row)
-  const K *kp = a.keys + base + threadIdx.x, *vp = a.vals + base + threadIdx.x;
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const bool live = FULL || j * PART_THREADS + threadIdx.x < rows;
-    k[j] = live ? load_stream(kp + j * PART_THREADS) : (K)0;
-    if constexpr (WITH_VALS) v[j] = live ? load_stream(vp + j * PART_THREADS) : (K)0;
-  }
-  uint32_t run = 0;
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const bool live = FULL || j * PART_THREADS + threadIdx.x < rows;
-    const uint32_t p = part_id<W>(a, k[j]);
-    const unsigned alive = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, live);
-    const unsigned b0 = __ballot_sync(0xffffffffu, p & 1u), b1 = __ballot_sync(0xffffffffu, p & 2u), b2 = __ballot_sync(0xffffffffu, p & 4u);
-    const unsigned m0 = (p & 1u) ? b0 : ~b0, m1 = (p & 2u) ? b1 : ~b1, m2 = (p & 4u) ? b2 : ~b2;
-    const unsigned peers = m0 & m1 & m2 & alive;
-    const uint32_t before = __shfl_sync(0xffffffffu, run, p);
-    pr[j] = live ? ((before + __popc(peers & lt)) << 4 | p) : 8u;
-    run += __popc(~(b0 ^ q0) & ~(b1 ^ q1) & ~(b2 ^ q2) & alive);
-  }
-  if (lane < 8) sm.wcnt[warp][lane] = run;
-  __syncthreads();
-  if (threadIdx.x < 8) {                           // partition q: prefix over warps, staging offset, global reservation
-    const unsigned q = threadIdx.x;
-    unsigned total = 0;
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) { const unsigned c = sm.wcnt[w][q]; sm.wcnt[w][q] = total; total += c; }
-    unsigned start = 0;
-    // exclusive scan over the 8 partitions through shuffles inside this (partial) warp
-    unsigned incl = total;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      const unsigned n = __shfl_up_sync(0xffu, incl, o);
-      if (q >= (unsigned)o) incl += n;
-    }
-    start = incl - total;
-    sm.start[q] = start;
-    const unsigned long long g = total ? atomicAdd(a.cursor + q, (unsigned long long)total) : 0ull;
-    sm.delta[q] = (long long)g - (long long)start;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    if (FULL || pr[j] != 8u) {
-      const uint32_t p = pr[j] & 15u;
-      const uint32_t s = sm.start[p] + sm.wcnt[warp][p] + (pr[j] >> 4);
-      sm.keys[s] = k[j];
-      if constexpr (WITH_VALS) sm.vals[s] = v[j];
-      sm.part[s] = (unsigned char)p;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const uint32_t s = j * PART_THREADS + threadIdx.x;
-    if (FULL || s < rows) {
-      const uint32_t p = sm.part[s];
-      const long long dst = (long long)s + sm.delta[p];
-      store_stream(sm.dstk[p] + dst, sm.keys[s]);
-      if constexpr (WITH_VALS) store_stream(sm.dstv[p] + dst, sm.vals[s]);
-    }
-  }
-  __syncthreads();
-}
-
-template <int W, int ITEMS>
-__global__ void __launch_bounds__(PART_THREADS, 3) partition_scatter8_staged_kernel(PartitionArgs<W> a) {
-  constexpr uint32_t TILE = PART_THREADS * ITEMS;
-  __shared__ Scatter8StagedSmem<W, ITEMS> sm;
-  if (threadIdx.x < 8) {
-    sm.dstk[threadIdx.x] = a.use_dst ? a.dst_keys[threadIdx.x] : a.out_keys;
-    sm.dstv[threadIdx.x] = a.use_dst ? a.dst_vals[threadIdx.x] : a.out_vals;
-  }
-  __syncthreads();
-  const bool with_vals = a.vals != nullptr;
-  const uint64_t num_tiles = (a.n + TILE - 1) / TILE;
-  for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const uint64_t base = tile * TILE;
-    const uint32_t rows = (uint32_t)min((uint64_t)TILE, a.n - base);
-    if (rows == TILE) {
-      if (with_vals) scatter8_staged_tile<W, ITEMS, true, true>(a, base, rows, sm);
-      else scatter8_staged_tile<W, ITEMS, true, false>(a, base, rows, sm);
-    } else {
-      if (with_vals) scatter8_staged_tile<W, ITEMS, false, true>(a, base, rows, sm);
-      else scatter8_staged_tile<W, ITEMS, false, false>(a, base, rows, sm);
-    }
-  }
-}
-
-// ---- exchange: push runs into peer memory with a FEW CTAs -------------------------------------------------------------
-// The folded exchange (dwj_xpart_*) leaves ranks x regions contiguous runs per relation, each bound for its own place
-// in some peer's receive area.  On this machine the copy engines serialise such a list at ~27 us per copy whatever
-// its size (112 copies of 8 MB: 3 ms, 310 GB/s), so the runs are pushed by a small kernel instead: a few dozen CTAs
-// stream all runs through registers with coalesced 128-byte (4-byte rows) / 256-byte warp stores -- the piece size
-// NVLink wants -- while the rest of the SMs go on partitioning and probing.  Work unit: one block of 256 x ELEMS
-// rows of one run; blocks are dealt round-robin to the CTAs.
-struct PushRun {
-  void *dst;
-  const void *src;
-  unsigned long long rows;
-  unsigned long long first_block;      // blocks of all earlier runs
-};
-
-template <int W, int ELEMS>
-__global__ void __launch_bounds__(256) push_runs_kernel(const PushRun *runs, uint32_t n_runs, unsigned long long total_blocks) {
-  using K = typename KeyT<W>::type;
-  constexpr unsigned long long BLOCK_ROWS = 256ull * ELEMS;
-  for (unsigned long long blk = blockIdx.x; blk < total_blocks; blk += gridDim.x) {
-    uint32_t lo = 0, hi = n_runs;                   // runs[lo].first_block <= blk < runs[hi].first_block
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (__ldg(&runs[mid].first_block) <= blk) lo = mid; else hi = mid;
-    }
-    const PushRun r = runs[lo];
-    const unsigned long long row0 = (blk - r.first_block) * BLOCK_ROWS + threadIdx.x;
-    const K *src = (const K *)r.src + row0;
-    K *dst = (K *)r.dst + row0;
-    K v[ELEMS];
-    if (row0 - threadIdx.x + BLOCK_ROWS <= r.rows) {
-#pragma unroll
-      for (int j = 0; j < ELEMS; ++j) v[j] = load_stream(src + j * 256);
-#pragma unroll
-      for (int j = 0; j < ELEMS; ++j) dst[j * 256] = v[j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < ELEMS; ++j) if (row0 + j * 256 < r.rows) v[j] = load_stream(src + j * 256);
-#pragma unroll
-      for (int j = 0; j < ELEMS; ++j) if (row0 + j * 256 < r.rows) dst[j * 256] = v[j];
-    }
-  }
 }
 
 }  // namespace dwj

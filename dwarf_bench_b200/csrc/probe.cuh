@@ -35,7 +35,12 @@ template <int W> struct ProbeArgs {
   uint64_t num_tiles;
   const Seg *segs;                 // segmented input (table.cuh), staged PAIRS kernel only; n_segs == 0: rows [0, n)
   uint32_t n_segs;
+  const unsigned long long *n_dev; // non-null: the row count lives on the device (input produced by a filtered
+                                   // partition pass); `n` is then an upper bound that sizes the grid
 };
+template <int W> DWJ_D uint64_t probe_rows(const ProbeArgs<W> &a) {
+  return a.n_dev ? min((uint64_t)__ldg(a.n_dev), a.n) : a.n;
+}
 
 // ---- decoupled look-back ----------------------------------------------------------------------
 // One 64-bit descriptor per tile: status in the top two bits, value in the low 62.
@@ -217,6 +222,7 @@ __global__ void __launch_bounds__(256) probe_simple_kernel(ProbeArgs<W> a) {
   constexpr uint64_t WTILE = 32ull * ITEMS;
   const unsigned lane = threadIdx.x & 31;
   const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  a.n = probe_rows(a);
   const uint64_t tiles = (a.n + WTILE - 1) / WTILE;
   unsigned long long local_count = 0;
   for (uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < tiles; tile += warps_total) {
@@ -248,6 +254,7 @@ __global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeA
   __syncthreads();
   const uint64_t tile = s_tile;
   const uint64_t base = tile * TILE;
+  a.n = probe_rows(a);
   const bool full = base + TILE <= a.n;
 
   K key[ITEMS], pval[ITEMS], pl[ITEMS][4];
@@ -396,11 +403,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) probe_pairs_staged_kernel(Pr
   if (t == 0) s_chunk = ORDERED ? atomicAdd(a.tile_state, 1ull) : (unsigned long long)blockIdx.x;
   __syncthreads();
   const uint64_t chunk = s_chunk;
-  uint64_t chunk_base = chunk * CHUNK, limit = a.n;
-  if (a.n_segs) {                                   // CTA-uniform: the chunk's rows live in one segment of the allocation
+  uint64_t chunk_base = chunk * CHUNK, limit = probe_rows(a);
+  if (a.n_segs) {                                   // CTA-uniform: the chunk's rows live in one segment (possibly peer memory)
     const Seg sg = a.segs[find_segment(a.segs, a.n_segs, chunk)];
-    chunk_base = sg.phys_row + (chunk - sg.first_unit) * CHUNK;
-    limit = sg.phys_row + sg.rows;
+    a.keys = (const K *)sg.keys;
+    a.vals = (const K *)sg.vals;
+    chunk_base = (chunk - sg.first_unit) * CHUNK;
+    limit = sg.rows;
   }
   const uint64_t warp_base = chunk_base + (uint64_t)warp * WROWS;
   K *wb = s_build + warp * WROWS, *wp = s_probe + warp * WROWS, *wk = s_key + warp * WROWS;

@@ -64,6 +64,19 @@ DWJ_HD uint32_t partition_of(uint64_t key, uint32_t log2_parts, uint64_t seed) {
   return log2_parts ? (uint32_t)(fmix64(key ^ seed) >> (64 - log2_parts)) : 0u;
 }
 
+// Pass filter (DWJ_OPT_PASS_FILTER): a join whose working set exceeds one GPU is run as several passes over key
+// CLASSES -- bits of the partition hash below the destination-rank bits.  A row whose class is not the current one is
+// treated as absent by the partition, histogram and build kernels.  mask == 0: no filter.
+struct PassFilter {
+  uint32_t shift, mask, want;
+};
+DWJ_HD bool pass_ok(uint32_t key, uint64_t seed, PassFilter f) {
+  return !f.mask || ((part_hash32(key, seed) >> f.shift) & f.mask) == f.want;
+}
+DWJ_HD bool pass_ok(uint64_t key, uint64_t seed, PassFilter f) {
+  return !f.mask || ((uint32_t)(fmix64(key ^ seed) >> f.shift) & f.mask) == f.want;
+}
+
 #if defined(__CUDACC__)
 
 // ---- bucket access -----------------------------------------------------------------------
@@ -144,15 +157,16 @@ template <int W> DWJ_D Bucket<W> load_bucket_stream(const void *table, uint64_t 
   return load_bucket_stream(table, b, (Bucket<W> *)nullptr);
 }
 // ---- segmented input ---------------------------------------------------------------------------------------------------
-// A relation may be handed to the build / probe kernels as a LIST OF SEGMENTS of one allocation instead of one
-// contiguous range (dwj_build_segments / dwj_probe_pairs_segments): the multi-GPU exchange delivers every source
-// rank's rows as one block (one large copy-engine transfer per peer), region-grouped inside the block, and the
-// kernels walk the blocks region by region -- segment (region g, source s) after (g, s-1) -- without a regrouping
-// pass.  A kernel's work unit (tile / chunk) never straddles two segments: segment i owns units [first_unit[i],
-// first_unit[i+1]).
+// A relation may be handed to the build / probe / scatter kernels as a LIST OF SEGMENTS instead of one contiguous range
+// (dwj_*_segments): every segment carries its own column pointers, so a segment may live anywhere -- in particular in a
+// PEER GPU's memory mapped over NVLink.  That is how the multi-GPU join moves data: the sender groups its rows by
+// destination in its own memory and the receiver's kernels read ("pull") their rows straight out of the senders'
+// buffers, one segment per (table region, source rank), without an intermediate copy (dwj_xj.cu).  A kernel's work unit
+// (tile / chunk) never straddles two segments: segment i owns units [first_unit[i], first_unit[i+1]).
 struct Seg {
   unsigned long long first_unit;   // first tile / chunk of this segment (entry n_segs holds the total)
-  unsigned long long phys_row;     // first row inside the allocation
+  const void *keys;                // first key of the segment
+  const void *vals;                // first payload (may be null where the kernel takes no payloads)
   unsigned long long rows;
 };
 DWJ_D uint32_t find_segment(const Seg *segs, uint32_t n_segs, unsigned long long unit) {

@@ -90,6 +90,8 @@ struct RunOptions {
   size_t iterations = 1;
   std::string root_path;
   std::string report_path;
+  size_t gpus = 1;   // not in the reference (one queue on one device, join/join.cpp:23-24): `--gpus N` runs the Join
+                     // dwarfs over N GPUs of the box (dwj_mg_*); 1 = the single-GPU engine
 };
 
 struct GroupByRunOptions : public RunOptions {

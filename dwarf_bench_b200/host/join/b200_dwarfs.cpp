@@ -1,6 +1,8 @@
 #include "b200_dwarfs.hpp"
 
+#include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <limits>
 #include <numeric>
 #include <stdexcept>
@@ -108,6 +110,66 @@ std::unique_ptr<HashJoinResult> join_iteration(b200::Engine &eng, const std::vec
   return result;
 }
 
+// GPUs the Join dwarfs use: RunOptions::gpus in this tree (`--gpus N`); under the reference's own headers (the drop-in
+// build, oracle/dropin_main.cpp) RunOptions has no such field and the environment variable DWARF_BENCH_GPUS decides.
+size_t gpus_of(const RunOptions &opts) {
+  size_t n = 1;
+#ifdef DWJ_HOST_FRAMEWORK
+  n = opts.gpus;
+#else
+  (void)opts;
+#endif
+  if (const char *v = std::getenv("DWARF_BENCH_GPUS")) n = std::max<size_t>(n, std::strtoul(v, nullptr, 10));
+  return std::max<size_t>(n, 1);
+}
+
+// The Join flow over N GPUs (dwj_mg_*): the host columns are dealt to the GPUs in arrival order, hash-partitioned and
+// exchanged over NVLink, joined locally; the result comes back compacted, so the reference's host compaction loop
+// (join.cpp:119-129) has nothing left to do.  Same check against the expected rows.
+void join_run_multi_gpu(const size_t buf_size, Meter &meter, size_t gpus, const std::vector<uint32_t> &ak, const std::vector<uint32_t> &av,
+                        const std::vector<uint32_t> &bk, const std::vector<uint32_t> &bv,
+                        const ColJoinedTableTy<uint32_t, uint32_t, uint32_t> &expected) {
+  const RunOptions &opts = meter.opts();
+  dwj_mg_config cfg{};
+  cfg.n_gpus = static_cast<int32_t>(gpus);
+  for (size_t i = 0; i < gpus && i < 8; ++i) cfg.devices[i] = static_cast<int32_t>(i);
+  cfg.key_bytes = 4;
+  cfg.flags = DWJ_FLAG_UNIQUE_BUILD_KEYS;
+  cfg.max_build_rows_per_gpu = cfg.max_probe_rows_per_gpu = std::max<size_t>((buf_size + gpus - 1) / gpus, 1);
+  cfg.recv_slack = 1.5;                                     // small inputs spread unevenly over the ranks
+  dwj_mg *mg = nullptr;
+  b200::Engine::check(dwj_mg_create(&cfg, &mg));
+  struct Guard { dwj_mg *m; ~Guard() { dwj_mg_destroy(m); } } guard{mg};
+  for (unsigned it = 0; it < opts.iterations; ++it) {
+    const size_t n = bk.size();
+    std::vector<uint32_t> res_k(n), res_present(n), res_val(n);
+    auto result = std::make_unique<HashJoinResult>();
+    dwj_mg_timing t{};
+    uint64_t n_out = 0;
+    const auto host_start = Clock::now();
+    b200::Engine::check(dwj_mg_join_host(mg, ak.data(), av.data(), ak.size(), bk.data(), bv.data(), n, res_k.data(), res_present.data(),
+                                         res_val.data(), n, &n_out, &t));
+    const auto host_end = Clock::now();
+    result->host_time = host_end - host_start;
+    result->build_time = ms(t.build_ms);                    // partition + exchange + local build, slowest GPU
+    result->probe_time = ms(t.total_ms - t.build_ms);
+    result->kernel_time = ms(t.total_ms);
+    res_k.resize(n_out);
+    res_present.resize(n_out);
+    res_val.resize(n_out);
+#ifdef DWJ_HOST_FRAMEWORK
+    result->matches = n_out;
+    result->tuples_per_second = (ak.size() + n) / (result->kernel_time.count() * 1e-6);
+#endif
+    const ColJoinedTableTy<uint32_t, uint32_t, uint32_t> output{res_k, {res_present, res_val}};
+    if (!(output == expected)) {
+      std::cerr << "Incorrect results" << std::endl;
+      result->valid = false;
+    }
+    meter.add_result(DwarfParams{{"buf_size", std::to_string(buf_size)}}, std::move(result));
+  }
+}
+
 void join_run(const size_t buf_size, Meter &meter) {
   const RunOptions &opts = meter.opts();
   const std::vector<uint32_t> table_a_keys = helpers::make_unique_random(buf_size);          // join.cpp:13-21
@@ -116,6 +178,10 @@ void join_run(const size_t buf_size, Meter &meter) {
   const std::vector<uint32_t> table_b_values = helpers::make_unique_random(table_b_keys.size());
   announce_device();
   const auto expected = sort_join<uint32_t, uint32_t, uint32_t>(table_a_keys, table_a_values, table_b_keys, table_b_values);
+  if (const size_t gpus = gpus_of(opts); gpus > 1) {
+    join_run_multi_gpu(buf_size, meter, gpus, table_a_keys, table_a_values, table_b_keys, table_b_values, expected);
+    return;
+  }
   b200::Engine eng(std::max<size_t>(buf_size, 1), DWJ_FLAG_UNIQUE_BUILD_KEYS);
   for (unsigned it = 0; it < opts.iterations; ++it) {
     auto result = join_iteration(eng, table_a_keys, table_a_values, table_b_keys, table_b_values, expected);

@@ -1,7 +1,7 @@
 // dwarf_bench -- command line front end (reference: main.cpp, there on boost::program_options).
 //
 //   dwarf_bench <Dwarf|list> [--input_size a b ...] [--iterations N] [--device cpu|gpu|igpu]
-//               [--report_path P] [--groups_count N] [--executors N] [--help]
+//               [--report_path P] [--groups_count N] [--executors N] [--gpus N] [--help]
 // Same spellings: positional dwarf name, multitoken --input_size, "--opt value" and "--opt=value",
 // case-insensitive device.  Deliberate difference: a caught exception makes the exit code 2 (the reference
 // prints "Caught exception" and still returns 0, main.cpp:97-100).
@@ -26,7 +26,8 @@ void print_help() {
                "  --device arg          Device to run on.\n"
                "  --report_path arg     Full/Relative path to a report file.\n"
                "  --groups_count arg    Number of unique keys for dwarfs with keys (groupby, hash build etc.).\n"
-               "  --executors arg       Number of executors for GroupByLocal.\n";
+               "  --executors arg       Number of executors for GroupByLocal.\n"
+               "  --gpus arg            GPUs of this box the Join dwarfs run on: 1, 2, 4 or 8 (not in the reference).\n";
 }
 
 size_t to_size(const std::string &opt, const std::string &text) {
@@ -90,6 +91,8 @@ int main(int argc, char *argv[]) {
         in >> opts->device_ty;
       } else if (name == "report_path") {
         opts->report_path = next_value();
+      } else if (name == "gpus") {
+        opts->gpus = to_size(name, next_value());
       } else if (name == "groups_count") {
         groups_count = to_size(name, next_value());
       } else if (name == "executors") {

@@ -27,9 +27,10 @@
  *                        implicit sycl::buffer H2D/D2H copies made explicit
  *   dwj_timings          HashJoinResult{build_time,probe_time,host_time,
  *                        kernel_time}  common/result.hpp:11-33
- *   dwj_partition*, dwj_xpart_*, dwj_*_grouped, dwj_copy_many
- *                        new (no reference counterpart): radix partition on
- *                        the key hash and exchange plumbing for the multi-GPU join
+ *   dwj_partition*, dwj_xpart_*, dwj_*_grouped, dwj_*_segments, dwj_xj_*, dwj_mg_*
+ *                        new (no reference counterpart: the reference runs one
+ *                        queue on one device, join/join.cpp:23-24): radix partition
+ *                        on the key hash and the multi-GPU exchange join
  */
 #ifndef DWJ_H
 #define DWJ_H
@@ -41,7 +42,7 @@
 extern "C" {
 #endif
 
-#define DWJ_ABI_VERSION 1
+#define DWJ_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DWJ_API __attribute__((visibility("default")))
@@ -91,7 +92,7 @@ typedef struct {
 typedef struct {
   float build_ms;     /* device time of the last dwj_build (table clear + insert)          */
   float probe_ms;     /* device time of the last dwj_probe_*                               */
-  float partition_ms; /* device time of the last dwj_partition                             */
+  float partition_ms; /* device time of the last dwj_partition / dwj_xpart_scatter          */
   float h2d_ms;       /* dwj_join_host only: host->device copies                           */
   float d2h_ms;       /* dwj_join_host only: device->host copies                           */
   float total_ms;     /* dwj_join_host: first copy to last copy; else build_ms + probe_ms  */
@@ -116,6 +117,10 @@ typedef struct {
                                 emits rows region by region instead of in probe-row order   */
   uint32_t probe_passes;     /* > 1: dwj_probe_pairs (unique build keys) sweeps the probe relation
                                 this many times, one table slice per pass, instead of partitioning it */
+  uint32_t flags;            /* dwj_config.flags the engine was created with                */
+  int32_t device;            /* its CUDA device                                             */
+  uint64_t hash_seed;
+  uint64_t max_build_rows;   /* dwj_config.max_build_rows                                   */
 } dwj_info;
 
 DWJ_API int dwj_abi_version(void);
@@ -188,15 +193,6 @@ DWJ_API int dwj_partition(dwj_engine *e, const void *d_keys, const void *d_vals,
 DWJ_API int dwj_partition_hist(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t n_parts, uint64_t *d_counts,
                        void *stream);
 
-/* Fused partition + exchange: rows of partition p are stored straight to dst_keys[p] / dst_vals[p] starting at row
- * dst_row_offsets[p] (host array).  The destinations may be PEER GPU memory mapped into this process (NVLink P2P,
- * e.g. torch symmetric memory): the scatter kernel's stores are the transfer, no intermediate copy and no
- * collective call.  1, 2, 4 or 8 partitions.  The caller plans the layout (dwj_partition_hist + an all-gather of the
- * counts) and synchronises the ranks afterwards.  dst_vals/d_vals may both be NULL.  Asynchronous. */
-DWJ_API int dwj_partition_scatter_to(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, uint32_t n_parts,
-                             void *const *dst_keys, void *const *dst_vals, const uint64_t *dst_row_offsets,
-                             void *stream);
-
 /* ---- exchange partition folded with the receiver's region grouping (multi-GPU) ----------------------------------
  * One pass over a relation that serves BOTH the exchange and the receiver's L2-region grouping: partition id =
  * destination rank (independent hash, as dwj_partition) x table region of the destination's table (top bits of the
@@ -225,30 +221,149 @@ DWJ_API int dwj_build_grouped(dwj_engine *e, const void *d_keys, const void *d_v
 DWJ_API int dwj_probe_pairs_grouped(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *d_out_key,
                             void *d_out_build_val, void *d_out_probe_val, uint64_t capacity, uint64_t *d_n_matches,
                             uint64_t *n_matches, void *stream);
-/* The same for rows that arrive as a LIST OF SEGMENTS of one allocation (d_keys / d_vals address the allocation,
- * segment i = rows [seg_first_row[i], +seg_rows[i]), host arrays, at most 512 segments) and are to be consumed in list
- * order: e.g. one block per source rank, region-grouped inside the block, walked region by region -- (region 0, source
- * 0), (region 0, source 1), ... -- so that every source's rows can be delivered with ONE large copy per peer and still
- * be built / probed one table region at a time.  segments_per_region (build; 0 = unknown) tells the look-ahead that
- * segments [r * segments_per_region, (r+1) * segments_per_region) belong to table region r.  The probe variant is
- * implemented for DWJ_FLAG_UNIQUE_BUILD_KEYS engines. */
-DWJ_API int dwj_build_segments(dwj_engine *e, const void *d_keys, const void *d_vals, uint32_t n_segments,
-                       const uint64_t *seg_first_row, const uint64_t *seg_rows, uint32_t segments_per_region, void *stream);
-DWJ_API int dwj_probe_pairs_segments(dwj_engine *e, const void *d_keys, const void *d_vals, uint32_t n_segments,
-                             const uint64_t *seg_first_row, const uint64_t *seg_rows, void *d_out_key, void *d_out_build_val,
-                             void *d_out_probe_val, uint64_t capacity, uint64_t *d_n_matches, uint64_t *n_matches,
-                             void *stream);
-/* n_copies device-to-device copies (local or peer memory mapped into this process), copy i on streams[i]: the copy
- * engines carry the exchange while the SMs partition and join.  Asynchronous. */
-DWJ_API int dwj_copy_many(dwj_engine *e, uint32_t n_copies, void *const *dsts, const void *const *srcs, const uint64_t *bytes,
-                  void *const *streams);
+/* The same for rows that arrive as a LIST OF SEGMENTS -- segment i = seg_rows[i] rows starting at seg_keys[i] /
+ * seg_vals[i] (host arrays of DEVICE pointers, at most 512 segments) -- consumed in list order.  A segment may live in
+ * a PEER GPU's memory mapped into this process (NVLink P2P): the kernels then read ("pull") their rows straight out of
+ * the sender's buffer, which is how the multi-GPU join moves data (dwj_xj_*): one segment per (table region, source
+ * rank), walked region by region -- (region 0, source 0), (region 0, source 1), ... -- so that the table is still built /
+ * probed one L2-resident region at a time without any intermediate copy.  segments_per_region (build; 0 = unknown) tells
+ * the look-ahead that segments [r * segments_per_region, (r+1) * segments_per_region) belong to table region r.  The
+ * probe variant is implemented for DWJ_FLAG_UNIQUE_BUILD_KEYS engines. */
+DWJ_API int dwj_build_segments(dwj_engine *e, uint32_t n_segments, const void *const *seg_keys, const void *const *seg_vals,
+                       const uint64_t *seg_rows, uint32_t segments_per_region, void *stream);
+DWJ_API int dwj_probe_pairs_segments(dwj_engine *e, uint32_t n_segments, const void *const *seg_keys, const void *const *seg_vals,
+                             const uint64_t *seg_rows, void *d_out_key, void *d_out_build_val, void *d_out_probe_val,
+                             uint64_t capacity, uint64_t *d_n_matches, uint64_t *n_matches, void *stream);
+/* Pull scatter: the rows of the segments (as above; local or peer memory) are grouped by the table region of THIS
+ * engine's table: the rows of region g are written to d_out_keys / d_out_vals[start_rows[g] ...] (HOST array of
+ * dwj_info.radix_parts row offsets; the caller knows the region sizes from the senders' dwj_xpart_hist2 counts).  The
+ * result feeds dwj_build_grouped / dwj_probe_pairs_grouped.  This is the receiving end of the exchange when ranks x
+ * regions exceeds 512 and the senders therefore group by destination rank only.  seg_vals / d_out_vals may both be
+ * NULL.  Asynchronous. */
+DWJ_API int dwj_region_scatter_segments(dwj_engine *e, uint32_t n_segments, const void *const *seg_keys, const void *const *seg_vals,
+                                const uint64_t *seg_rows, const uint64_t *start_rows, void *d_out_keys, void *d_out_vals,
+                                void *stream);
+/* Histogram over (destination rank, table region of the destination's table) with ALL of the engine's region bits,
+ * whether or not dwj_xpart_regions() folds them into the scatter: d_counts[n_ranks * dwj_info.radix_parts] (uint64,
+ * device), rank-major.  The senders count for the receivers.  n_ranks: 1, 2, 4 or 8.  Asynchronous. */
+DWJ_API int dwj_xpart_hist2(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t n_ranks, uint64_t *d_counts, void *stream);
 
-/* The same transfer done by a small kernel instead of the copy engines: run i = rows[i] rows (of key_bytes each) from
- * srcs[i] to dsts[i] (local or peer memory), all runs pushed by n_ctas CTAs (0 = 64) with coalesced warp stores, on
- * `stream`.  For many medium-sized runs (ranks x regions per relation) this beats one copy-engine job per run by far
- * and leaves most SMs free.  Asynchronous; at most 2048 runs per call. */
-DWJ_API int dwj_push_runs(dwj_engine *e, uint32_t n_runs, void *const *dsts, const void *const *srcs, const uint64_t *rows,
-                  uint32_t n_ctas, void *stream);
+/* Engine options (dwj_set_option) */
+#define DWJ_OPT_APPEND_OUTPUT 1 /* value != 0: dwj_probe_pairs* append their rows at the running count in *d_n_matches
+                                   (device, required) instead of starting from zero -- several probe calls (chunks of a
+                                   relation, passes over key classes) fill ONE compact result without a host sync.  Rows
+                                   are then emitted in no particular order.                                          */
+#define DWJ_OPT_PASS_FILTER 2   /* value = rank_bits | pass_bits << 8 | pass_id << 16.  A join whose working set exceeds
+                                   one GPU runs as 2^pass_bits passes over key CLASSES (the pass_bits bits of the
+                                   partition hash below the rank_bits destination-rank bits): while the filter is set,
+                                   dwj_build*, dwj_partition*, dwj_xpart_* and the region partition inside dwj_probe_pairs /
+                                   dwj_probe_count skip the rows of every other class.  pass_bits == 0 clears it.       */
+DWJ_API int dwj_set_option(dwj_engine *e, int option, uint64_t value);
+
+/* ---- multi-GPU join -------------------------------------------------------------------------------------------------
+ * No reference counterpart (one sycl::queue on one device, join/join.cpp:23-24).  Equal keys must meet on one GPU: both
+ * relations are radix-partitioned on the key hash and exchanged over NVLink, then every GPU builds and probes locally.
+ * The exchange is a PULL fused into the consuming kernels: a sender groups its rows by destination inside its own
+ * peer-mapped block and raises a flag in the peers' memory; the receiver's build / probe (or region-scatter) kernels read
+ * their rows straight out of the senders' blocks through segment lists.  Counts and flags travel through the same
+ * blocks -- no collective library on the data path.  (csrc/dwj_xj.cu)
+ *
+ * dwj_xj = one rank (one GPU).  The caller supplies `world` equally sized blocks of dwj_xj_block_bytes() bytes, one in
+ * every rank's memory, ALL mapped into this process (blocks[r] = this process's pointer to rank r's block): peer
+ * memory from cudaDeviceEnablePeerAccess / cudaIpcOpenMemHandle / torch symmetric memory.  Every rank creates its
+ * dwj_xj over an engine created with the same key width, table size and hash seed (verified at every join), and the
+ * ranks must be synchronised between the creates and the first join.  dwj_xj_join is collective: every rank calls it
+ * for every step (one host thread per rank, or one process per rank); it blocks once per pass on the exchange of the
+ * counts and otherwise only enqueues work.  The result of a rank -- its share of the global join, compacted, in no
+ * particular order -- is on `stream` when the call returns: rows in d_out_*, their number in *d_n_matches (device). */
+typedef struct dwj_xj dwj_xj;
+typedef struct {
+  int32_t rank, world;        /* world: 1, 2, 4 or 8                                                             */
+  uint64_t max_build_rows;    /* most rows of the build relation THIS rank passes to one dwj_xj_join (same value   */
+  uint64_t max_probe_rows;    /*   on every rank); sizes the send slots                                           */
+  uint64_t chunk_rows;        /* the probe relation travels in pieces of this many rows (0 = 2^26): the sender
+                                 partitions piece c+1 while the receivers pull piece c                           */
+  uint32_t passes;            /* power of two; > 1: the join runs once per key class (DWJ_OPT_PASS_FILTER) with the
+                                 table, slots and landing buffers sized for one class -- for working sets larger than
+                                 the GPUs' memory.  0 = 1                                                        */
+  uint32_t force_scatter_pull;/* testing: take the region-scatter receive path even where the direct pull applies */
+  double recv_slack;          /* head-room of the receive-side landing buffers over an even split (0 = 1.25)     */
+} dwj_xj_config;
+typedef struct {
+  uint32_t regions;           /* table regions of every rank's table                                             */
+  uint32_t fold_regions;      /* regions grouped by the SENDER's pass (== regions: the receiver pulls directly)   */
+  uint32_t chunks, ring;      /* probe chunks per join; send slots they rotate through                           */
+  uint32_t passes;
+  uint32_t direct_pull;       /* 1: build / probe kernels pull from the senders; 0: the receiver's region scatter does */
+  uint64_t chunk_rows;
+  uint64_t block_bytes;       /* = dwj_xj_block_bytes                                                            */
+  uint64_t landing_bytes;     /* local buffers of the region-scatter receive path                                */
+} dwj_xj_info;
+typedef struct {              /* device timeline of the last join on this rank, ms from its start (first pass)   */
+  float counts_ms;            /* counts of every batch computed, exchanged and read by the host                  */
+  float scattered_ms;         /* last batch grouped into its send slot                                           */
+  float built_ms;             /* local table built                                                               */
+  float total_ms;             /* last probe chunk done (all passes)                                              */
+  uint64_t remote_bytes;      /* bytes this rank pulled over NVLink                                              */
+} dwj_xj_timing;
+DWJ_API int dwj_xj_block_bytes(const dwj_engine *e, const dwj_xj_config *cfg, uint64_t *bytes);
+DWJ_API int dwj_xj_create(dwj_engine *e, const dwj_xj_config *cfg, void *const *blocks, dwj_xj **out);
+DWJ_API int dwj_xj_destroy(dwj_xj *x);
+DWJ_API int dwj_xj_describe(const dwj_xj *x, dwj_xj_info *info);
+DWJ_API int dwj_xj_join(dwj_xj *x, const void *d_build_keys, const void *d_build_vals, uint64_t n_build, const void *d_probe_keys,
+                const void *d_probe_vals, uint64_t n_probe, void *d_out_key, void *d_out_build_val, void *d_out_probe_val,
+                uint64_t capacity, uint64_t *d_n_matches, void *stream);
+/* Waits for the last join of this rank and returns its timeline (also the place a peer time-out surfaces). */
+DWJ_API int dwj_xj_sync_timings(dwj_xj *x, dwj_xj_timing *t);
+
+/* The layout plan of one batch as pure host functions (what dwj_xj_join computes from the exchanged counts; exported so
+ * the logic can be tested without a GPU).  Sender: mine[dst][region] -> start[] = first slot row of every partition of
+ * its pass (world * fold_regions entries; destination-major, region-minor).  Receiver `me`: tot[src][dst], reg[src][my
+ * region] -> direct != 0: regions * world segments in walking order (region-major, source-minor); direct == 0: one
+ * segment per source plus region_start[regions] of the landing buffer.  Rows are relative to the senders' blocks. */
+DWJ_API int dwj_xj_plan_send(uint32_t world, uint32_t regions, uint32_t fold_regions, uint64_t slot_base_row, const uint64_t *mine,
+                     uint64_t *start);
+DWJ_API int dwj_xj_plan_recv(uint32_t world, uint32_t me, uint32_t regions, uint64_t slot_base_row, const uint64_t *tot, const uint64_t *reg,
+                     int direct, uint64_t *seg_first_row, uint64_t *seg_rows, uint64_t *region_start, uint64_t *total);
+/* Table region (0 .. 2^region_bits - 1) a key falls into for a table of `buckets` 32-byte buckets -- host evaluation of
+ * the kernels' function, as dwj_partition_of. */
+DWJ_API uint32_t dwj_region_of(uint64_t key, int32_t key_bytes, uint64_t buckets, uint32_t region_bits, uint64_t hash_seed);
+
+/* All GPUs of one box from ONE process (the C++ host framework's `dwarf_bench Join --device=gpu --gpus N`): one engine
+ * and one dwj_xj per GPU, peer access enabled both ways, one host thread per GPU inside dwj_mg_join.  devices[] may
+ * name one GPU several times (ranks sharing a GPU: testing). */
+typedef struct dwj_mg dwj_mg;
+typedef struct {
+  int32_t n_gpus;             /* 1, 2, 4 or 8                                                                    */
+  int32_t devices[8];
+  int32_t key_bytes;          /* 4 or 8; payloads have the same width                                            */
+  uint32_t flags;             /* DWJ_FLAG_* of the engines                                                       */
+  uint64_t max_build_rows_per_gpu, max_probe_rows_per_gpu;   /* input rows a GPU holds before the exchange       */
+  double load_factor;         /* of the tables at an even split (0 = 0.5)                                        */
+  uint64_t hash_seed;
+  uint64_t chunk_rows;        /* as dwj_xj_config                                                                */
+  uint32_t passes;
+  uint32_t force_scatter_pull;
+  double recv_slack;
+} dwj_mg_config;
+typedef struct {              /* slowest GPU per mark, ms from the start of the join                             */
+  float counts_ms, partition_ms, build_ms, total_ms;
+  uint64_t remote_bytes;      /* bytes pulled over NVLink, all GPUs                                              */
+} dwj_mg_timing;
+DWJ_API int dwj_mg_create(const dwj_mg_config *cfg, dwj_mg **out);
+DWJ_API int dwj_mg_destroy(dwj_mg *m);
+DWJ_API int dwj_mg_describe(const dwj_mg *m, uint32_t rank, dwj_xj_info *info);
+/* Per-GPU DEVICE columns in, per-GPU compacted rows out (arrays of n_gpus entries; d_out_key may be NULL); n_out[r] =
+ * rows GPU r produced.  Synchronous. */
+DWJ_API int dwj_mg_join(dwj_mg *m, const void *const *d_build_keys, const void *const *d_build_vals, const uint64_t *n_build,
+                const void *const *d_probe_keys, const void *const *d_probe_vals, const uint64_t *n_probe, void *const *d_out_key,
+                void *const *d_out_build_val, void *const *d_out_probe_val, const uint64_t *capacity, uint64_t *n_out,
+                dwj_mg_timing *timing);
+/* HOST columns in and out: the rows are dealt to the GPUs in arrival order (not by key), joined, and the GPUs' result
+ * rows returned one GPU after the other.  Unique build keys (one output row per probe row at most). */
+DWJ_API int dwj_mg_join_host(dwj_mg *m, const void *build_keys, const void *build_vals, uint64_t n_build, const void *probe_keys,
+                     const void *probe_vals, uint64_t n_probe, void *out_key, void *out_build_val, void *out_probe_val,
+                     uint64_t out_capacity, uint64_t *n_out, dwj_mg_timing *timing);
 
 /* Partition id of one key on the host (same function the kernels use) -- lets callers and tests
  * reason about placement without a device. */

@@ -231,6 +231,9 @@ class Ref:
         lib.ref_join_build_probe_u32.restype = C.c_int
         lib.ref_join_build_probe_u32.argtypes = [_u32p, _u32p, C.c_uint64, _u32p, _u32p, C.c_uint64,
                                                  C.c_uint32, _u32p, _u32p, _u32p, _f64p]
+        if hasattr(lib, "ref_join_build_probe_u64"):
+            lib.ref_join_build_probe_u64.restype = C.c_int
+            lib.ref_join_build_probe_u64.argtypes = [_u64p, _u64p, C.c_uint64, _u64p, _u64p, C.c_uint64, _u64p, _u64p, _u64p, _f64p]
 
     @staticmethod
     def available(path: str = REF_SO) -> bool:
@@ -283,10 +286,17 @@ class Ref:
         return found[:len(q)], val[:len(q)], has[:len(q)]
 
     def join_build_probe(self, ak, av, bk, bv, seed: int = 42):
-        ak, av, bk, bv = _u32(ak), _u32(av), _u32(bk), _u32(bv)
         nb = len(bk)
-        ok, op, ov = (np.empty(max(nb, 1), np.uint32) for _ in range(3))
         t = np.zeros(3, np.float64)
+        if np.asarray(ak).dtype.itemsize == 8:      # the reference's templates at 64 bits (ref_driver.cpp), SimpleHasher
+            ak, av, bk, bv = _u64(ak), _u64(av), _u64(bk), _u64(bv)
+            ok, op, ov = (np.empty(max(nb, 1), np.uint64) for _ in range(3))
+            if self.lib.ref_join_build_probe_u64(ak, av, len(ak), bk, bv, nb, ok, op, ov, t) != 0:
+                raise ValueError("the reference's uint32 slot index cannot address this table")
+            return (ok[:nb], op[:nb], ov[:nb]), {"build_us": t[0], "probe_us": t[1], "host_us": t[2],
+                                                  "threads": self.max_threads()}
+        ak, av, bk, bv = _u32(ak), _u32(av), _u32(bk), _u32(bv)
+        ok, op, ov = (np.empty(max(nb, 1), np.uint32) for _ in range(3))
         self.lib.ref_join_build_probe_u32(ak, av, len(ak), bk, bv, nb, seed, ok, op, ov, t)
         return (ok[:nb], op[:nb], ov[:nb]), {"build_us": t[0], "probe_us": t[1], "host_us": t[2],
                                               "threads": self.max_threads()}

@@ -210,4 +210,57 @@ int ref_join_build_probe_u32(const uint32_t *ak, const uint32_t *av, uint64_t na
   return 0;
 }
 
+// The same loop body over 64-bit keys and payloads (BASELINE configs 4-5 have no reference counterpart: the reference
+// Join is uint32-only).  The reference's OWN templates instantiated at 64 bits: SimpleNonOwningHashTable<uint64_t,
+// uint64_t, SimpleHasher<uint64_t>> (hashtable.hpp:5-93, hashfunctions.hpp:43-49 -- Murmur3_x86_32 takes 32-bit input,
+// SimpleHasher is the reference's hasher that accepts any integral key), T = 2n slots, sentinel-filled probe-aligned
+// outputs, timed as join.cpp:59-113.  Slot indices are uint32_t in the reference (hashtable.hpp:16): na < 2^31.
+int ref_join_build_probe_u64(const uint64_t *ak, const uint64_t *av, uint64_t na,
+                             const uint64_t *bk, const uint64_t *bv, uint64_t nb,
+                             uint64_t *out_key, uint64_t *out_present, uint64_t *out_val,
+                             double *timing_us) {
+  constexpr uint64_t empty_element = std::numeric_limits<uint64_t>::max();
+  if (na >= (1ull << 31)) return -1;
+  const size_t ht_size = na * 2;
+  const size_t bitmask_sz = std::ceil((float)ht_size / 32);
+  SimpleHasher<uint64_t> hasher(ht_size ? ht_size : 1);
+  std::vector<uint32_t> bitmask(bitmask_sz ? bitmask_sz : 1, 0);
+  std::vector<uint64_t> data(ht_size ? ht_size : 1, 0);
+  std::vector<uint64_t> keys(ht_size ? ht_size : 1, empty_element);
+  std::fill(out_key, out_key + nb, empty_element);
+  std::fill(out_present, out_present + nb, empty_element);
+  std::fill(out_val, out_val + nb, empty_element);
+  uint64_t *kp = keys.data(), *dp = data.data();
+  uint32_t *mp = bitmask.data();
+  using Table = SimpleNonOwningHashTable<uint64_t, uint64_t, SimpleHasher<uint64_t>>;
+  auto host_start = std::chrono::steady_clock::now();
+  if (na) {
+#pragma omp parallel for schedule(static)
+    for (int64_t idx = 0; idx < (int64_t)na; ++idx) {
+      Table ht(ht_size, bitmask_sz, kp, dp, mp, hasher);
+      ht.insert(ak[idx], av[idx]);
+    }
+  }
+  auto build_end = std::chrono::steady_clock::now();
+  if (na) {
+#pragma omp parallel for schedule(static)
+    for (int64_t idx = 0; idx < (int64_t)nb; ++idx) {
+      Table ht(ht_size, bitmask_sz, kp, dp, mp, hasher);
+      auto ans = ht.at(bk[idx]);
+      if (ans.second) {
+        out_key[idx] = bk[idx];
+        out_present[idx] = ans.first;
+        out_val[idx] = bv[idx];
+      }
+    }
+  }
+  auto host_end = std::chrono::steady_clock::now();
+  using us = std::chrono::duration<double, std::micro>;
+  if (timing_us) {
+    timing_us[0] = us(build_end - host_start).count();
+    timing_us[1] = us(host_end - build_end).count();
+    timing_us[2] = us(host_end - host_start).count();
+  }
+  return 0;
+}
 } // extern "C"

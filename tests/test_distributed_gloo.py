@@ -107,96 +107,68 @@ def test_exchange_join_world2(tmp_path, oracle, world):
         assert all(capi.partition_of(int(k), 4, world, 42) == r for k in p["k"][:200])
 
 
-def test_plan_exchange_layout():
-    """Host logic of the fused P2P exchange: source-major receive layout, no overlaps, nothing lost."""
-    from dwarf_bench_b200.distributed import plan_exchange
-    rng = np.random.default_rng(3)
-    for world in (1, 2, 4, 8):
-        counts = rng.integers(0, 1000, (world, world)).tolist()
-        plans = [plan_exchange(counts, r) for r in range(world)]
-        for d in range(world):
-            # the ranges [offset_s, offset_s + counts[s][d]) written by every source s tile the receive buffer of d exactly
-            spans = sorted((plans[s][0][d], plans[s][0][d] + counts[s][d]) for s in range(world))
-            assert spans[0][0] == 0
-            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
-                assert a1 == b0
-            assert spans[-1][1] == plans[d][1] == sum(counts[s][d] for s in range(world))
+def _sim_exchange(world, regions, fold, direct, n_rows, key_bytes, rng, lib):
+    """The exchange of ONE batch, device memory played by numpy arrays, laid out by the exported plan functions
+    (include/dwj.h: dwj_xj_plan_send / dwj_xj_plan_recv) exactly as dwj_xj_join uses them."""
+    import ctypes as C
+    u64p = C.POINTER(C.c_uint64)
+    buckets = 1 << 12
+    region_bits = regions.bit_length() - 1
+    base = 64                                                   # the slot does not start at row 0
+    dt = np.uint32 if key_bytes == 4 else np.uint64
+    keys = [rng.integers(0, 2**31, n_rows[s]).astype(dt) for s in range(world)]
+    dst = [np.array([lib.dwj_partition_of(int(k), key_bytes, world, 42) for k in ks], dtype=np.int64) for ks in keys]
+    reg = [np.array([lib.dwj_region_of(int(k), key_bytes, buckets, region_bits, 42) for k in ks], dtype=np.int64) for ks in keys]
+    counts = np.zeros((world, world, regions), dtype=np.uint64)               # [src][dst][region]
+    for s in range(world):
+        np.add.at(counts[s], (dst[s], reg[s]), 1)
+    slots = []
+    for s in range(world):                                      # sender: partition pass into its slot
+        start = np.zeros(world * fold, dtype=np.uint64)
+        mine = np.ascontiguousarray(counts[s])
+        assert lib.dwj_xj_plan_send(world, regions, fold, base, mine.ctypes.data_as(u64p), start.ctypes.data_as(u64p)) == 0
+        slot = np.full(base + n_rows[s], -1, dtype=np.int64)
+        part = dst[s] * fold + (reg[s] if fold == regions else 0)
+        cursor = start.astype(np.int64).copy()
+        for i, p in enumerate(part):                            # any order inside a partition is fine
+            slot[cursor[p]] = i
+            cursor[p] += 1
+        assert (slot[base:] >= 0).all() and len(set(slot[base:])) == n_rows[s]
+        slots.append(slot)
+    seen = [np.zeros(n_rows[s], dtype=bool) for s in range(world)]
+    for me in range(world):                                     # receiver: segments into the senders' slots
+        tot = np.ascontiguousarray(counts.sum(axis=2))          # [src][dst]
+        rg = np.ascontiguousarray(counts[:, me, :])             # [src][region]
+        n = regions * world if direct else world
+        first, rows, rstart, total = (np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64), np.zeros(regions, dtype=np.uint64),
+                                      C.c_uint64(0))
+        assert lib.dwj_xj_plan_recv(world, me, regions, base, tot.ctypes.data_as(u64p), rg.ctypes.data_as(u64p), 1 if direct else 0,
+                                    first.ctypes.data_as(u64p), rows.ctypes.data_as(u64p), rstart.ctypes.data_as(u64p), C.byref(total)) == 0
+        assert total.value == tot[:, me].sum()
+        assert (rstart == np.cumsum(rg.sum(axis=0)) - rg.sum(axis=0)).all()
+        for i in range(n):
+            s = i % world if direct else i
+            idx = slots[s][int(first[i]):int(first[i] + rows[i])]
+            assert (idx >= 0).all() and not seen[s][idx].any()
+            seen[s][idx] = True
+            assert (dst[s][idx] == me).all()                    # equal keys meet on one rank ...
+            if direct:                                          # ... and arrive grouped by the receiver's table region
+                assert (reg[s][idx] == i // world).all()
+    for s in range(world):
+        assert seen[s].all()                                    # nothing lost, nothing delivered twice
 
 
-def test_plan_folded_exchange_layout():
-    """Folded exchange: at every destination each relation's receive buffer is tiled exactly by the (batch, region,
-    source) runs in that order; a batch is one contiguous segment; region offsets are the per-region totals; the
-    sender's runs tile its send buffer chunk by chunk."""
-    from dwarf_bench_b200.distributed import plan_folded_exchange
-    rng = np.random.default_rng(9)
-    for world, regions, chunks in ((2, 4, 1), (8, 8, 2), (4, 1, 3)):
-        parts = world * regions
-        counts = rng.integers(0, 300, (world, 1 + chunks, parts))
-        # rows of every probe chunk at every source (the sender scatters chunk c in place of its input rows)
-        bounds = [[0] + list(np.cumsum(counts[s, 1:].sum(axis=1))) for s in range(world)]      # chunks + 1 entries
-        plans = [plan_folded_exchange(counts, r, regions, bounds[r]) for r in range(world)]
-        for d in range(world):
-            for relation in (range(0, 1), range(1, 1 + chunks)):
-                spans = []
-                for b in relation:
-                    for g in range(regions):
-                        for s in range(world):
-                            p = d * regions + g
-                            spans.append((int(plans[s]["dst_row"][b, p]), int(counts[s, b, p]), b, g, s))
-                pos = 0
-                for start, rows, b, g, s in spans:                    # already in (batch, region, source) order
-                    assert start == pos, (world, regions, chunks, d, b, g, s)
-                    pos += rows
-                for b in relation:
-                    first, rows = plans[d]["seg"][b]
-                    mine = [sp for sp in spans if sp[2] == b]
-                    assert first == mine[0][0] and rows == sum(sp[1] for sp in mine)
-                    roff = plans[d]["region_off"][b]
-                    assert roff[0] == 0 and roff[-1] == rows
-                    for g in range(regions):
-                        assert roff[g + 1] - roff[g] == sum(sp[1] for sp in mine if sp[3] == g)
-        for s in range(world):
-            src = plans[s]["src_row"]
-            assert (src[0] == np.cumsum(counts[s, 0]) - counts[s, 0]).all()
-            for c in range(chunks):
-                assert src[1 + c, 0] == bounds[s][c]
-                assert (np.diff(src[1 + c]) == counts[s, 1 + c, :-1]).all()
-
-
-def test_plan_blocked_exchange_layout():
-    """Blocked (source-major) folded exchange: one block per (source, destination, batch); the blocks and the rows a
-    rank scatters in place tile every receive area exactly; the segment list walks a batch region by region, source by
-    source, and names exactly the rows of that (source, region) run."""
-    from dwarf_bench_b200.distributed import plan_blocked_exchange
-    rng = np.random.default_rng(1)
-    for w, G, C in ((2, 4, 1), (8, 8, 2), (4, 2, 3)):
-        cnt = rng.integers(0, 50, (w, 1 + C, w * G))
-        bounds = [[0] + list(np.cumsum(cnt[s, 1:].sum(axis=1))) for s in range(w)]
-        plans = [plan_blocked_exchange(cnt, r, G, bounds[r]) for r in range(w)]
-        tag = lambda s, b, p: (s * 100 + b) * 1000 + p                  # noqa: E731
-        for d in range(w):
-            for rel in (range(0, 1), range(1, 1 + C)):
-                area = np.full(sum(plans[d]["seg"][b][1] for b in rel), -1)
-                for s in range(w):
-                    for b in rel:
-                        if s == d:                                        # scattered in place, run by run
-                            for g in range(G):
-                                r0, n = plans[s]["own_row"][b, g], cnt[s, b, d * G + g]
-                                assert (area[r0:r0 + n] == -1).all()
-                                area[r0:r0 + n] = tag(s, b, d * G + g)
-                        else:                                             # one transfer: the sender's (d, *) stretch
-                            r0, n = plans[s]["block_dst"][b, d], plans[s]["block_rows"][b, d]
-                            assert n == cnt[s, b, d * G:(d + 1) * G].sum()
-                            assert plans[s]["block_src"][b, d] == plans[s]["src_row"][b, d * G]
-                            ids = [np.full(cnt[s, b, d * G + g], tag(s, b, d * G + g)) for g in range(G)]
-                            assert (area[r0:r0 + n] == -1).all()
-                            area[r0:r0 + n] = np.concatenate(ids)
-                assert (area != -1).all()
-                for b in rel:
-                    f, r = plans[d]["seg_first"][b], plans[d]["seg_rows"][b]
-                    i = 0
-                    for g in range(G):
-                        for s in range(w):
-                            assert r[i] == cnt[s, b, d * G + g] and (area[f[i]:f[i] + r[i]] == tag(s, b, d * G + g)).all()
-                            i += 1
-                    assert r.sum() == plans[d]["seg"][b][1]
+@pytest.mark.parametrize("world,regions", [(1, 4), (2, 8), (4, 1), (8, 16), (8, 64)])
+@pytest.mark.parametrize("key_bytes", [4, 8])
+def test_xj_plan_layout(world, regions, key_bytes):
+    """Host logic of the multi-GPU pull exchange without a GPU: sender layout and receiver segment lists tile every slot
+    exactly, every row reaches the rank (and region) its key hashes to, for the direct pull (regions folded into the
+    sender's pass) and for the region-scatter pull (sender groups by destination only)."""
+    from dwarf_bench_b200 import capi
+    lib = capi.load_library()
+    rng = np.random.default_rng(world * 100 + regions + key_bytes)
+    n_rows = [int(x) for x in rng.integers(200, 900, world)]
+    n_rows[-1] = 0 if world > 2 else n_rows[-1]                # a rank with nothing to send
+    _sim_exchange(world, regions, regions, True, n_rows, key_bytes, rng, lib)
+    _sim_exchange(world, regions, 1, False, n_rows, key_bytes, rng, lib)
+    _sim_exchange(world, regions, regions, False, n_rows, key_bytes, rng, lib)      # non-unique engines: folded sender, scatter pull

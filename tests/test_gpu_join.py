@@ -415,151 +415,133 @@ def test_region_partitioned_path_small(dwj, oracle, monkeypatch, wide, unique):
         np.testing.assert_array_equal(w, x)
 
 
+def _unique_keys(rng, n, dt):
+    space = 2**32 - 7 if dt == np.uint32 else 2**62
+    k = np.unique(rng.integers(0, space, n + n // 8).astype(dt))[:n]
+    rng.shuffle(k)
+    return k
+
+
 @pytest.mark.parametrize("wide", [False, True])
-@pytest.mark.parametrize("parts", [2, 8])
-def test_partition_scatter_to_destinations(dwj, wide, parts):
-    """The fused partition+exchange entry point with LOCAL destinations standing in for peer buffers: every partition
-    lands in its own buffer at the planned row offset; counts from dwj_partition_hist match."""
+@pytest.mark.parametrize("regions", [False, True])
+def test_pass_filter_and_append(dwj, oracle, monkeypatch, wide, regions):
+    """DWJ_OPT_PASS_FILTER + DWJ_OPT_APPEND_OUTPUT: the join run as 4 passes over key classes, the probe relation in three
+    pieces per pass, every piece appending to ONE compact result through the device counter -- same multiset as the
+    oracle's single join, with and without the engine's region partition."""
+    if regions:
+        monkeypatch.setenv("DWJ_PARTITION_MIN_MB", "0")
+        monkeypatch.setenv("DWJ_REGION_MB", "0.125")
     from dwarf_bench_b200 import capi
-    rng = np.random.default_rng(parts + wide)
+    rng = np.random.default_rng(31 + wide)
     dt = np.uint64 if wide else np.uint32
-    n = 700_001
-    k = rng.integers(0, 2**31, n).astype(dt)
-    v = np.arange(n, dtype=dt)
-    with dwj.Engine(16, key_bytes=dt().itemsize, hash_seed=42) as e:
-        counts = torch.zeros(parts, dtype=torch.int64, device="cuda")
-        dk, dv = dev(k), dev(v)
-        e.partition_hist(dk, n, parts, counts)
-        c = counts.cpu().numpy()
-        pid = np.array([capi.partition_of(int(x), dt().itemsize, parts, 42) for x in k[:5000]])
-        assert c.sum() == n and (np.diff(np.sort(c)) >= 0).all()
-        start = [17 * (p + 1) for p in range(parts)]                    # planned offsets inside each destination
-        bufk = [empty_like_dev(int(c[p]) + start[p] + 5, dt) for p in range(parts)]
-        bufv = [empty_like_dev(int(c[p]) + start[p] + 5, dt) for p in range(parts)]
-        for b in bufk + bufv:
-            b.fill_(-1)
-        e.partition_scatter_to(dk, dv, n, parts, [b.data_ptr() for b in bufk], [b.data_ptr() for b in bufv], start)
+    ak = _unique_keys(rng, 120_000, dt)
+    av = rng.integers(0, 2**31, len(ak)).astype(dt)
+    bk = np.concatenate([ak[rng.integers(0, len(ak), 260_000)], rng.integers(0, 2**31, 9_001).astype(dt)])
+    bv = np.arange(len(bk), dtype=dt)
+    want = oracle.sort_join(ak, av, bk, bv)
+    P = 4
+    with dwj.Engine(len(ak) // P * 2, key_bytes=dt().itemsize, flags=dwj.FLAG_UNIQUE_BUILD_KEYS) as e:
+        assert (e.info()["radix_parts"] > 1) == regions
+        dak, dav, dbk, dbv = dev(ak), dev(av), dev(bk), dev(bv)
+        cap = len(bk)
+        ok, oa, ob = (empty_like_dev(cap, dt) for _ in range(3))
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        e.set_option(capi.OPT_APPEND_OUTPUT, 1)
+        bounds = [0, 100_000, 100_001, len(bk)]
+        for p in range(P):
+            e.set_pass_filter(0, 2, p)
+            e.build(dak, dav, len(ak))
+            for c in range(3):
+                lo, hi = bounds[c], bounds[c + 1]
+                e.probe_pairs(dbk[lo:], dbv[lo:], hi - lo, ok, oa, ob, cap, d_n_matches=cnt, sync=False)
+        e.set_pass_filter(0, 0, 0)
+        e.set_option(capi.OPT_APPEND_OUTPUT, 0)
         torch.cuda.synchronize()
-        seen = []
-        for p in range(parts):
-            kk, vv = host(bufk[p], dt), host(bufv[p], dt)
-            assert (kk[:start[p]] == dt(~dt(0))).all() and (kk[start[p] + c[p]:] == dt(~dt(0))).all()   # nothing outside the plan
-            rows = vv[start[p]:start[p] + c[p]].astype(np.int64)
-            np.testing.assert_array_equal(k[rows], kk[start[p]:start[p] + c[p]])
-            assert all(capi.partition_of(int(x), dt().itemsize, parts, 42) == p for x in kk[start[p]:start[p] + 300])
-            seen.append(rows)
-        np.testing.assert_array_equal(np.sort(np.concatenate(seen)), np.arange(n))
-        assert np.bincount(pid, minlength=parts).sum() == 5000
+        m = int(cnt.item())
+        got = pyoracle.canonical_rows(*(host(t, dt)[:m] for t in (ok, oa, ob)))
+    assert m == len(want[0])
+    for w, x in zip(want, got):
+        np.testing.assert_array_equal(w, x)
 
 
 @pytest.mark.parametrize("wide", [False, True])
-@pytest.mark.parametrize("layout", ["region", "blocked"])
-@pytest.mark.parametrize("world,chunks", [(4, 2), (8, 1), (2, 3)])
-def test_folded_exchange_single_gpu(dwj, oracle, monkeypatch, wide, world, chunks, layout):
-    """The folded exchange (dwj_xpart_hist / dwj_xpart_scatter / dwj_copy_many / dwj_build_grouped /
-    dwj_probe_pairs_grouped + plan_folded_exchange) with `world` VIRTUAL ranks on one GPU: every virtual rank
-    partitions its own rows, the planned copies fill every destination's receive buffer, every destination joins what
-    it received, and the union of the destinations' results is the oracle's join of the whole input."""
-    from dwarf_bench_b200 import capi
-    from dwarf_bench_b200.distributed import plan_blocked_exchange, plan_folded_exchange
+def test_segments_pull_and_region_scatter(dwj, oracle, monkeypatch, wide):
+    """Pointer-based segment lists (the receiving end of the multi-GPU exchange, here all in local memory): the build and
+    the probe read their rows from scattered pieces of several allocations; dwj_xpart_hist2 counts per (rank, region);
+    dwj_region_scatter_segments gathers pieces into a region-grouped buffer that dwj_*_grouped consume."""
     monkeypatch.setenv("DWJ_PARTITION_MIN_MB", "0")
-    monkeypatch.setenv("DWJ_REGION_MB", "0.125")              # force table regions at test size
-    rng = np.random.default_rng(11 + world + chunks + wide)
+    monkeypatch.setenv("DWJ_REGION_MB", "0.125")
+    from dwarf_bench_b200 import capi
+    lib = capi.load_library()
+    rng = np.random.default_rng(77 + wide)
     dt = np.uint64 if wide else np.uint32
-    tdt = torch.int64 if wide else torch.int32
-    item = dt().itemsize
-    nb, npr = 40_001, 90_007                                   # rows per virtual rank
-    all_ak = np.unique(rng.integers(1, 2**31, world * nb * 2).astype(dt))[:world * nb]
-    rng.shuffle(all_ak)
-    all_av = rng.integers(0, 2**31, len(all_ak)).astype(dt)
-    all_bk = np.concatenate([all_ak[rng.integers(0, len(all_ak), world * npr - 1000)], rng.integers(2**31, 2**32 - 2, 1000).astype(dt)])
-    rng.shuffle(all_bk)
-    all_bv = np.arange(len(all_bk), dtype=dt)
-    cap = int(len(all_ak) / world * 1.5)
-    with dwj.Engine(cap, key_bytes=item, flags=dwj.FLAG_UNIQUE_BUILD_KEYS, hash_seed=42) as e:
-        regions = e.xpart_regions(world)
-        assert regions == e.info()["radix_parts"] and regions >= 2 and world * regions <= 512
-        parts = world * regions
-        B = 1 + chunks
-        src = []                                               # per virtual rank: inputs, send buffers, counts
-        counts = torch.zeros(world, B, parts, dtype=torch.int64, device="cuda")
-        for s in range(world):
-            ak, av = dev(all_ak[s * nb:(s + 1) * nb]), dev(all_av[s * nb:(s + 1) * nb])
-            bk, bv = dev(all_bk[s * npr:(s + 1) * npr]), dev(all_bv[s * npr:(s + 1) * npr])
-            bounds = [npr * c // chunks for c in range(chunks + 1)]
-            send = [torch.empty(nb, dtype=tdt, device="cuda"), torch.empty(nb, dtype=tdt, device="cuda"),
-                    torch.empty(npr, dtype=tdt, device="cuda"), torch.empty(npr, dtype=tdt, device="cuda")]
-            def starts(cnt):                                   # compact layout: partition runs one after the other
-                c_ = cnt.cpu().numpy()
-                return np.cumsum(c_) - c_
-            e.xpart_hist(ak, nb, world, counts[s, 0])
-            e.xpart_scatter(ak, av, nb, world, starts(counts[s, 0]), send[0], send[1])
-            for c in range(chunks):
-                r0, n = bounds[c], bounds[c + 1] - bounds[c]
-                e.xpart_hist(bk[r0:], n, world, counts[s, 1 + c])
-                e.xpart_scatter(bk[r0:], bv[r0:], n, world, starts(counts[s, 1 + c]), send[2][r0:], send[3][r0:])
-            src.append((send, bounds))
+    W = dt().itemsize
+    ak = _unique_keys(rng, 90_000, dt)
+    av = rng.integers(0, 2**31, len(ak)).astype(dt)
+    bk = ak[rng.integers(0, len(ak), 200_003)]
+    bv = np.arange(len(bk), dtype=dt)
+    want = oracle.sort_join(ak, av, bk, bv)
+    with dwj.Engine(len(ak), key_bytes=W, flags=dwj.FLAG_UNIQUE_BUILD_KEYS) as e:
+        info = e.info()
+        G = info["radix_parts"]
+        assert G >= 8
+        buckets = info["slots"] // info["slots_per_bucket"]
+        region_bits = G.bit_length() - 1
+        # (rank, region) histogram against the host functions
+        dbk = dev(bk)
+        counts = torch.zeros(4 * G, dtype=torch.int64, device="cuda")
+        e.xpart_hist2(dbk, len(bk), 4, counts)
+        sample = bk[:3000]
+        exp = np.zeros(4 * G, dtype=np.int64)
+        for k in sample:
+            exp[lib.dwj_partition_of(int(k), W, 4, 42) * G + lib.dwj_region_of(int(k), W, buckets, region_bits, 42)] += 1
+        c2 = torch.zeros(4 * G, dtype=torch.int64, device="cuda")
+        e.xpart_hist2(dbk, len(sample), 4, c2)
+        assert int(counts.sum().item()) == len(bk) and np.array_equal(c2.cpu().numpy(), exp)
+
+        # pieces of the relations in separate allocations, odd sizes, one empty
+        def pieces(k, v, cuts):
+            out = []
+            for lo, hi in zip(cuts, cuts[1:]):
+                out.append((dev(k[lo:hi]) if hi > lo else None, dev(v[lo:hi]) if hi > lo else None, hi - lo))
+            return out
+        bp = pieces(ak, av, [0, 1, 30_011, 30_011, 70_000, len(ak)])
+        pp = pieces(bk, bv, [0, 4097, 100_000, len(bk)])
+        ptr = lambda t: 0 if t is None else t.data_ptr()          # noqa: E731
+
+        # 1. region scatter of the pieces -> grouped build; probe pieces -> region scatter -> grouped probe (append)
+        reg_of = lambda ks: np.array([lib.dwj_region_of(int(k), W, buckets, region_bits, 42) for k in ks], dtype=np.int64)   # noqa: E731
+        rb = np.bincount(reg_of(ak), minlength=G)
+        start = np.cumsum(rb) - rb
+        lk, lv = empty_like_dev(len(ak), dt), empty_like_dev(len(ak), dt)
+        e.region_scatter_segments([ptr(p[0]) for p in bp], [ptr(p[1]) for p in bp], [p[2] for p in bp], start, lk, lv)
+        roff = torch.from_numpy(np.concatenate([start, [len(ak)]]).astype(np.int64)).cuda()
+        e.build_grouped(lk, lv, len(ak), roff)
         torch.cuda.synchronize()
-        m = counts.cpu().numpy()
-        assert m[:, 0].sum() == world * nb and m[:, 1:].sum() == world * npr
-        # a sampled key sits in the (rank, region) run its hash says; rank part == dwj_partition_of
-        send0 = host(src[0][0][0], dt)
-        run_start = np.cumsum(m[0, 0]) - m[0, 0]
-        for p in rng.integers(0, parts, 40):
-            if m[0, 0, p]:
-                key = int(send0[run_start[p]])
-                assert capi.partition_of(key, item, world, 42) == p // regions
-        blocked = layout == "blocked"
-        plans = [(plan_blocked_exchange if blocked else plan_folded_exchange)(m, r, regions, src[r][1]) for r in range(world)]
-        recv_rows_b = [plans[d]["seg"][0][1] for d in range(world)]
-        recv_rows_p = [sum(n for _, n in plans[d]["seg"][1:]) for d in range(world)]
-        recv = [[torch.full((max(n, 1),), -1, dtype=tdt, device="cuda") for n in (recv_rows_b[d], recv_rows_b[d], recv_rows_p[d], recv_rows_p[d])]
-                for d in range(world)]
-        stream = torch.cuda.current_stream()
-        for s in range(world):
-            send, _ = src[s]
-            pl = plans[s]
-            copies = []
-            for b in range(B):
-                col = 0 if b == 0 else 2
-                if blocked:                                        # one copy per (destination, column); own rows run by run
-                    for d in range(world):
-                        for cc in (col, col + 1):
-                            if d != s:
-                                copies.append((recv[d][cc].data_ptr() + int(pl["block_dst"][b, d]) * item,
-                                               send[cc].data_ptr() + int(pl["block_src"][b, d]) * item, int(pl["block_rows"][b, d]) * item, stream))
-                            else:
-                                for g in range(regions):
-                                    p = d * regions + g
-                                    copies.append((recv[d][cc].data_ptr() + int(pl["own_row"][b, g]) * item,
-                                                   send[cc].data_ptr() + int(pl["src_row"][b, p]) * item, int(pl["rows"][b, p]) * item, stream))
-                else:
-                    for p in range(parts):
-                        d = p // regions
-                        for cc in (col, col + 1):
-                            copies.append((recv[d][cc].data_ptr() + int(pl["dst_row"][b, p]) * item,
-                                           send[cc].data_ptr() + int(pl["src_row"][b, p]) * item, int(pl["rows"][b, p]) * item, stream))
-            e.copy_many(copies)
+        got_reg = reg_of(host(lk, dt)[:len(ak)][::97])
+        assert (np.diff(got_reg) >= 0).all()                        # region-grouped
+        cap = len(bk)
+        ok, oa, ob = (empty_like_dev(cap, dt) for _ in range(3))
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        e.set_option(capi.OPT_APPEND_OUTPUT, 1)
+        for k, v, n in pp:
+            rp = np.bincount(reg_of(host(k, dt)), minlength=G)
+            pk_, pv_ = empty_like_dev(n, dt), empty_like_dev(n, dt)
+            e.region_scatter_segments([ptr(k)], [ptr(v)], [n], np.cumsum(rp) - rp, pk_, pv_)
+            e.probe_pairs_grouped(pk_, pv_, n, ok, oa, ob, cap, d_n_matches=cnt, sync=False)
         torch.cuda.synchronize()
-        got_rows = []
-        for d in range(world):
-            ok, oa, ob = (empty_like_dev(recv_rows_p[d], dt) for _ in range(3))
-            total = 0
-            if blocked:
-                e.build_segments(recv[d][0], recv[d][1], plans[d]["seg_first"][0], plans[d]["seg_rows"][0], world)
-                for c in range(chunks):
-                    rows = plans[d]["seg"][1 + c][1]
-                    total += e.probe_pairs_segments(recv[d][2], recv[d][3], plans[d]["seg_first"][1 + c], plans[d]["seg_rows"][1 + c],
-                                                    ok[total:], oa[total:], ob[total:], rows)
-            else:
-                roff = torch.from_numpy(plans[d]["region_off"][0]).cuda()
-                e.build_grouped(recv[d][0], recv[d][1], recv_rows_b[d], roff)
-                for (row0, rows) in plans[d]["seg"][1:]:
-                    total += e.probe_pairs_grouped(recv[d][2][row0:], recv[d][3][row0:], rows, ok[total:], oa[total:], ob[total:], rows)
-            torch.cuda.synchronize()
-            got_rows.append(tuple(host(t, dt)[:total] for t in (ok, oa, ob)))
-    got = pyoracle.canonical_rows(*(np.concatenate([g[i] for g in got_rows]) for i in range(3)))
-    want = oracle.sort_join(all_ak, all_av, all_bk, all_bv)
-    assert len(got[0]) == len(want[0]) == world * npr - 1000
-    for w_, g_ in zip(want, got):
-        np.testing.assert_array_equal(w_, g_)
+        m = int(cnt.item())
+        got = pyoracle.canonical_rows(*(host(t, dt)[:m] for t in (ok, oa, ob)))
+        assert m == len(want[0])
+        for w, x in zip(want, got):
+            np.testing.assert_array_equal(w, x)
+
+        # 2. the kernels pull from the pieces directly
+        e.set_option(capi.OPT_APPEND_OUTPUT, 0)
+        e.build_segments([ptr(p[0]) for p in bp], [ptr(p[1]) for p in bp], [p[2] for p in bp])
+        m2 = e.probe_pairs_segments([ptr(p[0]) for p in pp], [ptr(p[1]) for p in pp], [p[2] for p in pp], ok, oa, ob, cap)
+        torch.cuda.synchronize()
+        got = pyoracle.canonical_rows(*(host(t, dt)[:m2] for t in (ok, oa, ob)))
+        assert m2 == len(want[0])
+        for w, x in zip(want, got):
+            np.testing.assert_array_equal(w, x)

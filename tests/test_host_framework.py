@@ -35,7 +35,7 @@ def test_c_abi_exports_every_declared_symbol(built):
     from dwarf_bench_b200 import capi
     assert set(capi.SYMBOLS) == declared
     lib = capi.load_library()                       # loads without a GPU; only creating an engine needs one
-    assert lib.dwj_abi_version() == 1
+    assert lib.dwj_abi_version() == 2
     assert capi.partition_of(12345, 4, 8) in range(8) and capi.partition_of(12345, 8, 1) == 0
 
 
