@@ -58,6 +58,11 @@ struct StagedShape { int warps, items, sub, minb; };
 constexpr StagedShape STAGED_SHAPES_4[] = {{8, 4, 4, 4}, {8, 4, 8, 2}, {8, 2, 8, 4}, {4, 4, 4, 8}, {8, 8, 2, 2}};
 constexpr StagedShape STAGED_SHAPES_8[] = {{8, 2, 4, 4}, {8, 2, 8, 2}, {8, 4, 2, 4}, {4, 2, 4, 8}, {8, 4, 4, 2}};
 constexpr int DEFAULT_STAGED_SHAPE_4 = 2, DEFAULT_STAGED_SHAPE_8 = 3;   // gpurun sweep, profiles/r1_probe.md
+constexpr bool DEFAULT_SCATTER_MATCH = false;
+// log2(partitions) from which the shared-memory RED histogram replaces the private-counter ones (profiles/r2_partition_sweep.txt:
+// 8-byte keys 0.35 ms per 2^28 rows at every partition count against 0.35 .. 0.79; 4-byte keys 0.29 against 0.22 / 0.24 / 0.35 / 0.65
+// at 32 / 128 / 256 / 512 partitions)
+constexpr int DEFAULT_HIST_RED_FROM_4 = 8, DEFAULT_HIST_RED_FROM_8 = 4;
 constexpr int SIMPLE_ITEMS_4 = 4, SIMPLE_ITEMS_8 = 4;   // rows per thread per round, warp-centric kernel
 constexpr uint64_t HOST_CHUNK_BYTES = 32ull << 20;   // per column per pipeline stage in dwj_join_host
 constexpr int HOST_STAGES = 4;                       // staging slots of the dwj_join_host pipeline
@@ -215,7 +220,9 @@ template <int W, uint32_t MODE> int hist_red_launch(dwj_engine *e, const dwj::Pa
 // Histogram of a.keys into a.hist (zeroed by the caller).
 template <int W> int hist_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
   if (!a.n) return DWJ_OK;
-  if (a.filter.mask || a.log2_parts > 9) {
+  static const int red_env = getenv("DWJ_HIST_RED_FROM") ? atoi(getenv("DWJ_HIST_RED_FROM")) : -1;   // tuning sweep
+  const int red_from = red_env >= 0 ? red_env : (W == 4 ? DEFAULT_HIST_RED_FROM_4 : DEFAULT_HIST_RED_FROM_8);
+  if (a.filter.mask || a.log2_parts > 9 || (int)a.log2_parts >= red_from) {
     if (a.mode == dwj::PART_BY_BUCKET) return hist_red_launch<W, dwj::PART_BY_BUCKET>(e, a, s);
     if (a.mode == dwj::PART_BY_HASH) return hist_red_launch<W, dwj::PART_BY_HASH>(e, a, s);
     return hist_red_launch<W, dwj::PART_BY_BOTH>(e, a, s);
@@ -225,14 +232,60 @@ template <int W> int hist_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, 
   return hist_launch_mode<W, dwj::PART_BY_BOTH>(e, a, s);
 }
 
+// Shape of the many-way scatter: threads per CTA, rows per thread, CTAs per SM.  The tile (threads x rows) decides the
+// length of the runs a CTA writes per partition (tile / partitions rows) and how far the per-tile overhead -- counter
+// scan, one global reservation per partition -- is amortised; profiles/r2_partition_sweep.txt.  DWJ_SCATTER_SHAPE /
+// DWJ_SCATTER_MATCH pick a shape / the MATCH-instruction ranking at run time for tuning sweeps.
+struct ScatterShape { int threads, items, minb; };
+constexpr ScatterShape SCATTER_SHAPES_4[] = {{256, 16, 3}, {512, 16, 2}, {512, 32, 1}, {1024, 16, 1}, {256, 32, 2}};
+constexpr ScatterShape SCATTER_SHAPES_8[] = {{256, 8, 3}, {512, 8, 2}, {512, 16, 1}, {1024, 8, 1}, {256, 16, 2}};
+constexpr int N_SCATTER_SHAPES = 5, FILTER_SCATTER_SHAPE = 4;   // shape 4: twice the rows per thread -- under a pass filter
+                                                                // only a fraction of a tile's rows is staged and written
+template <int W> constexpr ScatterShape scatter_shape_of(int i) { return W == 4 ? SCATTER_SHAPES_4[i] : SCATTER_SHAPES_8[i]; }
+template <int W> size_t scatter_smem(int shape, uint32_t parts) {
+  const ScatterShape sh = scatter_shape_of<W>(shape);
+  return (size_t)sh.threads * sh.items * (2 * W + 2) + (size_t)parts * (8 + 4 * (sh.threads / 32));
+}
+// Shape for a scatter into 2^bits partitions (bits < 5: always the small tile -- long runs anyway).  Measured
+// (profiles/r2_partition_sweep.txt): the small tile wins everywhere except 512-way with 16-byte rows, where a tile of
+// 2048 rows leaves 32-byte runs (2.25 TB/s; 2.76 with 4096 rows).  MATCH-instruction ranking lost everywhere.
+template <int W> int pick_scatter_shape(uint32_t bits, bool filtered = false) {
+  if (bits < 5) return 0;
+  static const int forced = getenv("DWJ_SCATTER_SHAPE") ? atoi(getenv("DWJ_SCATTER_SHAPE")) : -1;
+  static const int forced_filtered = getenv("DWJ_SCATTER_SHAPE_FILTERED") ? atoi(getenv("DWJ_SCATTER_SHAPE_FILTERED")) : -1;
+  int shape = W == 8 && bits >= 9 ? 1 : 0;
+  if (filtered) shape = forced_filtered >= 0 && forced_filtered < N_SCATTER_SHAPES ? forced_filtered : FILTER_SCATTER_SHAPE;
+  else if (forced >= 0 && forced < N_SCATTER_SHAPES) shape = forced;
+  while (shape > 0 && scatter_smem<W>(shape, 1u << bits) > 227 * 1024) --shape;
+  return shape;
+}
+template <int W> uint64_t scatter_tile_rows(uint32_t bits) {
+  const ScatterShape sh = scatter_shape_of<W>(pick_scatter_shape<W>(bits));
+  return (uint64_t)sh.threads * sh.items;
+}
+
+template <int W, int BITS, int SHAPE, bool MATCH>
+int scatter_many_launch_shape(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
+  constexpr ScatterShape S = scatter_shape_of<W>(SHAPE);
+  constexpr uint64_t TILE = (uint64_t)S.threads * S.items;
+  const uint64_t tiles = a.n_segs ? a.n : (a.n + TILE - 1) / TILE;
+  auto kern = dwj::partition_scatter_many_kernel<W, BITS, S.threads, S.items, S.minb, MATCH>;
+  CU(launch(e, kern, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(S.threads), s, a, false, scatter_smem<W>(SHAPE, 1u << BITS)));
+  return DWJ_OK;
+}
 template <int W, int BITS>
 int scatter_many_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
-  constexpr int THREADS = 256, ITEMS = W == 4 ? 16 : 8, MINB = 3;
-  using SM = dwj::ScatterManySmem<W, THREADS, ITEMS>;
-  const uint64_t tiles = a.n_segs ? a.n : (a.n + SM::TILE - 1) / SM::TILE;
-  auto kern = dwj::partition_scatter_many_kernel<W, BITS, THREADS, ITEMS, MINB>;
-  CU(launch(e, kern, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(THREADS), s, a, false, SM::bytes(1u << BITS)));
-  return DWJ_OK;
+  static const bool match = getenv("DWJ_SCATTER_MATCH") ? atoi(getenv("DWJ_SCATTER_MATCH")) != 0 : DEFAULT_SCATTER_MATCH;
+  if constexpr (BITS >= 5) {
+    switch (pick_scatter_shape<W>(BITS, a.filter.mask != 0)) {
+    case 4: return match ? scatter_many_launch_shape<W, BITS, 4, true>(e, a, s) : scatter_many_launch_shape<W, BITS, 4, false>(e, a, s);
+    case 1: return match ? scatter_many_launch_shape<W, BITS, 1, true>(e, a, s) : scatter_many_launch_shape<W, BITS, 1, false>(e, a, s);
+    case 2: return match ? scatter_many_launch_shape<W, BITS, 2, true>(e, a, s) : scatter_many_launch_shape<W, BITS, 2, false>(e, a, s);
+    case 3: return match ? scatter_many_launch_shape<W, BITS, 3, true>(e, a, s) : scatter_many_launch_shape<W, BITS, 3, false>(e, a, s);
+    default: break;
+    }
+  }
+  return match ? scatter_many_launch_shape<W, BITS, 0, true>(e, a, s) : scatter_many_launch_shape<W, BITS, 0, false>(e, a, s);
 }
 // Scatter a.keys / a.vals to a.out_* at the running positions in a.cursor (1 .. 512 partitions).
 template <int W> int scatter_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, cudaStream_t s) {
@@ -369,7 +422,7 @@ int region_scatter_segments_impl(dwj_engine *e, const uint64_t *h_start_rows, vo
   a.out_vals = (K *)ov;
   a.cursor = e->pull_cursor;
   if (int rc = upload_words(e, a.cursor, h_start_rows, 1u << e->region_bits, s)) return rc;
-  constexpr uint64_t TILE = dwj::ScatterManySmem<W, 256, W == 4 ? 16 : 8>::TILE;
+  const uint64_t TILE = scatter_tile_rows<W>(std::max<uint32_t>(e->region_bits, 1));     // one partition runs the 2-way kernel
   uint64_t tiles = 0;
   uint32_t slot = 0;
   if (int rc = upload_segments(e, TILE, s, &a.segs, &tiles, &slot)) return rc;

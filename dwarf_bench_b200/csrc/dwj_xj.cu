@@ -36,6 +36,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
@@ -181,6 +183,8 @@ struct dwj_xj {
   uint64_t local_build_rows = 0;
   unsigned long long step = 0, slot_use[MAX_SLOTS]{};
   unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;      // DWJ_XJ_TIMEOUT_MS
+  void (*host_barrier)(void *) = nullptr;      // dwj_mg: aligns the rank threads' enqueue order (ranks sharing one process)
+  void *host_barrier_ctx = nullptr;
   dwj_xj_timing last{};
   uint64_t last_remote_bytes = 0;
 };
@@ -208,7 +212,14 @@ int xj_layout(const dwj_engine *e, const dwj_xj_config *cfg, dwj_xj *x) {
   x->W = info.slot_bytes / 2;
   x->regions = info.radix_parts;
   x->fold_regions = dwj_xpart_regions(e, x->world);
-  x->chunk_rows = cfg->chunk_rows ? cfg->chunk_rows : (1ull << 26);
+  // Chunking the probe relation lets the senders partition piece c+1 while the receivers pull piece c -- but every piece
+  // walks all table regions, so a table that does not stay in L2 is read from HBM once PER PIECE.  Small tables: pieces
+  // of 2^26 rows.  Large tables: two pieces across GPUs (one overlap point), one piece on a single GPU (nothing to
+  // overlap with; measured on the 2^31 x 2^31 join: 32 pieces 266 ms per step).
+  const uint64_t probe_rows = std::max<uint64_t>(cfg->max_probe_rows, 1);
+  if (cfg->chunk_rows) x->chunk_rows = cfg->chunk_rows;
+  else if (info.table_bytes <= (512ull << 20)) x->chunk_rows = 1ull << 26;
+  else x->chunk_rows = cfg->world == 1 ? probe_rows : (probe_rows + 1) / 2;
   x->chunks = (uint32_t)std::max<uint64_t>(1, (cfg->max_probe_rows + x->chunk_rows - 1) / x->chunk_rows);
   if (x->chunks > 255) return xfail(DWJ_ERR_INVALID, "%u probe chunks: raise chunk_rows", x->chunks);
   x->ring = std::min<uint32_t>(x->chunks, 3);
@@ -351,6 +362,7 @@ int dwj_xj_create(dwj_engine *e, const dwj_xj_config *cfg, void *const *blocks, 
   auto bail = [&](int rc) { dwj_xj_destroy(x); if (prev >= 0) cudaSetDevice(prev); return rc; };
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = numerically lowest = highest priority
+  if (getenv("DWJ_XJ_NO_PRIORITY") && atoi(getenv("DWJ_XJ_NO_PRIORITY"))) hi = lo;     // A/B switch (development)
   // Scatters go ahead of the local build / probes: everything downstream (on every rank) waits for them.
   if (cudaStreamCreateWithPriority(&x->s_part, cudaStreamNonBlocking, hi) != cudaSuccess ||
       cudaStreamCreateWithPriority(&x->s_pull, cudaStreamNonBlocking, hi) != cudaSuccess ||
@@ -491,17 +503,19 @@ static int xj_pass(dwj_xj *x, uint32_t pass, const void *bk, const void *bv, uin
   const uint32_t fold = x->fold_regions, parts = w * fold;
   std::vector<uint64_t> start(parts);
   std::vector<unsigned long long> use(B);
-  for (uint32_t b = 0; b < B; ++b) {
+  for (uint32_t b = 0; b < B; ++b) use[b] = ++x->slot_use[b == 0 ? 0 : 1 + (b - 1) % x->ring];
+  auto send_batch = [&](uint32_t b) -> int {
     const uint32_t slot = b == 0 ? 0 : 1 + (b - 1) % x->ring;
-    use[b] = ++x->slot_use[slot];
-    const uint64_t base = slot_base_row(x, slot);
-    dwj_xj_plan_send(w, G, fold, base, (const uint64_t *)(x->h_counts + (uint64_t)b * w * G), start.data());
+    dwj_xj_plan_send(w, G, fold, slot_base_row(x, slot), (const uint64_t *)(x->h_counts + (uint64_t)b * w * G), start.data());
     if (use[b] > 1) XRC(wait_all(x, FLAG_DONE + slot * MAX_WORLD, use[b] - 1, x->s_part));    // every reader of the previous filling is done
     XRC(dwj_xpart_scatter(e, batch[b].k, batch[b].v, batch[b].n, w, start.data(), x->keys_base[x->me], x->vals_base[x->me], x->s_part));
     XRC(signal_all(x, FLAG_READY + slot * MAX_WORLD, use[b], x->s_part));
-  }
-  if (timed) XCU(cudaEventRecord(x->ev_t[2], x->s_part));
-  XCU(cudaEventRecord(x->ev_part_end, x->s_part));
+    if (b + 1 == B) {
+      if (timed) XCU(cudaEventRecord(x->ev_t[2], x->s_part));
+      XCU(cudaEventRecord(x->ev_part_end, x->s_part));
+    }
+    return DWJ_OK;
+  };
 
   // ---- 4. receiver: pull --------------------------------------------------------------------------------------------------
   // where rank s keeps its rows for me (and, inside that block, for my region g) in the slot of batch b: dwj_xj_plan_recv
@@ -526,48 +540,44 @@ static int xj_pass(dwj_xj *x, uint32_t pass, const void *bk, const void *bv, uin
     }
     return total;
   };
-  auto direct_segments = [&](uint32_t b) { return plan_recv(b, true); };
-  auto block_segments = [&](uint32_t b) { return plan_recv(b, false); };
-
-  if (pass == 0) XCU(cudaMemsetAsync(d_count, 0, 8, x->s_join));
-  XRC(dwj_set_option(e, DWJ_OPT_APPEND_OUTPUT, 1));
-  // build
-  if (x->direct) {
-    direct_segments(0);
-    XRC(wait_all(x, FLAG_READY, use[0], x->s_join));
-    XRC(dwj_build_segments(e, G * w, sk.data(), sv.data(), sr.data(), w, x->s_join));
-    XRC(signal_all(x, FLAG_DONE, use[0], x->s_join));
-  } else {
-    const uint64_t nb = block_segments(0);
-    XRC(wait_all(x, FLAG_READY, use[0], x->s_pull));
-    XCU(cudaStreamWaitEvent(x->s_pull, x->ev_join_end, 0));        // the previous step's build may still read the landing buffer
-    char *lk = (char *)x->local_build, *lv = lk + x->local_build_rows * W;
-    XRC(dwj_region_scatter_segments(e, w, sk.data(), sv.data(), sr.data(), rstart.data(), lk, lv, x->s_pull));
-    XRC(signal_all(x, FLAG_DONE, use[0], x->s_pull));
-    XCU(cudaEventRecord(x->ev_build_pulled, x->s_pull));
-    // region offsets of the landing buffer for the build's look-ahead (ring of 4 pinned / device arrays)
-    const uint32_t ro = x->region_off_calls++ % 4;
-    if (x->region_off_calls > 4) XCU(cudaEventSynchronize(x->ev_region_off[ro]));
-    unsigned long long *h_ro = x->h_region_off + (uint64_t)ro * (G + 1), *d_ro = x->d_region_off + (uint64_t)ro * (G + 1);
-    for (uint32_t g = 0; g < G; ++g) h_ro[g] = rstart[g];
-    h_ro[G] = nb;
-    xj_stage_kernel<<<1, 256, 0, x->s_join>>>(d_ro, h_ro, G + 1);      // a kernel, not a copy-engine job: see stage_words (dwj_api.cu)
-    XCU(cudaGetLastError());
-    XCU(cudaStreamWaitEvent(x->s_join, x->ev_build_pulled, 0));
-    XRC(dwj_build_grouped(e, lk, lv, nb, G > 1 ? (const uint64_t *)d_ro : nullptr, x->s_join));
-    XCU(cudaEventRecord(x->ev_region_off[ro], x->s_join));
-  }
-  if (timed) XCU(cudaEventRecord(x->ev_t[3], x->s_join));
-  // probe chunks
-  for (uint32_t c = 0; c < x->chunks; ++c) {
+  auto recv_build = [&]() -> int {
+    if (x->direct) {
+      plan_recv(0, true);
+      XRC(wait_all(x, FLAG_READY, use[0], x->s_join));
+      XRC(dwj_build_segments(e, G * w, sk.data(), sv.data(), sr.data(), w, x->s_join));
+      XRC(signal_all(x, FLAG_DONE, use[0], x->s_join));
+    } else {
+      const uint64_t nb = plan_recv(0, false);
+      XRC(wait_all(x, FLAG_READY, use[0], x->s_pull));
+      XCU(cudaStreamWaitEvent(x->s_pull, x->ev_join_end, 0));        // the previous step's build may still read the landing buffer
+      char *lk = (char *)x->local_build, *lv = lk + x->local_build_rows * W;
+      XRC(dwj_region_scatter_segments(e, w, sk.data(), sv.data(), sr.data(), rstart.data(), lk, lv, x->s_pull));
+      XRC(signal_all(x, FLAG_DONE, use[0], x->s_pull));
+      XCU(cudaEventRecord(x->ev_build_pulled, x->s_pull));
+      // region offsets of the landing buffer for the build's look-ahead (ring of 4 pinned / device arrays)
+      const uint32_t ro = x->region_off_calls++ % 4;
+      if (x->region_off_calls > 4) XCU(cudaEventSynchronize(x->ev_region_off[ro]));
+      unsigned long long *h_ro = x->h_region_off + (uint64_t)ro * (G + 1), *d_ro = x->d_region_off + (uint64_t)ro * (G + 1);
+      for (uint32_t g = 0; g < G; ++g) h_ro[g] = rstart[g];
+      h_ro[G] = nb;
+      xj_stage_kernel<<<1, 256, 0, x->s_join>>>(d_ro, h_ro, G + 1);      // a kernel, not a copy-engine job: see stage_words (dwj_api.cu)
+      XCU(cudaGetLastError());
+      XCU(cudaStreamWaitEvent(x->s_join, x->ev_build_pulled, 0));
+      XRC(dwj_build_grouped(e, lk, lv, nb, G > 1 ? (const uint64_t *)d_ro : nullptr, x->s_join));
+      XCU(cudaEventRecord(x->ev_region_off[ro], x->s_join));
+    }
+    if (timed) XCU(cudaEventRecord(x->ev_t[3], x->s_join));
+    return DWJ_OK;
+  };
+  auto recv_chunk = [&](uint32_t c) -> int {
     const uint32_t b = 1 + c, slot = 1 + c % x->ring;
     if (x->direct) {
-      direct_segments(b);
+      plan_recv(b, true);
       XRC(wait_all(x, FLAG_READY + slot * MAX_WORLD, use[b], x->s_join));
       XRC(dwj_probe_pairs_segments(e, G * w, sk.data(), sv.data(), sr.data(), ok, ob, op, capacity, d_count, nullptr, x->s_join));
       XRC(signal_all(x, FLAG_DONE + slot * MAX_WORLD, use[b], x->s_join));
     } else {
-      const uint64_t np_ = block_segments(b);
+      const uint64_t np_ = plan_recv(b, false);
       const uint32_t lb = c & 1;
       char *lk = (char *)x->local_probe[lb], *lv = lk + x->cap_recv_chunk * W;
       XRC(wait_all(x, FLAG_READY + slot * MAX_WORLD, use[b], x->s_pull));
@@ -578,6 +588,31 @@ static int xj_pass(dwj_xj *x, uint32_t pass, const void *bk, const void *bv, uin
       XCU(cudaStreamWaitEvent(x->s_join, x->ev_pulled[lb], 0));
       XRC(dwj_probe_pairs_grouped(e, lk, lv, np_, ok, ob, op, capacity, d_count, nullptr, x->s_join));
       XCU(cudaEventRecord(x->ev_consumed[lb], x->s_join));
+    }
+    return DWJ_OK;
+  };
+
+  // ---- 5. enqueue, in dependency order -------------------------------------------------------------------------------------
+  // A batch that reuses a slot waits (inside a kernel, on the partition stream) until every reader of the slot's previous
+  // filling is done.  This rank's own reader is therefore enqueued BEFORE that wait: hardware work queues are shared
+  // between streams, and work submitted behind a polling kernel may not start until the kernel ends -- measured: with all
+  // sender batches enqueued first, the pulls they waited for sat behind the waits until those timed out.
+  if (pass == 0) XCU(cudaMemsetAsync(d_count, 0, 8, x->s_join));
+  XRC(dwj_set_option(e, DWJ_OPT_APPEND_OUTPUT, 1));
+  // Ranks that share one process (dwj_mg) may even share one GPU (tests): there the same rule must hold ACROSS ranks --
+  // whatever a polling kernel waits for has been submitted before it -- so the rank threads meet at a host barrier
+  // between every send and the receives that poll for it.  Ranks in separate processes own their GPU's queues.
+  auto hb = [&]() { if (x->host_barrier) x->host_barrier(x->host_barrier_ctx); };
+  XRC(send_batch(0));
+  for (uint32_t b = 1; b <= std::min(x->ring, x->chunks); ++b) XRC(send_batch(b));
+  hb();
+  XRC(recv_build());
+  for (uint32_t c = 0; c < x->chunks; ++c) {
+    XRC(recv_chunk(c));
+    if (c + x->ring + 1 < B) {
+      hb();                                                          // every reader of the slot is enqueued ...
+      XRC(send_batch(c + x->ring + 1));                              // ... before the batch that refills it
+      hb();
     }
   }
   XRC(dwj_set_option(e, DWJ_OPT_APPEND_OUTPUT, 0));
@@ -641,7 +676,20 @@ int dwj_xj_sync_timings(dwj_xj *x, dwj_xj_timing *t) {
     r.remote_bytes = x->last_remote_bytes;
     unsigned long long err_word = 0;
     XCU(cudaMemcpy(&err_word, x->ctrl + FLAG_ERR, 8, cudaMemcpyDeviceToHost));
-    if (err_word) return xfail(DWJ_ERR_STATE, "rank %u: timed out waiting for flag %llu of a peer", x->me, err_word - 1);
+    if (err_word) {
+      unsigned long long fl[FLAG_DONE + MAX_SLOTS * MAX_WORLD];
+      XCU(cudaMemcpy(fl, x->ctrl, sizeof(fl), cudaMemcpyDeviceToHost));
+      char buf[400] = "";
+      for (uint32_t sl = 0; sl <= x->ring; ++sl) {
+        const size_t at = strlen(buf);
+        snprintf(buf + at, sizeof(buf) - at, " slot%u use %llu ready[", sl, x->slot_use[sl]);
+        for (uint32_t q = 0; q < x->world; ++q) { const size_t a2 = strlen(buf); snprintf(buf + a2, sizeof(buf) - a2, "%llu ", fl[FLAG_READY + sl * MAX_WORLD + q]); }
+        { const size_t a2 = strlen(buf); snprintf(buf + a2, sizeof(buf) - a2, "] done["); }
+        for (uint32_t q = 0; q < x->world; ++q) { const size_t a2 = strlen(buf); snprintf(buf + a2, sizeof(buf) - a2, "%llu ", fl[FLAG_DONE + sl * MAX_WORLD + q]); }
+        { const size_t a2 = strlen(buf); snprintf(buf + a2, sizeof(buf) - a2, "]"); }
+      }
+      return xfail(DWJ_ERR_STATE, "rank %u: timed out waiting for flag %llu of a peer;%s", x->me, err_word - 1, buf);
+    }
     x->last = r;
     *t = r;
     return DWJ_OK;
@@ -658,7 +706,41 @@ int dwj_xj_sync_timings(dwj_xj *x, dwj_xj_timing *t) {
 // One engine + one dwj_xj per GPU, peer access enabled both ways, blocks from cudaMalloc; dwj_mg_join runs the ranks on
 // one host thread each (every rank blocks once per step on the count exchange, which needs all of them enqueued).
 // ---------------------------------------------------------------------------------------------------------------------------
+namespace {
+// Reusable barrier of the rank threads of dwj_mg_join; abort() releases everybody for good (a rank failed).
+struct HostBarrier {
+  std::mutex mu;
+  std::condition_variable cv;
+  uint32_t n = 1, waiting = 0;
+  uint64_t generation = 0;
+  bool aborted = false;
+  void arrive() {
+    std::unique_lock<std::mutex> lk(mu);
+    if (aborted || n <= 1) return;
+    const uint64_t gen = generation;
+    if (++waiting == n) {
+      waiting = 0;
+      ++generation;
+      cv.notify_all();
+      return;
+    }
+    cv.wait(lk, [&] { return generation != gen || aborted; });
+  }
+  void abort() {
+    std::lock_guard<std::mutex> lk(mu);
+    aborted = true;
+    cv.notify_all();
+  }
+  void reset(uint32_t ranks) {
+    std::lock_guard<std::mutex> lk(mu);
+    n = ranks; waiting = 0; aborted = false;
+  }
+};
+void host_barrier_arrive(void *ctx) { static_cast<HostBarrier *>(ctx)->arrive(); }
+}  // namespace
+
 struct dwj_mg {
+  HostBarrier barrier;
   dwj_mg_config cfg{};
   uint32_t n = 0;
   dwj_engine *eng[MAX_WORLD]{};
@@ -754,6 +836,8 @@ int dwj_mg_create(const dwj_mg_config *cfg, dwj_mg **out) {
   for (uint32_t r = 0; r < m->n; ++r) {
     xc.rank = (int32_t)r;
     if (int rc = dwj_xj_create(m->eng[r], &xc, m->block, &m->xj[r])) return bail(rc);
+    m->xj[r]->host_barrier = host_barrier_arrive;
+    m->xj[r]->host_barrier_ctx = &m->barrier;
   }
   *out = m;
   return DWJ_OK;
@@ -779,15 +863,28 @@ int dwj_mg_join(dwj_mg *m, const void *const *d_build_keys, const void *const *d
     if (!rc && cudaMemcpyAsync(&cnt, m->d_count[r], 8, cudaMemcpyDeviceToHost, m->stream[r]) == cudaSuccess && cudaStreamSynchronize(m->stream[r]) == cudaSuccess)
       n_out[r] = cnt;
     else if (!rc) rc = DWJ_ERR_CUDA;
-    if (rc) snprintf(msgs[r], sizeof(msgs[r]), "%s", dwj_last_error());
+    if (rc) {
+      snprintf(msgs[r], sizeof(msgs[r]), "%s", dwj_last_error());
+      m->barrier.abort();                        // the other ranks must not wait for this one
+    }
     rcs[r] = rc;
   };
+  m->barrier.reset(m->n);
   std::vector<std::thread> th;
   for (uint32_t r = 1; r < m->n; ++r) th.emplace_back(run, r);
   run(0);
   for (auto &t : th) t.join();
-  for (uint32_t r = 0; r < m->n; ++r)
-    if (rcs[r]) return xfail(rcs[r], "GPU %u: %s", r, msgs[r]);
+  {
+    char all[480] = "";
+    int first = 0;
+    for (uint32_t r = 0; r < m->n; ++r)
+      if (rcs[r]) {
+        if (!first) first = rcs[r];
+        const size_t at = strlen(all);
+        snprintf(all + at, sizeof(all) - at, "%sGPU %u: %.150s", at ? "; " : "", r, msgs[r]);
+      }
+    if (first) return xfail(first, "%s", all);
+  }
   for (uint32_t r = 0; r < m->n; ++r)
     if (n_out[r] > capacity[r]) return xfail(DWJ_ERR_OVERFLOW, "GPU %u produced %llu rows, output capacity is %llu", r, (unsigned long long)n_out[r], (unsigned long long)capacity[r]);
   if (timing) {

@@ -180,7 +180,7 @@ template <int W, int THREADS, int ITEMS> struct ScatterManySmem {
   static size_t bytes(uint32_t parts) { return (size_t)TILE * (2 * sizeof(K) + 2) + (size_t)parts * (8 + 4 * WARPS); }
 };
 
-template <int W, int BITS, int THREADS, int ITEMS, bool FULL>
+template <int W, int BITS, int THREADS, int ITEMS, bool FULL, bool MATCH>
 DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, const typename KeyT<W>::type *kp, const typename KeyT<W>::type *vp, uint32_t rows,
                              unsigned char *smem, unsigned int *s_scan) {
   using K = typename KeyT<W>::type;
@@ -219,7 +219,8 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, const typename KeyT<W>::
     const bool live = FULL || (livemask >> j & 1u);
     const uint32_t p = part_id<W>(a, k[j]);
     const unsigned alive = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, live);
-    const unsigned peers = match_partition<BITS>(p, alive);
+    // lanes of the warp bound for the same partition: one MATCH instruction or one ballot per partition-id bit
+    const unsigned peers = MATCH ? (__match_any_sync(0xffffffffu, p) & alive) : match_partition<BITS>(p, alive);
     uint32_t old = 0;
     if (live && (peers & lt) == 0) {                // lowest lane of the group: plain RMW on the warp's own counter
       old = mywc[p];
@@ -297,7 +298,7 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, const typename KeyT<W>::
   }
 }
 
-template <int W, int BITS, int THREADS, int ITEMS, int MINB>
+template <int W, int BITS, int THREADS, int ITEMS, int MINB, bool MATCH>
 __global__ void __launch_bounds__(THREADS, MINB) partition_scatter_many_kernel(PartitionArgs<W> a) {
   constexpr uint32_t TILE = THREADS * ITEMS;
   using K = typename KeyT<W>::type;
@@ -315,8 +316,8 @@ __global__ void __launch_bounds__(THREADS, MINB) partition_scatter_many_kernel(P
       limit = sg.rows;
     }
     const uint32_t rows = (uint32_t)min((uint64_t)TILE, limit - base);
-    if (rows == TILE && !a.filter.mask) scatter_many_tile<W, BITS, THREADS, ITEMS, true>(a, kp + base, vp + base, rows, s_dyn, s_scan);
-    else scatter_many_tile<W, BITS, THREADS, ITEMS, false>(a, kp + base, vp + base, rows, s_dyn, s_scan);
+    if (rows == TILE && !a.filter.mask) scatter_many_tile<W, BITS, THREADS, ITEMS, true, MATCH>(a, kp + base, vp + base, rows, s_dyn, s_scan);
+    else scatter_many_tile<W, BITS, THREADS, ITEMS, false, MATCH>(a, kp + base, vp + base, rows, s_dyn, s_scan);
     __syncthreads();                                // shared memory is reused by the next tile
   }
 }

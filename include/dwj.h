@@ -281,8 +281,9 @@ typedef struct {
   int32_t rank, world;        /* world: 1, 2, 4 or 8                                                             */
   uint64_t max_build_rows;    /* most rows of the build relation THIS rank passes to one dwj_xj_join (same value   */
   uint64_t max_probe_rows;    /*   on every rank); sizes the send slots                                           */
-  uint64_t chunk_rows;        /* the probe relation travels in pieces of this many rows (0 = 2^26): the sender
-                                 partitions piece c+1 while the receivers pull piece c                           */
+  uint64_t chunk_rows;        /* the probe relation travels in pieces of this many rows: the sender partitions piece
+                                 c+1 while the receivers pull piece c.  0 = 2^26 for tables up to 512 MB; for larger
+                                 tables (re-read from HBM once per piece) two pieces, one piece when world == 1   */
   uint32_t passes;            /* power of two; > 1: the join runs once per key class (DWJ_OPT_PASS_FILTER) with the
                                  table, slots and landing buffers sized for one class -- for working sets larger than
                                  the GPUs' memory.  0 = 1                                                        */

@@ -52,7 +52,7 @@ def main():
         per_b, per_p = -(-n_build // world), -(-n_probe // world)
         o = pyoracle.Oracle()
         res = {"steps": []}
-        with dwj.MultiGpuJoin([0] * world, key_bytes, per_b, per_p, chunk_rows=9_000, passes=passes,
+        with dwj.MultiGpuJoin([0] * world, key_bytes, per_b, per_p, chunk_rows=int(os.environ.get('DWJ_TEST_CHUNK_ROWS', 9_000)), passes=passes,
                               force_scatter_pull=(pull == "scatter"), recv_slack=1.5) as mg:
             info = mg.describe(0)
             res["info"] = info
