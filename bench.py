@@ -536,17 +536,18 @@ def exchange_run(args, wname, steps, warmup, device, local_rank, world, rank, wa
         wall_ms = (time.perf_counter() - t_wall) * 1e3
     total_ms = ev[0][0].elapsed_time(ev[-1][1])
     tl = xj.timings()                        # device timeline of the last timed step on this rank
-    per_rank = [total_ms, tl["counts_ms"], tl["scattered_ms"], tl["built_ms"], tl["total_ms"], float(tl["remote_bytes"])]
+    per_rank = [total_ms, tl["counts_ms"], tl["scattered_ms"], tl["built_ms"], tl["total_ms"], float(tl["remote_bytes"]),
+                tl["build_pulled_ms"], tl["last_pulled_ms"]]
     if world > 1:
         t = torch.tensor(per_rank, device=device, dtype=torch.float64)
         allt = torch.empty(world * len(per_rank), device=device, dtype=torch.float64)
         dist.all_gather_into_tensor(allt, t)
         allt = allt.cpu().view(world, len(per_rank))
         total_ms = float(allt[:, 0].max())
-        tl_max = [float(allt[:, i].max()) for i in range(1, 5)]
+        tl_max = [float(allt[:, i].max()) for i in range(1, 5)] + [float(allt[:, 6].max()), float(allt[:, 7].max())]
         remote = float(allt[:, 5].max())
     else:
-        tl_max, remote = per_rank[1:5], per_rank[5]
+        tl_max, remote = per_rank[1:5] + per_rank[6:8], per_rank[5]
     ms_per_step = total_ms / steps
     tuples = (n_build + n_probe) * world
     launches = xinfo["passes"] * (2 * (1 + xinfo["chunks"]) + 2            # histograms (+ memsets), publish, count wait
@@ -566,8 +567,10 @@ def exchange_run(args, wname, steps, warmup, device, local_rank, world, rank, wa
                                     f"building a table for one class; all {tuples} input rows are joined and all result rows are resident at the end")
                    if world == 1 and xinfo["passes"] > 1 else None,
                    "probe_chunks": xinfo["chunks"], "chunk_rows": xinfo["chunk_rows"], "send_slots_in_rotation": xinfo["ring"],
-                   "receive_path": "build / probe kernels pull their rows from the senders' slots (one segment per table region and source)"
-                   if xinfo["direct_pull"] else "the receiver's region-scatter kernel pulls from the senders' slots, build / probe run on its output",
+                   "transfer": ("a copy kernel pulls every source's rows out of its slot over NVLink (blocks dealt round-robin over the "
+                                "sources), " if xinfo["copy_pull"] else "the consuming kernels read the senders' slots themselves, ")
+                               + ("build / probe walk them per (table region, source) segment" if xinfo["direct_pull"] else
+                                  "a region scatter groups them by table region for build / probe"),
                    "exchange_block_bytes_per_gpu": xinfo["block_bytes"], "landing_bytes_per_gpu": xinfo["landing_bytes"],
                    "l2_between_iterations": "inputs and outputs (%.1f GB per GPU per step) far exceed the 126 MB L2; no explicit flush"
                                             % ((n_build + n_probe) * 2 * key_bytes * 2 / 1e9),
@@ -575,7 +578,8 @@ def exchange_run(args, wname, steps, warmup, device, local_rank, world, rank, wa
                                   "peer-mapped slots, flags + counts in peer memory, receiver-side pull over NVLink, no collective on the data path"},
         "gpu_launches": launches * steps, "clocks": clocks.summary(), "wall_ms_per_step": wall_ms / steps, "parity": parity,
         "timeline_ms_last_step_max_over_ranks": {"counts_exchanged": tl_max[0], "last_batch_scattered": tl_max[1], "table_built": tl_max[2],
-                                                 "last_probe_done": tl_max[3], "note": "from the step's start, first pass for the inner marks"},
+                                                 "last_probe_done": tl_max[3], "build_rows_pulled": tl_max[4], "last_chunk_pulled": tl_max[5],
+                                                 "note": "from the step's start, first pass for the inner marks; the pulled marks are 0 on one GPU"},
     }
     if world > 1:
         window_ms = max(tl_max[3] - tl_max[0], 1e-6)

@@ -27,7 +27,7 @@ SYMBOLS = ("dwj_abi_version", "dwj_last_error", "dwj_create", "dwj_destroy", "dw
            "dwj_join_host", "dwj_partition", "dwj_partition_hist", "dwj_partition_of",
            "dwj_xpart_regions", "dwj_xpart_hist", "dwj_xpart_hist2", "dwj_xpart_scatter", "dwj_build_grouped",
            "dwj_probe_pairs_grouped", "dwj_build_segments", "dwj_probe_pairs_segments", "dwj_region_scatter_segments",
-           "dwj_set_option", "dwj_xj_block_bytes", "dwj_xj_create", "dwj_xj_destroy", "dwj_xj_describe", "dwj_xj_join",
+           "dwj_set_option", "dwj_clear_table", "dwj_xj_block_bytes", "dwj_xj_create", "dwj_xj_destroy", "dwj_xj_describe", "dwj_xj_join",
            "dwj_xj_sync_timings", "dwj_xj_plan_send", "dwj_xj_plan_recv", "dwj_region_of", "dwj_mg_create", "dwj_mg_destroy", "dwj_mg_describe", "dwj_mg_join", "dwj_mg_join_host")
 ABI_VERSION = 2
 OPT_APPEND_OUTPUT, OPT_PASS_FILTER = 1, 2
@@ -64,13 +64,13 @@ class XjConfig(C.Structure):
 
 class XjInfo(C.Structure):
     _fields_ = [("regions", C.c_uint32), ("fold_regions", C.c_uint32), ("chunks", C.c_uint32), ("ring", C.c_uint32),
-                ("passes", C.c_uint32), ("direct_pull", C.c_uint32), ("chunk_rows", C.c_uint64), ("block_bytes", C.c_uint64),
+                ("passes", C.c_uint32), ("direct_pull", C.c_uint32), ("copy_pull", C.c_uint32), ("chunk_rows", C.c_uint64), ("block_bytes", C.c_uint64),
                 ("landing_bytes", C.c_uint64)]
 
 
 class XjTiming(C.Structure):
     _fields_ = [("counts_ms", C.c_float), ("scattered_ms", C.c_float), ("built_ms", C.c_float), ("total_ms", C.c_float),
-                ("remote_bytes", C.c_uint64)]
+                ("build_pulled_ms", C.c_float), ("last_pulled_ms", C.c_float), ("remote_bytes", C.c_uint64)]
 
 
 class MgConfig(C.Structure):
@@ -144,6 +144,7 @@ def load_library():
     lib.dwj_probe_pairs_segments.argtypes = [vp, u32, vpp, vpp, u64p, vp, vp, vp, u64, vp, u64p, vp]
     lib.dwj_region_scatter_segments.argtypes = [vp, u32, vpp, vpp, u64p, u64p, vp, vp, vp]
     lib.dwj_set_option.argtypes = [vp, C.c_int, u64]
+    lib.dwj_clear_table.argtypes = [vp, vp]
     lib.dwj_xj_block_bytes.argtypes = [vp, C.POINTER(XjConfig), u64p]
     lib.dwj_xj_create.argtypes = [vp, C.POINTER(XjConfig), vpp, C.POINTER(vp)]
     lib.dwj_xj_destroy.argtypes = [vp]
@@ -151,7 +152,7 @@ def load_library():
     lib.dwj_xj_join.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp, vp, vp, u64, vp, vp]
     lib.dwj_xj_sync_timings.argtypes = [vp, C.POINTER(XjTiming)]
     lib.dwj_xj_plan_send.argtypes = [u32, u32, u32, u64, u64p, u64p]
-    lib.dwj_xj_plan_recv.argtypes = [u32, u32, u32, u64, u64p, u64p, C.c_int, u64p, u64p, u64p, u64p]
+    lib.dwj_xj_plan_recv.argtypes = [u32, u32, u32, u64, u64p, u64p, C.c_int, u32, u64p, u64p, C.POINTER(u32), u64p, u64p, C.POINTER(u32)]
     lib.dwj_region_of.argtypes = [u64, C.c_int32, u64, u32, u64]
     lib.dwj_region_of.restype = u32
     lib.dwj_mg_create.argtypes = [C.POINTER(MgConfig), C.POINTER(vp)]
@@ -335,6 +336,9 @@ class Engine:
 
     def xpart_hist2(self, d_keys, n_rows: int, n_ranks: int, d_counts, stream=None) -> None:
         self._check(self.lib.dwj_xpart_hist2(self._h, _ptr(d_keys), n_rows, n_ranks, _ptr(d_counts), _stream(stream)))
+
+    def clear_table(self, stream=None) -> None:
+        self._check(self.lib.dwj_clear_table(self._h, _stream(stream)))
 
     def set_option(self, option: int, value: int) -> None:
         self._check(self.lib.dwj_set_option(self._h, option, value))

@@ -103,6 +103,8 @@ struct dwj_engine {
   uint32_t pin_calls = 0;
   dwj::PassFilter filter{};                    // DWJ_OPT_PASS_FILTER
   bool append_output = false;                  // DWJ_OPT_APPEND_OUTPUT
+  bool pre_cleared = false;                    // dwj_clear_table ran: the next build skips its own clear
+  cudaEvent_t ev_cleared = nullptr;
   unsigned long long *xpart_cursor = nullptr;  // PART_MAX cursors of dwj_xpart_scatter (own scratch: may run beside a local join)
   unsigned long long *pull_cursor = nullptr;   // PART_MAX cursors of dwj_region_scatter_segments: its own scratch, so the
                                                // receiving scatter on one stream can overlap a sending one on another
@@ -450,10 +452,14 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
     vals = pv;
     e->launches_build += 4;
   }
-  CU(cudaMemsetAsync(e->table, 0xFF, e->table_bytes, s));
-  e->launches_build++;
+  if (e->pre_cleared) {                 // dwj_clear_table did both clears, possibly on another stream
+    CU(cudaStreamWaitEvent(s, e->ev_cleared, 0));
+  } else {
+    CU(cudaMemsetAsync(e->table, 0xFF, e->table_bytes, s));
+    e->launches_build++;
+  }
   if (n) {
-    CU(cudaMemsetAsync(e->fill, 0, e->buckets * sizeof(unsigned int), s));
+    if (!e->pre_cleared) CU(cudaMemsetAsync(e->fill, 0, e->buckets * sizeof(unsigned int), s));
     dwj::BuildArgs<W> a{};
     a.keys = (const K *)keys;
     a.vals = (const K *)vals;
@@ -489,6 +495,7 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
     if (e->pending_segs) CU(cudaEventRecord(e->seg_done[seg_slot], s));
     e->launches_build += 2;
   }
+  e->pre_cleared = false;
   CU(cudaEventRecord(e->ev_build[1], s));
   e->have_build = true;
   e->build_rows = n;
@@ -783,6 +790,7 @@ int dwj_destroy(dwj_engine *e) {
   cudaFree(e->counter);
   cudaFree(e->part_scratch);
   cudaFree(e->pull_cursor);
+  if (e->ev_cleared) cudaEventDestroy(e->ev_cleared);
   cudaFree(e->xpart_cursor);
   cudaFree(e->seg_tables);
   if (e->seg_tables_host) cudaFreeHost(e->seg_tables_host);
@@ -1087,6 +1095,18 @@ int dwj_xpart_hist2(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t
   const uint32_t mode = e->region_bits ? dwj::PART_BY_BOTH : dwj::PART_BY_HASH;
   return e->W == 4 ? partition_hist_impl<4>(e, d_keys, n_rows, bits, mode, rb, d_counts, (cudaStream_t)stream)
                    : partition_hist_impl<8>(e, d_keys, n_rows, bits, mode, rb, d_counts, (cudaStream_t)stream);
+}
+
+int dwj_clear_table(dwj_engine *e, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  DeviceGuard g(e->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!e->ev_cleared) CU(cudaEventCreateWithFlags(&e->ev_cleared, cudaEventDisableTiming));
+  CU(cudaMemsetAsync(e->table, 0xFF, e->table_bytes, s));
+  CU(cudaMemsetAsync(e->fill, 0, e->buckets * sizeof(unsigned int), s));
+  CU(cudaEventRecord(e->ev_cleared, s));
+  e->pre_cleared = true;
+  return DWJ_OK;
 }
 
 int dwj_set_option(dwj_engine *e, int option, uint64_t value) {

@@ -113,6 +113,60 @@ __global__ void xj_wait_kernel(unsigned long long *ctrl, uint32_t world, uint32_
     }
   }
 }
+// ---- the transfer: a copy kernel that keeps every NVLink busy ------------------------------------------------------------
+// Measured (profiles/r2_exchange.md): build / probe / scatter kernels that read their rows straight out of peer memory
+// ("fused pull") move 215-285 GB/s per GPU -- a tile loads, then computes, and while it computes its SM has nothing in
+// flight on a link with ~3 us of latency.  A kernel that does nothing but load and store keeps the SMs' miss queues full:
+// every CTA streams 32 KB blocks (uint4 per lane, 8 deep) and the blocks are dealt ROUND-ROBIN over the runs -- one run
+// per (source rank, column) -- so all peers are read at once and no source's egress is shared by several readers.
+struct CopyRun {
+  const char *src;          // first byte (any 4-byte alignment); the 16-byte aligned body starts `head` bytes in
+  char *dst;
+  unsigned long long bytes;
+  unsigned int head;        // bytes before src becomes 16-byte aligned (< 16, <= bytes)
+  unsigned int blocks;      // 32 KB blocks of the body (the last one partial)
+};
+constexpr int COPY_THREADS = 256, COPY_UNROLL = 8;
+constexpr unsigned long long COPY_BLOCK = (unsigned long long)COPY_THREADS * COPY_UNROLL * 16;
+__device__ __forceinline__ uint4 ld_stream16(const void *p) {
+  uint4 v;
+  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__global__ void __launch_bounds__(COPY_THREADS) xj_copy_runs_kernel(const CopyRun *runs, uint32_t n_runs, uint32_t max_blocks) {
+  const unsigned long long total = (unsigned long long)max_blocks * n_runs;
+  for (unsigned long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const CopyRun r = runs[t % n_runs];
+    const unsigned int lb = (unsigned int)(t / n_runs);
+    if (lb >= r.blocks) continue;
+    if (lb == 0)                                       // the few bytes before the aligned body
+      for (unsigned int i = threadIdx.x * 4; i < r.head; i += COPY_THREADS * 4) *(unsigned int *)(r.dst + i) = *(const unsigned int *)(r.src + i);
+    const unsigned long long off = r.head + (unsigned long long)lb * COPY_BLOCK, len = min(COPY_BLOCK, r.bytes - off);
+    const char *src = r.src + off;
+    char *dst = r.dst + off;
+    const bool dst16 = ((unsigned long long)dst & 15) == 0;
+    if (len == COPY_BLOCK) {
+      uint4 v[COPY_UNROLL];
+#pragma unroll
+      for (int j = 0; j < COPY_UNROLL; ++j) v[j] = ld_stream16(src + ((size_t)j * COPY_THREADS + threadIdx.x) * 16);
+#pragma unroll
+      for (int j = 0; j < COPY_UNROLL; ++j) {
+        char *d = dst + ((size_t)j * COPY_THREADS + threadIdx.x) * 16;
+        if (dst16) *(uint4 *)d = v[j];
+        else { unsigned int *q = (unsigned int *)d; q[0] = v[j].x; q[1] = v[j].y; q[2] = v[j].z; q[3] = v[j].w; }
+      }
+    } else {
+      const unsigned long long vec = len / 16;
+      for (unsigned long long i = threadIdx.x; i < vec; i += COPY_THREADS) {
+        const uint4 v = ld_stream16(src + i * 16);
+        unsigned int *q = (unsigned int *)(dst + i * 16);
+        q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+      }
+      for (unsigned long long i = vec * 16 + threadIdx.x * 4; i < len; i += COPY_THREADS * 4) *(unsigned int *)(dst + i) = *(const unsigned int *)(src + i);
+    }
+  }
+}
+
 __global__ void xj_stage_kernel(unsigned long long *dst, const unsigned long long *pinned_src, uint32_t words) {
   for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = pinned_src[i];
 }
@@ -174,13 +228,23 @@ struct dwj_xj {
   unsigned long long *ctrl = nullptr;        // = peers.ctrl[me]
   cudaStream_t s_part = nullptr, s_join = nullptr, s_pull = nullptr;
   cudaEvent_t ev_in = nullptr, ev_part_end = nullptr, ev_join_end = nullptr, ev_pulled[2]{}, ev_consumed[2]{}, ev_build_pulled = nullptr;
-  cudaEvent_t ev_t[6]{};                     // timeline of the last step: start, counts, scattered, built, done (+ spare)
+  cudaEvent_t ev_t[7]{};                     // timeline of the last step: start, counts, scattered, built, done, build pulled, last chunk pulled
   unsigned long long *d_counts = nullptr, *h_counts = nullptr, *h_gather = nullptr;
   unsigned long long *d_region_off = nullptr, *h_region_off = nullptr;   // ring of 4
   uint32_t region_off_calls = 0;
   cudaEvent_t ev_region_off[4]{};
-  void *local_build = nullptr, *local_probe[2] = {nullptr, nullptr};     // scatter-pull mode: region-grouped landing buffers
+  void *local_build = nullptr, *local_probe[2] = {nullptr, nullptr};     // fused scatter pull: region-grouped landing buffers
   uint64_t local_build_rows = 0;
+  // copy pull (world > 1): the rows of a batch are first copied out of the senders' slots by xj_copy_runs_kernel.
+  //   direct : arena_a = [build landing | probe landing 0 | probe landing 1], consumed in place through segment lists
+  //   scatter: arena_a holds the raw rows (build, then the two probe halves), arena_b their region-grouped form
+  bool copy_pull = false;
+  void *arena_a = nullptr, *arena_b = nullptr;
+  uint64_t arena_rows = 0, cap_build = 0;
+  CopyRun *d_runs = nullptr, *h_runs = nullptr;   // ring of RUN_SLOTS x 2 * MAX_WORLD
+  uint32_t run_calls = 0;
+  cudaEvent_t ev_runs[32]{}, ev_scat_b = nullptr, ev_scat[2]{};
+  int sm_count = 148;
   unsigned long long step = 0, slot_use[MAX_SLOTS]{};
   unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;      // DWJ_XJ_TIMEOUT_MS
   void (*host_barrier)(void *) = nullptr;      // dwj_mg: aligns the rank threads' enqueue order (ranks sharing one process)
@@ -269,28 +333,53 @@ int dwj_xj_plan_send(uint32_t world, uint32_t regions, uint32_t fold_regions, ui
   return DWJ_OK;
 }
 // Receiver `me`: tot[src][dst] = rows src sends to dst (so src's block for me starts sum(tot[src][0..me)) rows into its
-// slot), reg[src][region] = of those for me, the rows of my table region.  direct != 0: one segment per (region, source)
-// in walking order -- region-major, source-minor -- each pointing at its run inside the source's slot.  direct == 0: one
-// segment per source (its whole block for me) and region_start[g] = first row of region g in the landing buffer the
-// pulling scatter fills.  *total = rows this rank receives.
+// slot), reg[src][region] = of those for me, the rows of my table region.  Every list visits the sources in ROTATED order
+// me, me+1, ... (mod world): if all ranks started with source 0, eight readers would share one GPU's NVLink egress while
+// seven links idle (measured: 215 GB/s per GPU instead of ~700).
+//   direct != 0: one segment per (region, source) in walking order -- region-major, rotated source-minor.
+//   direct == 0: every source's block for me is cut into up to `pieces` pieces (of at least 2^16 rows) and the pieces are
+//                dealt round-robin over the sources, so the pulling scatter reads from all peers at once;
+//                region_start[g] = first row of region g in the landing buffer it fills.
+// seg_src[i] = source rank of segment i; *n_segments = segments written (at most max(regions, pieces) * world);
+// *total = rows this rank receives.
 int dwj_xj_plan_recv(uint32_t world, uint32_t me, uint32_t regions, uint64_t slot_base_row, const uint64_t *tot, const uint64_t *reg, int direct,
-                     uint64_t *seg_first_row, uint64_t *seg_rows, uint64_t *region_start, uint64_t *total) {
-  if (!tot || !reg || !seg_first_row || !seg_rows || !total || !world || !regions || me >= world) return xfail(DWJ_ERR_INVALID, "bad plan argument");
+                     uint32_t pieces, uint64_t *seg_first_row, uint64_t *seg_rows, uint32_t *seg_src, uint64_t *region_start, uint64_t *total,
+                     uint32_t *n_segments) {
+  if (!tot || !reg || !seg_first_row || !seg_rows || !seg_src || !total || !n_segments || !world || !regions || me >= world)
+    return xfail(DWJ_ERR_INVALID, "bad plan argument");
   uint64_t sum = 0;
+  uint32_t n = 0;
+  std::vector<uint64_t> block(world);                       // first row of src's block for me inside src's slot
   for (uint32_t s = 0; s < world; ++s) {
     uint64_t r = slot_base_row;
     for (uint32_t d = 0; d < me; ++d) r += tot[(size_t)s * world + d];
-    if (direct) {
-      for (uint32_t g = 0; g < regions; ++g) {
-        seg_first_row[(size_t)g * world + s] = r;
-        seg_rows[(size_t)g * world + s] = reg[(size_t)s * regions + g];
-        r += reg[(size_t)s * regions + g];
-      }
-    } else {
-      seg_first_row[s] = r;
-      seg_rows[s] = tot[(size_t)s * world + me];
-    }
+    block[s] = r;
     sum += tot[(size_t)s * world + me];
+  }
+  if (direct) {
+    std::vector<uint64_t> at(block);
+    for (uint32_t g = 0; g < regions; ++g)
+      for (uint32_t i = 0; i < world; ++i) {
+        const uint32_t s = (me + i) % world;
+        seg_first_row[n] = at[s];
+        seg_rows[n] = reg[(size_t)s * regions + g];
+        seg_src[n] = s;
+        at[s] += reg[(size_t)s * regions + g];
+        ++n;
+      }
+  } else {
+    uint64_t most = 0;
+    for (uint32_t s = 0; s < world; ++s) most = std::max<uint64_t>(most, tot[(size_t)s * world + me]);
+    const uint32_t k = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(pieces ? pieces : 1, most >> 16));
+    for (uint32_t p = 0; p < k; ++p)
+      for (uint32_t i = 0; i < world; ++i) {
+        const uint32_t s = (me + i) % world;
+        const uint64_t rows = tot[(size_t)s * world + me], lo = rows * p / k, hi = rows * (p + 1) / k;
+        seg_first_row[n] = block[s] + lo;
+        seg_rows[n] = hi - lo;
+        seg_src[n] = s;
+        ++n;
+      }
   }
   if (region_start) {
     uint64_t run = 0;
@@ -300,6 +389,7 @@ int dwj_xj_plan_recv(uint32_t world, uint32_t me, uint32_t regions, uint64_t slo
     }
   }
   *total = sum;
+  *n_segments = n;
   return DWJ_OK;
 }
 
@@ -327,6 +417,12 @@ int dwj_xj_destroy(dwj_xj *x) {
   cudaFree(x->local_build);
   cudaFree(x->local_probe[0]);
   cudaFree(x->local_probe[1]);
+  cudaFree(x->arena_a);
+  cudaFree(x->arena_b);
+  cudaFree(x->d_runs);
+  if (x->h_runs) cudaFreeHost(x->h_runs);
+  for (auto ev : x->ev_runs) if (ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : {x->ev_scat_b, x->ev_scat[0], x->ev_scat[1]}) if (ev) cudaEventDestroy(ev);
   if (x->h_counts) cudaFreeHost(x->h_counts);
   if (x->h_gather) cudaFreeHost(x->h_gather);
   if (x->h_region_off) cudaFreeHost(x->h_region_off);
@@ -362,8 +458,11 @@ int dwj_xj_create(dwj_engine *e, const dwj_xj_config *cfg, void *const *blocks, 
   auto bail = [&](int rc) { dwj_xj_destroy(x); if (prev >= 0) cudaSetDevice(prev); return rc; };
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = numerically lowest = highest priority
-  if (getenv("DWJ_XJ_NO_PRIORITY") && atoi(getenv("DWJ_XJ_NO_PRIORITY"))) hi = lo;     // A/B switch (development)
-  // Scatters go ahead of the local build / probes: everything downstream (on every rank) waits for them.
+  // One priority for all three streams.  Measured on 8 GPUs (profiles/r2_exchange.md): with the partition stream above
+  // the join stream, the local build -- a few hundred microseconds of work at BASELINE config 2 -- did not start before
+  // the LAST probe chunk had been partitioned (table built at 4.0 ms of a 7.6 ms step), and at config 5 the build kernel,
+  // which is the critical path, ran at half speed beside the chunk traffic.  DWJ_XJ_PRIORITY=1 restores the old order.
+  if (!(getenv("DWJ_XJ_PRIORITY") && atoi(getenv("DWJ_XJ_PRIORITY")))) hi = lo;
   if (cudaStreamCreateWithPriority(&x->s_part, cudaStreamNonBlocking, hi) != cudaSuccess ||
       cudaStreamCreateWithPriority(&x->s_pull, cudaStreamNonBlocking, hi) != cudaSuccess ||
       cudaStreamCreateWithPriority(&x->s_join, cudaStreamNonBlocking, lo) != cudaSuccess)
@@ -381,7 +480,24 @@ int dwj_xj_create(dwj_engine *e, const dwj_xj_config *cfg, void *const *blocks, 
       cudaHostAlloc((void **)&x->h_gather, (x->world * x->src_stride_words + 8) * 8, cudaHostAllocDefault) != cudaSuccess ||
       cudaHostAlloc((void **)&x->h_region_off, 4 * (uint64_t)(x->regions + 1) * 8, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
     return bail(xfail(DWJ_ERR_OOM, "scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
-  if (!x->direct) {
+  x->copy_pull = x->world > 1 && !(getenv("DWJ_XJ_FUSED_PULL") && atoi(getenv("DWJ_XJ_FUSED_PULL")));
+  cudaDeviceGetAttribute(&x->sm_count, cudaDevAttrMultiProcessorCount, x->device);
+  if (x->copy_pull) {
+    const double slack = cfg->recv_slack > 0 ? cfg->recv_slack : 1.25;
+    x->cap_build = std::max<uint64_t>(x->info.max_build_rows, 64);
+    x->cap_recv_chunk = round_up((uint64_t)((double)x->slot_rows[1] * slack) + 4096, 64);
+    x->arena_rows = x->direct ? x->cap_build + 2 * x->cap_recv_chunk : std::max(x->cap_build, 2 * x->cap_recv_chunk);
+    constexpr uint32_t RUN_SLOTS = 32;
+    if (cudaMalloc(&x->arena_a, 2 * x->arena_rows * x->W) != cudaSuccess || (!x->direct && cudaMalloc(&x->arena_b, 2 * x->arena_rows * x->W) != cudaSuccess) ||
+        cudaMalloc((void **)&x->d_runs, RUN_SLOTS * 2 * MAX_WORLD * sizeof(CopyRun)) != cudaSuccess ||
+        cudaHostAlloc((void **)&x->h_runs, RUN_SLOTS * 2 * MAX_WORLD * sizeof(CopyRun), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
+      return bail(xfail(DWJ_ERR_OOM, "landing buffers (%llu rows x %d): %s", (unsigned long long)x->arena_rows, x->direct ? 1 : 2,
+                        cudaGetErrorString(cudaGetLastError())));
+    for (auto &ev : x->ev_runs)
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail(xfail(DWJ_ERR_CUDA, "cudaEventCreate failed"));
+    for (cudaEvent_t *ev : {&x->ev_scat_b, &x->ev_scat[0], &x->ev_scat[1]})
+      if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return bail(xfail(DWJ_ERR_CUDA, "cudaEventCreate failed"));
+  } else if (!x->direct) {
     // Landing buffers of the pulling scatter: what this rank can receive (table capacity; a probe chunk from every
     // source with head-room -- the plan checks the real counts).
     const double slack = cfg->recv_slack > 0 ? cfg->recv_slack : 1.25;
@@ -423,7 +539,9 @@ int dwj_xj_describe(const dwj_xj *x, dwj_xj_info *info) {
   info->direct_pull = x->direct ? 1u : 0u;
   info->chunk_rows = x->chunk_rows;
   info->block_bytes = x->ctrl_bytes + 2 * round_up(x->rows_total * x->W, 4096);
-  info->landing_bytes = x->direct ? 0 : 2 * (x->local_build_rows + 2 * x->cap_recv_chunk) * x->W;
+  info->landing_bytes = x->copy_pull ? 2 * x->arena_rows * x->W * (x->direct ? 1 : 2)
+                                     : x->direct ? 0 : 2 * (x->local_build_rows + 2 * x->cap_recv_chunk) * x->W;
+  info->copy_pull = x->copy_pull ? 1u : 0u;
   return DWJ_OK;
 }
 
@@ -481,7 +599,7 @@ static int xj_pass(dwj_xj *x, uint32_t pass, const void *bk, const void *bv, uin
     if (nb > x->info.max_build_rows && (double)nb > 0.9 * (double)x->info.slots)
       return xfail(DWJ_ERR_CAPACITY, "rank %u would receive %llu build rows, its table was created for %llu", d, (unsigned long long)nb,
                    (unsigned long long)x->info.max_build_rows);
-    if (!x->direct)
+    if (!x->direct || x->copy_pull)
       for (uint32_t b = 1; b < B; ++b) {
         uint64_t np_ = 0;
         for (uint32_t s = 0; s < w; ++s) np_ += tot(s, b, d);
@@ -522,36 +640,177 @@ static int xj_pass(dwj_xj *x, uint32_t pass, const void *bk, const void *bv, uin
   std::vector<const void *> sk, sv;
   std::vector<uint64_t> sr, sfirst, rstart(G), tot_b((size_t)w * w), reg_b((size_t)w * G);
   uint64_t remote_bytes = 0;
+  const uint32_t pieces = std::max<uint32_t>(1, 256 / w);        // scatter pull: pieces per source, dealt round-robin
+  std::vector<uint32_t> ssrc;
+  uint32_t nseg = 0;
   auto plan_recv = [&](uint32_t b, bool direct) {
     for (uint32_t s = 0; s < w; ++s) {
       for (uint32_t d = 0; d < w; ++d) tot_b[(size_t)s * w + d] = tot(s, b, d);
       for (uint32_t g = 0; g < G; ++g) reg_b[(size_t)s * G + g] = reg(s, b, g);
     }
-    const size_t n = direct ? (size_t)G * w : w;
-    sfirst.assign(n, 0); sr.assign(n, 0); sk.assign(n, nullptr); sv.assign(n, nullptr);
+    const size_t cap = (size_t)std::max(G, pieces) * w;
+    sfirst.assign(cap, 0); sr.assign(cap, 0); ssrc.assign(cap, 0); sk.assign(cap, nullptr); sv.assign(cap, nullptr);
     uint64_t total = 0;
-    dwj_xj_plan_recv(w, x->me, G, slot_base_row(x, b == 0 ? 0 : 1 + (b - 1) % x->ring), tot_b.data(), reg_b.data(), direct ? 1 : 0,
-                     sfirst.data(), sr.data(), rstart.data(), &total);
-    for (size_t i = 0; i < n; ++i) {
-      const uint32_t src = (uint32_t)(direct ? i % w : i);
+    dwj_xj_plan_recv(w, x->me, G, slot_base_row(x, b == 0 ? 0 : 1 + (b - 1) % x->ring), tot_b.data(), reg_b.data(), direct ? 1 : 0, pieces,
+                     sfirst.data(), sr.data(), ssrc.data(), rstart.data(), &total, &nseg);
+    for (uint32_t i = 0; i < nseg; ++i) {
+      const uint32_t src = ssrc[i];
       sk[i] = x->keys_base[src] + sfirst[i] * W;
       sv[i] = x->vals_base[src] + sfirst[i] * W;
       if (src != x->me) remote_bytes += 2ull * sr[i] * W;
     }
     return total;
   };
+  // ---- copy pull: rows of batch b, from every source's slot into a local landing area, source-major --------------------
+  std::vector<uint64_t> lrow(w + 1);
+  auto block_row = [&](uint32_t s, uint32_t b) {
+    uint64_t r = slot_base_row(x, b == 0 ? 0 : 1 + (b - 1) % x->ring);
+    for (uint32_t d = 0; d < x->me; ++d) r += tot(s, b, d);
+    return r;
+  };
+  auto copy_batch = [&](uint32_t b, char *lk, char *lv, cudaStream_t st) -> int {
+    constexpr uint32_t RUN_SLOTS = 32, PER = 2 * MAX_WORLD;
+    const uint32_t slot = x->run_calls++ % RUN_SLOTS;
+    if (x->run_calls > RUN_SLOTS) XCU(cudaEventSynchronize(x->ev_runs[slot]));
+    CopyRun *h = x->h_runs + (size_t)slot * PER, *d = x->d_runs + (size_t)slot * PER;
+    lrow[0] = 0;
+    for (uint32_t s = 0; s < w; ++s) lrow[s + 1] = lrow[s] + tot(s, b, x->me);
+    uint32_t n = 0, max_blocks = 0;
+    for (uint32_t i = 0; i < w; ++i) {                        // rotated: at any time every source is read by one reader
+      const uint32_t src = (x->me + i) % w;
+      const uint64_t bytes = tot(src, b, x->me) * W, from = block_row(src, b) * W, to = lrow[src] * W;
+      if (!bytes) continue;
+      for (int col = 0; col < 2; ++col) {
+        CopyRun r{};
+        r.src = (col ? x->vals_base[src] : x->keys_base[src]) + from;
+        r.dst = (col ? lv : lk) + to;
+        r.bytes = bytes;
+        r.head = (unsigned int)std::min<uint64_t>(bytes, (16 - ((uintptr_t)r.src & 15)) & 15);
+        r.blocks = (unsigned int)((bytes - r.head + COPY_BLOCK - 1) / COPY_BLOCK);
+        if (!r.blocks) r.blocks = 1;                          // the head alone
+        max_blocks = std::max(max_blocks, r.blocks);
+        h[n++] = r;
+      }
+      if (src != x->me) remote_bytes += 2 * bytes;
+    }
+    if (n) {
+      static_assert(sizeof(CopyRun) % 8 == 0, "CopyRun is staged word by word");
+      xj_stage_kernel<<<1, 256, 0, st>>>((unsigned long long *)d, (const unsigned long long *)h, n * (uint32_t)(sizeof(CopyRun) / 8));
+      const unsigned long long total = (unsigned long long)max_blocks * n;
+      // two CTAs per SM keep 64 KB per SM in flight -- 9 MB on the chip against the ~3 MB that 770 GB/s x 3.5 us needs --
+      // and leave the SMs' thread slots to the kernels that run beside the transfer
+      static const int per_sm = getenv("DWJ_XJ_COPY_CTAS") ? std::max(1, atoi(getenv("DWJ_XJ_COPY_CTAS"))) : 2;
+      xj_copy_runs_kernel<<<(unsigned)std::min<unsigned long long>(total, (unsigned long long)x->sm_count * per_sm), COPY_THREADS, 0, st>>>(d, n, max_blocks);
+      XCU(cudaGetLastError());
+    }
+    XCU(cudaEventRecord(x->ev_runs[slot], st));
+    return DWJ_OK;
+  };
+  // segments of a landed batch for the direct path: (region, source), all local now
+  auto landed_segments = [&](uint32_t b, char *lk, char *lv) {
+    sk.assign((size_t)G * w, nullptr); sv.assign((size_t)G * w, nullptr); sr.assign((size_t)G * w, 0);
+    for (uint32_t s = 0; s < w; ++s) {
+      uint64_t r = lrow[s];
+      for (uint32_t g = 0; g < G; ++g) {
+        sk[(size_t)g * w + s] = lk + r * W;
+        sv[(size_t)g * w + s] = lv + r * W;
+        sr[(size_t)g * w + s] = reg(s, b, g);
+        r += reg(s, b, g);
+      }
+    }
+    nseg = G * w;
+  };
+  auto region_starts = [&](uint32_t b) {
+    uint64_t run = 0;
+    for (uint32_t g = 0; g < G; ++g) {
+      rstart[g] = run;
+      for (uint32_t s = 0; s < w; ++s) run += reg(s, b, g);
+    }
+    return run;
+  };
+  char *const A_k = (char *)x->arena_a, *const A_v = A_k + x->arena_rows * W;
+  char *const B_k = (char *)x->arena_b, *const B_v = x->arena_b ? B_k + x->arena_rows * W : nullptr;
+  auto copy_recv_build = [&]() -> int {
+    XRC(dwj_clear_table(e, x->s_join));
+    XRC(wait_all(x, FLAG_READY, use[0], x->s_pull));
+    XCU(cudaStreamWaitEvent(x->s_pull, x->ev_join_end, 0));          // the previous pass / step has left the landing areas
+    XRC(copy_batch(0, A_k, A_v, x->s_pull));
+    XRC(signal_all(x, FLAG_DONE, use[0], x->s_pull));
+    XCU(cudaEventRecord(x->ev_build_pulled, x->s_pull));
+    if (timed) XCU(cudaEventRecord(x->ev_t[5], x->s_pull));
+    XCU(cudaStreamWaitEvent(x->s_join, x->ev_build_pulled, 0));
+    if (x->direct) {
+      landed_segments(0, A_k, A_v);
+      XRC(dwj_build_segments(e, nseg, sk.data(), sv.data(), sr.data(), w, x->s_join));
+    } else {
+      const uint64_t nb = region_starts(0);
+      const void *k1[1] = {A_k}, *v1[1] = {A_v};
+      const uint64_t r1[1] = {nb};
+      XRC(dwj_region_scatter_segments(e, 1, k1, v1, r1, rstart.data(), B_k, B_v, x->s_join));
+      XCU(cudaEventRecord(x->ev_scat_b, x->s_join));                 // arena A may take the first probe chunks
+      const uint32_t ro = x->region_off_calls++ % 4;
+      if (x->region_off_calls > 4) XCU(cudaEventSynchronize(x->ev_region_off[ro]));
+      unsigned long long *h_ro = x->h_region_off + (uint64_t)ro * (G + 1), *d_ro = x->d_region_off + (uint64_t)ro * (G + 1);
+      for (uint32_t g = 0; g < G; ++g) h_ro[g] = rstart[g];
+      h_ro[G] = nb;
+      xj_stage_kernel<<<1, 256, 0, x->s_join>>>(d_ro, h_ro, G + 1);
+      XCU(cudaGetLastError());
+      XRC(dwj_build_grouped(e, B_k, B_v, nb, G > 1 ? (const uint64_t *)d_ro : nullptr, x->s_join));
+      XCU(cudaEventRecord(x->ev_region_off[ro], x->s_join));
+    }
+    if (timed) XCU(cudaEventRecord(x->ev_t[3], x->s_join));
+    return DWJ_OK;
+  };
+  auto copy_recv_chunk = [&](uint32_t c) -> int {
+    const uint32_t b = 1 + c, slot = 1 + c % x->ring, h = c & 1;
+    // landing of this chunk: direct -- behind the build landing; scatter -- one half of arena A (raw), grouped into
+    // the same half of arena B
+    const uint64_t row0 = x->direct ? x->cap_build + (uint64_t)h * x->cap_recv_chunk : (uint64_t)h * (x->arena_rows / 2);
+    char *lk = A_k + row0 * W, *lv = A_v + row0 * W;
+    XRC(wait_all(x, FLAG_READY + slot * MAX_WORLD, use[b], x->s_pull));
+    if (x->direct) {
+      if (c >= 2) XCU(cudaStreamWaitEvent(x->s_pull, x->ev_consumed[h], 0));      // the probe that last read this landing
+    } else {
+      if (c < 2) XCU(cudaStreamWaitEvent(x->s_pull, x->ev_scat_b, 0));            // arena A held the raw build rows
+      else XCU(cudaStreamWaitEvent(x->s_pull, x->ev_scat[h], 0));                 // the scatter that last read this half
+    }
+    XRC(copy_batch(b, lk, lv, x->s_pull));
+    XRC(signal_all(x, FLAG_DONE + slot * MAX_WORLD, use[b], x->s_pull));
+    XCU(cudaEventRecord(x->ev_pulled[h], x->s_pull));
+    if (timed && c + 1 == x->chunks) XCU(cudaEventRecord(x->ev_t[6], x->s_pull));
+    XCU(cudaStreamWaitEvent(x->s_join, x->ev_pulled[h], 0));
+    if (x->direct) {
+      landed_segments(b, lk, lv);
+      XRC(dwj_probe_pairs_segments(e, nseg, sk.data(), sv.data(), sr.data(), ok, ob, op, capacity, d_count, nullptr, x->s_join));
+      XCU(cudaEventRecord(x->ev_consumed[h], x->s_join));
+    } else {
+      const uint64_t np_ = region_starts(b);
+      char *gk = B_k + row0 * W, *gv = B_v + row0 * W;                // B is free: the build and the probe of chunk c-2 precede on this stream
+      const void *k1[1] = {lk}, *v1[1] = {lv};
+      const uint64_t r1[1] = {np_};
+      XRC(dwj_region_scatter_segments(e, 1, k1, v1, r1, rstart.data(), gk, gv, x->s_join));
+      XCU(cudaEventRecord(x->ev_scat[h], x->s_join));
+      XRC(dwj_probe_pairs_grouped(e, gk, gv, np_, ok, ob, op, capacity, d_count, nullptr, x->s_join));
+    }
+    return DWJ_OK;
+  };
+
   auto recv_build = [&]() -> int {
+    if (x->copy_pull) return copy_recv_build();
+    // The clear of the table needs nothing from the peers: it runs (on the join stream, behind the previous probes)
+    // while the senders still partition and the first rows are pulled.
+    XRC(dwj_clear_table(e, x->s_join));
     if (x->direct) {
       plan_recv(0, true);
       XRC(wait_all(x, FLAG_READY, use[0], x->s_join));
-      XRC(dwj_build_segments(e, G * w, sk.data(), sv.data(), sr.data(), w, x->s_join));
+      XRC(dwj_build_segments(e, nseg, sk.data(), sv.data(), sr.data(), w, x->s_join));
       XRC(signal_all(x, FLAG_DONE, use[0], x->s_join));
     } else {
       const uint64_t nb = plan_recv(0, false);
       XRC(wait_all(x, FLAG_READY, use[0], x->s_pull));
       XCU(cudaStreamWaitEvent(x->s_pull, x->ev_join_end, 0));        // the previous step's build may still read the landing buffer
       char *lk = (char *)x->local_build, *lv = lk + x->local_build_rows * W;
-      XRC(dwj_region_scatter_segments(e, w, sk.data(), sv.data(), sr.data(), rstart.data(), lk, lv, x->s_pull));
+      XRC(dwj_region_scatter_segments(e, nseg, sk.data(), sv.data(), sr.data(), rstart.data(), lk, lv, x->s_pull));
       XRC(signal_all(x, FLAG_DONE, use[0], x->s_pull));
       XCU(cudaEventRecord(x->ev_build_pulled, x->s_pull));
       // region offsets of the landing buffer for the build's look-ahead (ring of 4 pinned / device arrays)
@@ -570,11 +829,12 @@ static int xj_pass(dwj_xj *x, uint32_t pass, const void *bk, const void *bv, uin
     return DWJ_OK;
   };
   auto recv_chunk = [&](uint32_t c) -> int {
+    if (x->copy_pull) return copy_recv_chunk(c);
     const uint32_t b = 1 + c, slot = 1 + c % x->ring;
     if (x->direct) {
       plan_recv(b, true);
       XRC(wait_all(x, FLAG_READY + slot * MAX_WORLD, use[b], x->s_join));
-      XRC(dwj_probe_pairs_segments(e, G * w, sk.data(), sv.data(), sr.data(), ok, ob, op, capacity, d_count, nullptr, x->s_join));
+      XRC(dwj_probe_pairs_segments(e, nseg, sk.data(), sv.data(), sr.data(), ok, ob, op, capacity, d_count, nullptr, x->s_join));
       XRC(signal_all(x, FLAG_DONE + slot * MAX_WORLD, use[b], x->s_join));
     } else {
       const uint64_t np_ = plan_recv(b, false);
@@ -582,7 +842,7 @@ static int xj_pass(dwj_xj *x, uint32_t pass, const void *bk, const void *bv, uin
       char *lk = (char *)x->local_probe[lb], *lv = lk + x->cap_recv_chunk * W;
       XRC(wait_all(x, FLAG_READY + slot * MAX_WORLD, use[b], x->s_pull));
       if (c >= 2 || step > 1) XCU(cudaStreamWaitEvent(x->s_pull, x->ev_consumed[lb], 0));   // the probe that last read this landing buffer
-      XRC(dwj_region_scatter_segments(e, w, sk.data(), sv.data(), sr.data(), rstart.data(), lk, lv, x->s_pull));
+      XRC(dwj_region_scatter_segments(e, nseg, sk.data(), sv.data(), sr.data(), rstart.data(), lk, lv, x->s_pull));
       XRC(signal_all(x, FLAG_DONE + slot * MAX_WORLD, use[b], x->s_pull));
       XCU(cudaEventRecord(x->ev_pulled[lb], x->s_pull));
       XCU(cudaStreamWaitEvent(x->s_join, x->ev_pulled[lb], 0));
@@ -673,6 +933,10 @@ int dwj_xj_sync_timings(dwj_xj *x, dwj_xj_timing *t) {
     XCU(cudaEventElapsedTime(&r.scattered_ms, x->ev_t[0], x->ev_t[2]));
     XCU(cudaEventElapsedTime(&r.built_ms, x->ev_t[0], x->ev_t[3]));
     XCU(cudaEventElapsedTime(&r.total_ms, x->ev_t[0], x->ev_t[4]));
+    if (x->copy_pull) {
+      XCU(cudaEventElapsedTime(&r.build_pulled_ms, x->ev_t[0], x->ev_t[5]));
+      XCU(cudaEventElapsedTime(&r.last_pulled_ms, x->ev_t[0], x->ev_t[6]));
+    }
     r.remote_bytes = x->last_remote_bytes;
     unsigned long long err_word = 0;
     XCU(cudaMemcpy(&err_word, x->ctrl + FLAG_ERR, 8, cudaMemcpyDeviceToHost));

@@ -248,6 +248,11 @@ DWJ_API int dwj_region_scatter_segments(dwj_engine *e, uint32_t n_segments, cons
  * device), rank-major.  The senders count for the receivers.  n_ranks: 1, 2, 4 or 8.  Asynchronous. */
 DWJ_API int dwj_xpart_hist2(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t n_ranks, uint64_t *d_counts, void *stream);
 
+/* Clears the table on `stream` AHEAD of the next dwj_build* call, which then waits for this clear instead of doing its own:
+ * the clear (a pure HBM write of the whole table) can overlap whatever produces the build rows -- a partition pass, an
+ * exchange -- on another stream.  The table must not be probed between the two calls.  Asynchronous. */
+DWJ_API int dwj_clear_table(dwj_engine *e, void *stream);
+
 /* Engine options (dwj_set_option) */
 #define DWJ_OPT_APPEND_OUTPUT 1 /* value != 0: dwj_probe_pairs* append their rows at the running count in *d_n_matches
                                    (device, required) instead of starting from zero -- several probe calls (chunks of a
@@ -295,7 +300,10 @@ typedef struct {
   uint32_t fold_regions;      /* regions grouped by the SENDER's pass (== regions: the receiver pulls directly)   */
   uint32_t chunks, ring;      /* probe chunks per join; send slots they rotate through                           */
   uint32_t passes;
-  uint32_t direct_pull;       /* 1: build / probe kernels pull from the senders; 0: the receiver's region scatter does */
+  uint32_t direct_pull;       /* 1: build / probe kernels consume the rows per (region, source) segment; 0: a region
+                                 scatter groups them first (ranks x regions > 512, or duplicate build keys)      */
+  uint32_t copy_pull;         /* 1: a copy kernel first moves the rows out of the senders' slots over NVLink (world > 1);
+                                 0: the consuming kernels read the slots themselves (world == 1, DWJ_XJ_FUSED_PULL=1) */
   uint64_t chunk_rows;
   uint64_t block_bytes;       /* = dwj_xj_block_bytes                                                            */
   uint64_t landing_bytes;     /* local buffers of the region-scatter receive path                                */
@@ -305,6 +313,8 @@ typedef struct {              /* device timeline of the last join on this rank, 
   float scattered_ms;         /* last batch grouped into its send slot                                           */
   float built_ms;             /* local table built                                                               */
   float total_ms;             /* last probe chunk done (all passes)                                              */
+  float build_pulled_ms;      /* copy pull: the build relation's rows have landed                                 */
+  float last_pulled_ms;       /* copy pull: the last probe chunk's rows have landed                               */
   uint64_t remote_bytes;      /* bytes this rank pulled over NVLink                                              */
 } dwj_xj_timing;
 DWJ_API int dwj_xj_block_bytes(const dwj_engine *e, const dwj_xj_config *cfg, uint64_t *bytes);
@@ -320,12 +330,16 @@ DWJ_API int dwj_xj_sync_timings(dwj_xj *x, dwj_xj_timing *t);
 /* The layout plan of one batch as pure host functions (what dwj_xj_join computes from the exchanged counts; exported so
  * the logic can be tested without a GPU).  Sender: mine[dst][region] -> start[] = first slot row of every partition of
  * its pass (world * fold_regions entries; destination-major, region-minor).  Receiver `me`: tot[src][dst], reg[src][my
- * region] -> direct != 0: regions * world segments in walking order (region-major, source-minor); direct == 0: one
- * segment per source plus region_start[regions] of the landing buffer.  Rows are relative to the senders' blocks. */
+ * region] -> segment lists that visit the sources in rotated order me, me+1, ... (so the ranks never all read from one
+ * GPU): direct != 0: regions * world segments in walking order (region-major, source-minor); direct == 0: every
+ * source's block cut into up to `pieces` pieces dealt round-robin over the sources, plus region_start[regions] of the
+ * landing buffer.  seg_src[i] = source of segment i; at most max(regions, pieces) * world segments.  Rows are relative
+ * to the senders' blocks. */
 DWJ_API int dwj_xj_plan_send(uint32_t world, uint32_t regions, uint32_t fold_regions, uint64_t slot_base_row, const uint64_t *mine,
                      uint64_t *start);
 DWJ_API int dwj_xj_plan_recv(uint32_t world, uint32_t me, uint32_t regions, uint64_t slot_base_row, const uint64_t *tot, const uint64_t *reg,
-                     int direct, uint64_t *seg_first_row, uint64_t *seg_rows, uint64_t *region_start, uint64_t *total);
+                     int direct, uint32_t pieces, uint64_t *seg_first_row, uint64_t *seg_rows, uint32_t *seg_src,
+                     uint64_t *region_start, uint64_t *total, uint32_t *n_segments);
 /* Table region (0 .. 2^region_bits - 1) a key falls into for a table of `buckets` 32-byte buckets -- host evaluation of
  * the kernels' function, as dwj_partition_of. */
 DWJ_API uint32_t dwj_region_of(uint64_t key, int32_t key_bytes, uint64_t buckets, uint32_t region_bits, uint64_t hash_seed);

@@ -139,15 +139,20 @@ def _sim_exchange(world, regions, fold, direct, n_rows, key_bytes, rng, lib):
     for me in range(world):                                     # receiver: segments into the senders' slots
         tot = np.ascontiguousarray(counts.sum(axis=2))          # [src][dst]
         rg = np.ascontiguousarray(counts[:, me, :])             # [src][region]
-        n = regions * world if direct else world
-        first, rows, rstart, total = (np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64), np.zeros(regions, dtype=np.uint64),
-                                      C.c_uint64(0))
-        assert lib.dwj_xj_plan_recv(world, me, regions, base, tot.ctypes.data_as(u64p), rg.ctypes.data_as(u64p), 1 if direct else 0,
-                                    first.ctypes.data_as(u64p), rows.ctypes.data_as(u64p), rstart.ctypes.data_as(u64p), C.byref(total)) == 0
+        pieces = 4
+        cap = max(regions, pieces) * world
+        first, rows, src, rstart, total, nseg = (np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint32),
+                                                 np.zeros(regions, dtype=np.uint64), C.c_uint64(0), C.c_uint32(0))
+        assert lib.dwj_xj_plan_recv(world, me, regions, base, tot.ctypes.data_as(u64p), rg.ctypes.data_as(u64p), 1 if direct else 0, pieces,
+                                    first.ctypes.data_as(u64p), rows.ctypes.data_as(u64p), src.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                    rstart.ctypes.data_as(u64p), C.byref(total), C.byref(nseg)) == 0
+        n = nseg.value
+        assert n == (regions * world if direct else world * max(1, min(pieces, int(tot[:, me].max()) >> 16)))
         assert total.value == tot[:, me].sum()
         assert (rstart == np.cumsum(rg.sum(axis=0)) - rg.sum(axis=0)).all()
+        assert [int(x) for x in src[:world]] == [(me + i) % world for i in range(world)]      # rotated: no two ranks start at one source
         for i in range(n):
-            s = i % world if direct else i
+            s = int(src[i])
             idx = slots[s][int(first[i]):int(first[i] + rows[i])]
             assert (idx >= 0).all() and not seen[s][idx].any()
             seen[s][idx] = True

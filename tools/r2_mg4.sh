@@ -1,9 +1,8 @@
 #!/bin/bash
-N=${1:-2}
-O=gpurun_out/r2_mg${N}c; mkdir -p $O; rm -f $O/*
+N=${1:-4}
+O=gpurun_out/r2_mg${N}b; mkdir -p $O; rm -f $O/*
 export DWJ_XJ_TIMEOUT_MS=15000
-timeout 400 python -m pytest tests/test_gpu_multi.py -m gpu -q -k two_ranks --timeout 200 > $O/pytest.log 2>&1; echo "rc=$?" >> $O/pytest.log; tail -6 $O/pytest.log | cut -c1-400
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521"
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519"
 run() { tag=$1; shift; ( time timeout 420 $TR bench.py --gpus $N "$@" > $O/$tag.json 2> $O/$tag.err ) 2> $O/$tag.time; echo "== $tag rc=$? $(grep real $O/$tag.time)"; grep -v "OMP_NUM_THREADS\|^\*\*\*\|NCCL version" $O/$tag.err | tail -3 | cut -c1-400; python - "$O/$tag.json" <<'PY'
 import json,sys
 try:
@@ -14,6 +13,5 @@ try:
 except Exception as ex: print('  no json', ex)
 PY
 }
-run cfg5 --steps 5 --warmup 2 --no-e2e
+run cfg5 --steps 8 --warmup 3 --no-e2e
 run cfg2_weak --steps 15 --warmup 4 --no-e2e --workload join_16Mx256M_u32_unique
-DWJ_XJ_FUSED_PULL=1 run cfg2_weak_fused --steps 15 --warmup 4 --no-e2e --workload join_16Mx256M_u32_unique
