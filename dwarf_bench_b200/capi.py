@@ -54,7 +54,7 @@ class Info(C.Structure):
                 ("slots_per_bucket", C.c_uint32), ("l2_persist", C.c_uint32), ("sm_count", C.c_uint32),
                 ("l2_bytes", C.c_uint64), ("launches_build", C.c_uint32), ("launches_probe", C.c_uint32),
                 ("radix_parts", C.c_uint32), ("probe_passes", C.c_uint32), ("flags", C.c_uint32), ("device", C.c_int32),
-                ("hash_seed", C.c_uint64), ("max_build_rows", C.c_uint64)]
+                ("hash_seed", C.c_uint64), ("max_build_rows", C.c_uint64), ("hot_probe_keys", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class XjConfig(C.Structure):

@@ -128,7 +128,7 @@ namespace {
 
 template <class Kern, class Args>
 cudaError_t launch(dwj_engine *e, Kern kern, dim3 grid, dim3 block, cudaStream_t s, Args args, bool table_window, size_t smem = 0) {
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {        // dynamic + the kernel's static shared memory may pass the 48 KB default together
     cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ae != cudaSuccess) return ae;
   }
@@ -241,12 +241,15 @@ template <int W> int hist_launch(dwj_engine *e, const dwj::PartitionArgs<W> &a, 
 struct ScatterShape { int threads, items, minb; };
 constexpr ScatterShape SCATTER_SHAPES_4[] = {{256, 16, 3}, {512, 16, 2}, {512, 32, 1}, {1024, 16, 1}, {256, 32, 2}};
 constexpr ScatterShape SCATTER_SHAPES_8[] = {{256, 8, 3}, {512, 8, 2}, {512, 16, 1}, {1024, 8, 1}, {256, 16, 2}};
-constexpr int N_SCATTER_SHAPES = 5, FILTER_SCATTER_SHAPE = 4;   // shape 4: twice the rows per thread -- under a pass filter
-                                                                // only a fraction of a tile's rows is staged and written
+constexpr int N_SCATTER_SHAPES = 5, FILTER_SCATTER_SHAPE = 0;   // under a pass filter only a fraction of a tile's rows is staged and
+                                                                // written; measured on the 2^31 x 2^31 int64 join, one GPU, 2 passes
+                                                                // (ms per filtered 2^31-row scatter / per step): shape 0 28.7 / 247,
+                                                                // shape 1 25.7 / 256, shape 2 37.6 / 284, shape 4 (twice the rows
+                                                                // per thread) 33.7 / 267
 template <int W> constexpr ScatterShape scatter_shape_of(int i) { return W == 4 ? SCATTER_SHAPES_4[i] : SCATTER_SHAPES_8[i]; }
 template <int W> size_t scatter_smem(int shape, uint32_t parts) {
   const ScatterShape sh = scatter_shape_of<W>(shape);
-  return (size_t)sh.threads * sh.items * (2 * W + 2) + (size_t)parts * (8 + 4 * (sh.threads / 32));
+  return (size_t)sh.threads * sh.items * (2 * W + (W == 4 ? 2 : 0)) + (size_t)parts * (8 + 4 * (sh.threads / 32));
 }
 // Shape for a scatter into 2^bits partitions (bits < 5: always the small tile -- long runs anyway).  Measured
 // (profiles/r2_partition_sweep.txt): the small tile wins everywhere except 512-way with 16-byte rows, where a tile of
@@ -543,7 +546,8 @@ int multi_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
   }
   if (tiles) {
     if (tiles > 0x7fffffffull) return fail(DWJ_ERR_INVALID, "probe of %llu rows needs more than 2^31 tiles", (unsigned long long)a.n);
-    CU(launch(e, dwj::probe_pairs_multi_kernel<W, ORDERED, THREADS, ITEMS, MINB>, dim3((unsigned)tiles), dim3(THREADS), s, a, true));
+    const size_t stage = (size_t)TILE * 4 * W * (a.out_key ? 3 : 2);       // result rows of a tile, staged for contiguous stores
+    CU(launch(e, dwj::probe_pairs_multi_kernel<W, ORDERED, THREADS, ITEMS, MINB>, dim3((unsigned)tiles), dim3(THREADS), s, a, true, stage));
     e->launches_probe++;
   }
   return DWJ_OK;
@@ -574,6 +578,13 @@ int staged_launch_shape(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
   }
   if (chunks) {
     if (chunks > 0x7fffffffull) return fail(DWJ_ERR_INVALID, "probe of %llu rows needs more than 2^31 chunks", (unsigned long long)a.n);
+    unsigned int *hot = (unsigned int *)(e->counter + 4);
+    if (!e->pending_segs && a.n >= 65536) {          // skewed probe keys? (the staged kernel bypasses L1 for table sectors otherwise)
+      dwj::probe_skew_sample_kernel<W><<<1, 1024, 0, s>>>(a.keys, a.n, a.n_dev, a.bucket_mask, a.seed, hot);
+      CU(cudaGetLastError());
+      a.hot_keys = hot;
+      e->launches_probe++;
+    }
     auto kern = dwj::probe_pairs_staged_kernel<W, ORDERED, WITH_KEY, S.warps, S.items, S.sub, S.minb>;
     const size_t smem = CHUNK * W * (WITH_KEY ? 3 : 2);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -775,6 +786,7 @@ int dwj_create(const dwj_config *cfg, dwj_engine **out) {
       cudaGetLastError();
     }
   }
+  cudaMemset(e->counter, 0, 64);
   *out = e;
   return DWJ_OK;
 }
@@ -839,6 +851,14 @@ int dwj_get_info(const dwj_engine *e, dwj_info *info) {
   info->device = e->cfg.device;
   info->hash_seed = e->cfg.hash_seed;
   info->max_build_rows = e->cfg.max_build_rows;
+  info->hot_probe_keys = 0;
+  info->reserved = 0;
+  if (e->have_probe) {                  // verdict of the last staged probe's key sample (synchronises with the device)
+    unsigned int hot = 0;
+    DeviceGuard g(e->cfg.device);
+    if (cudaMemcpy(&hot, (const unsigned int *)(e->counter + 4), sizeof(hot), cudaMemcpyDeviceToHost) == cudaSuccess) info->hot_probe_keys = hot;
+    else cudaGetLastError();
+  }
   return DWJ_OK;
 }
 

@@ -172,12 +172,26 @@ __global__ void __launch_bounds__(THREADS) partition_hist_private_kernel(Partiti
   }
 }
 
+template <int W> struct PairT;
+template <> struct PairT<4> {
+  using type = uint2;
+  static DWJ_D uint2 make(uint32_t k, uint32_t v) { return make_uint2(k, v); }
+  static DWJ_D uint32_t key(uint2 r) { return r.x; }
+  static DWJ_D uint32_t val(uint2 r) { return r.y; }
+};
+template <> struct PairT<8> {
+  using type = ulonglong2;
+  static DWJ_D ulonglong2 make(uint64_t k, uint64_t v) { return make_ulonglong2(k, v); }
+  static DWJ_D uint64_t key(ulonglong2 r) { return r.x; }
+  static DWJ_D uint64_t val(ulonglong2 r) { return r.y; }
+};
+
 template <int W, int THREADS, int ITEMS> struct ScatterManySmem {
   using K = typename KeyT<W>::type;
   static constexpr uint32_t TILE = THREADS * ITEMS;
   static constexpr int WARPS = THREADS / 32;
-  // dynamic shared memory: keys[TILE] | vals[TILE] | delta[parts] (int64) | wc[WARPS][parts] (uint32) | part[TILE] (uint16)
-  static size_t bytes(uint32_t parts) { return (size_t)TILE * (2 * sizeof(K) + 2) + (size_t)parts * (8 + 4 * WARPS); }
+  // dynamic shared memory: rows[TILE] (pairs, or keys | payloads) | delta[parts] (int64) | wc[WARPS][parts] (uint32) | part[TILE] (uint16, 8-byte rows)
+  static size_t bytes(uint32_t parts) { return (size_t)TILE * (2 * sizeof(K) + (W == 4 ? 2 : 0)) + (size_t)parts * (8 + 4 * WARPS); }
 };
 
 template <int W, int BITS, int THREADS, int ITEMS, bool FULL, bool MATCH>
@@ -188,12 +202,20 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, const typename KeyT<W>::
   constexpr int WARPS = THREADS / 32;
   constexpr uint32_t PARTS = 1u << BITS;
   constexpr int PER = (PARTS + THREADS - 1) / THREADS;
+  // 16-byte rows are staged as (key, payload) PAIRS -- one shared-memory store and one load per row instead of two of
+  // each -- and the partition of a staged row is recomputed from its key when the row leaves (a dozen ALU instructions
+  // against a store and a load): that kernel is bound by the shared-memory pipe (r2 ncu: mio + short-scoreboard 42 % of
+  // the stall samples, issue slots 41 % busy; +3..8 %).  8-byte rows keep separate columns and a staged partition id:
+  // their kernel is bound by issue slots, and the re-hash cost 20 % (profiles/r2_partition_sweep.txt).
+  constexpr bool PAIRS = W == 8;
+  using Pair = typename PairT<W>::type;
+  Pair *s_rows = reinterpret_cast<Pair *>(smem);
   K *s_keys = reinterpret_cast<K *>(smem);
   K *s_vals = s_keys + TILE;
-  long long *s_delta = reinterpret_cast<long long *>(s_vals + TILE);
+  long long *s_delta = reinterpret_cast<long long *>(smem + (size_t)TILE * 2 * sizeof(K));
   unsigned int *s_wc = reinterpret_cast<unsigned int *>(s_delta + PARTS);
-  unsigned short *s_part = reinterpret_cast<unsigned short *>(s_wc + WARPS * PARTS);   // partition of every staged row: two
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                     // shared-memory ops instead of a re-hash
+  unsigned short *s_part = reinterpret_cast<unsigned short *>(s_wc + WARPS * PARTS);   // 8-byte rows: partition of every staged row
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const bool with_vals = a.vals != nullptr;
   unsigned int *mywc = s_wc + warp * PARTS;
@@ -280,9 +302,13 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, const typename KeyT<W>::
   for (int j = 0; j < ITEMS; ++j) {
     if (FULL || pr[j] != PART_DEAD) {
       const uint32_t s = mywc[pr[j] >> 16] + (pr[j] & 0xFFFFu);
-      s_keys[s] = k[j];
-      s_vals[s] = v[j];
-      s_part[s] = (unsigned short)(pr[j] >> 16);
+      if constexpr (PAIRS) {
+        s_rows[s] = PairT<W>::make(k[j], v[j]);
+      } else {
+        s_keys[s] = k[j];
+        s_vals[s] = v[j];
+        s_part[s] = (unsigned short)(pr[j] >> 16);
+      }
     }
   }
   __syncthreads();
@@ -291,9 +317,16 @@ DWJ_D void scatter_many_tile(const PartitionArgs<W> &a, const typename KeyT<W>::
   for (int j = 0; j < ITEMS; ++j) {
     const uint32_t s = j * THREADS + threadIdx.x;
     if (FULL || s < staged_rows) {
-      const long long dst = (long long)s + s_delta[s_part[s]];
-      store_stream(a.out_keys + dst, s_keys[s]);
-      if (with_vals) store_stream(a.out_vals + dst, s_vals[s]);
+      if constexpr (PAIRS) {
+        const Pair row = s_rows[s];
+        const long long dst = (long long)s + s_delta[part_id<W>(a, PairT<W>::key(row))];
+        store_stream(a.out_keys + dst, PairT<W>::key(row));
+        if (with_vals) store_stream(a.out_vals + dst, PairT<W>::val(row));
+      } else {
+        const long long dst = (long long)s + s_delta[s_part[s]];
+        store_stream(a.out_keys + dst, s_keys[s]);
+        if (with_vals) store_stream(a.out_vals + dst, s_vals[s]);
+      }
     }
   }
 }

@@ -22,14 +22,14 @@ void Engine::check(int rc) {
   if (rc != DWJ_OK) throw std::runtime_error(std::string("dwj: ") + dwj_last_error());
 }
 
-Engine::Engine(size_t max_build_rows, unsigned flags, int key_bytes) {
+Engine::Engine(size_t max_build_rows, unsigned flags, int key_bytes, double load_factor) {
   dwj_config cfg{};
   cfg.device = 0;
   cfg.key_bytes = key_bytes;
   cfg.payload_bytes = key_bytes;
   cfg.flags = flags;
   cfg.max_build_rows = max_build_rows;
-  cfg.load_factor = 0.5;                       // join/join.cpp:30: ht_size = buf_size * 2
+  cfg.load_factor = load_factor > 0 ? load_factor : 0.5;     // join/join.cpp:30: ht_size = buf_size * 2
   cfg.hash_seed = helpers::make_random();      // join/join.cpp:32: seed = make_random()
   check(dwj_create(&cfg, &e_));
 }
@@ -98,6 +98,8 @@ std::unique_ptr<HashJoinResult> join_iteration(b200::Engine &eng, const std::vec
       res_present.push_back(key_present_out[i]);
       res_val.push_back(val_out[i]);
     }
+  result->iterations = 1;                                   // result.hpp:15-17: present in the reference, never filled there
+  result->bytes = result->bytes_per_iteration = (2 * ak.size() + 2 * n + 3 * res_k.size()) * sizeof(uint32_t);   // columns in, rows out
 #ifdef DWJ_HOST_FRAMEWORK      // extra fields exist only in this tree's HashJoinResult
   result->matches = res_k.size();
   result->tuples_per_second = (ak.size() + n) / (result->kernel_time.count() * 1e-6);
@@ -157,6 +159,8 @@ void join_run_multi_gpu(const size_t buf_size, Meter &meter, size_t gpus, const 
     res_k.resize(n_out);
     res_present.resize(n_out);
     res_val.resize(n_out);
+    result->iterations = 1;
+    result->bytes = result->bytes_per_iteration = (2 * ak.size() + 2 * n + 3 * n_out) * sizeof(uint32_t);
 #ifdef DWJ_HOST_FRAMEWORK
     result->matches = n_out;
     result->tuples_per_second = (ak.size() + n) / (result->kernel_time.count() * 1e-6);
@@ -223,13 +227,20 @@ void SlabJoin::run(const RunOptions &opts) {
 }
 void SlabJoin::init(const RunOptions &opts) { std_init(*this, opts); }
 
-// ---- HashBuild: timed build, untimed has() check (hash/hash_build.cpp:8-87) ------------------------------------
-HashBuild::HashBuild() : Dwarf("HashBuild") {}
-void HashBuild::_run(const size_t buf_size, Meter &meter) {
+// ---- build-only dwarfs: timed build, untimed has() check --------------------------------------------------------
+// HashBuild (hash/hash_build.cpp:8-87) and its siblings differ in the reference by table type, fill and key generator;
+// here one table serves them all, created at each dwarf's own load factor:
+//   HashBuild            bitmask table, T = 2n                      (hash_build.cpp:17)        keys in [1,10000]
+//   HashBuildNonBitmask  CAS-on-key table, T = n                    (hash_build_non_bitmask.cpp:19; 0.9 is this engine's cap)
+//   SlabHashBuild        chained slabs at 60 % utilisation = 0.625  (slab_hash_build.cpp:11, slab_hash.hpp:30-58)
+//   CuckooHashBuild      cuckoo table, T = 4n                       (cuckoo_hash_build.cpp:14)  unique keys
+namespace {
+void hash_build_run(const size_t buf_size, Meter &meter, double load_factor, bool unique_keys) {
   const RunOptions &opts = meter.opts();
-  const std::vector<uint32_t> host_src = helpers::make_random<uint32_t>(buf_size);           // hash_build.cpp:10-11
+  const std::vector<uint32_t> host_src = unique_keys ? helpers::make_unique_random(buf_size)      // cuckoo_hash_build.cpp:12
+                                                     : helpers::make_random<uint32_t>(buf_size);  // hash_build.cpp:10-11
   announce_device();
-  b200::Engine eng(std::max<size_t>(buf_size, 1), 0);
+  b200::Engine eng(std::max<size_t>(buf_size, 1), unique_keys ? DWJ_FLAG_UNIQUE_BUILD_KEYS : 0, 4, load_factor);
   DeviceColumn src(buf_size * 4), flags(buf_size * 4);
   for (unsigned it = 0; it < opts.iterations; ++it) {
     auto result = std::make_unique<Result>();
@@ -241,6 +252,10 @@ void HashBuild::_run(const size_t buf_size, Meter &meter) {
     dwj_timing t{};
     b200::Engine::check(dwj_timings(eng.get(), &t));
     result->kernel_time = ms(t.build_ms);
+    dwj_info info{};
+    b200::Engine::check(dwj_get_info(eng.get(), &info));
+    result->iterations = 1;                                                                  // result.hpp:15-17, never filled by the reference
+    result->bytes = result->bytes_per_iteration = buf_size * 2 * sizeof(uint32_t) + info.table_bytes;   // rows in, the table written
     std::vector<uint32_t> output(buf_size, 0);                                               // :61-81
     b200::Engine::check(dwj_probe_contains(eng.get(), src.ptr, buf_size, static_cast<uint32_t *>(flags.ptr), nullptr));
     if (cudaMemcpy(output.data(), flags.ptr, buf_size * 4, kD2H) != 0) throw std::runtime_error("cudaMemcpy D2H failed");
@@ -251,11 +266,20 @@ void HashBuild::_run(const size_t buf_size, Meter &meter) {
     meter.add_result(DwarfParams{{"buf_size", std::to_string(buf_size)}}, std::move(result));
   }
 }
-void HashBuild::run(const RunOptions &opts) {
-  b200::require_gpu(opts, name());
-  for (auto size : opts.input_size) _run(size, meter());
-}
-void HashBuild::init(const RunOptions &opts) { std_init(*this, opts); }
+}  // namespace
+
+#define B200_BUILD_ONLY_DWARF(NAME, LOAD, UNIQUE)                                           \
+  NAME::NAME() : Dwarf(#NAME) {}                                                            \
+  void NAME::_run(const size_t buf_size, Meter &meter) { hash_build_run(buf_size, meter, LOAD, UNIQUE); } \
+  void NAME::run(const RunOptions &opts) {                                                  \
+    b200::require_gpu(opts, name());                                                        \
+    for (auto size : opts.input_size) _run(size, meter());                                  \
+  }                                                                                         \
+  void NAME::init(const RunOptions &opts) { std_init(*this, opts); }
+B200_BUILD_ONLY_DWARF(HashBuild, 0.5, false)
+B200_BUILD_ONLY_DWARF(HashBuildNonBitmask, 0.9, false)
+B200_BUILD_ONLY_DWARF(SlabHashBuild, 0.625, false)
+B200_BUILD_ONLY_DWARF(CuckooHashBuild, 0.25, true)
 
 // ---- SlabProbe: untimed build, timed find (probe/slab_probe.cpp:9-107) ------------------------------------------
 SlabProbe::SlabProbe() : Dwarf("SlabProbe") {}

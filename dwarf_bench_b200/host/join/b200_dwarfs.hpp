@@ -3,6 +3,7 @@
 // Registry names and what they time are the reference's:
 //   Join            join/join.cpp            build + probe, probe-aligned outputs, host compaction, == seq_join
 //   HashBuild       hash/hash_build.cpp      build only (val = key, keys in [1,10000]); has() == 1 for every key
+//   HashBuildNonBitmask, SlabHashBuild, CuckooHashBuild   hash/*.cpp   the same at their own fill (0.9 / 0.625 / 0.25)
 //   SlabProbe       probe/slab_probe.cpp     probe only (build untimed); find() == 1 for every key
 //   SlabJoin        join/slab_join.cpp       Join's flow (the reference's slab variant); here the same table
 //   JoinOmnisci     join/join_omnisci.cpp    one-to-many join on row ids, keys in [1,10000]
@@ -17,7 +18,7 @@ namespace b200 {
 // RAII handle over a dwj_engine; throws std::runtime_error carrying dwj_last_error() on any failure.
 class Engine {
 public:
-  Engine(size_t max_build_rows, unsigned flags, int key_bytes = 4);
+  Engine(size_t max_build_rows, unsigned flags, int key_bytes = 4, double load_factor = 0.0);
   ~Engine();
   Engine(const Engine &) = delete;
   Engine &operator=(const Engine &) = delete;
@@ -45,6 +46,9 @@ void require_gpu(const RunOptions &opts, const std::string &dwarf);
 B200_DECLARE_DWARF(Join)
 B200_DECLARE_DWARF(SlabJoin)
 B200_DECLARE_DWARF(HashBuild)
+B200_DECLARE_DWARF(HashBuildNonBitmask)
+B200_DECLARE_DWARF(SlabHashBuild)
+B200_DECLARE_DWARF(CuckooHashBuild)
 B200_DECLARE_DWARF(SlabProbe)
 B200_DECLARE_DWARF(JoinOmnisci)
 B200_DECLARE_DWARF(JoinOmnisciCuda)

@@ -8,6 +8,9 @@
 void populate_registry() {
   auto registry = Registry::instance();
   registry->registerd(new HashBuild());
+  registry->registerd(new HashBuildNonBitmask());
+  registry->registerd(new SlabHashBuild());
+  registry->registerd(new CuckooHashBuild());
   registry->registerd(new Join());
   registry->registerd(new JoinOmnisci());
   registry->registerd(new JoinOmnisciCuda());

@@ -146,7 +146,8 @@ static void framework_tests() {
   populate_registry();                                                     // idempotent
   std::set<std::string> names;
   for (const auto &dw : *Registry::instance()) names.insert(dw.first);
-  CHECK((names == std::set<std::string>{"HashBuild", "Join", "JoinOmnisci", "JoinOmnisciCuda", "SlabJoin", "SlabProbe"}));
+  CHECK((names == std::set<std::string>{"CuckooHashBuild", "HashBuild", "HashBuildNonBitmask", "Join", "JoinOmnisci", "JoinOmnisciCuda",
+                                        "SlabHashBuild", "SlabJoin", "SlabProbe"}));
   CHECK(Registry::instance()->find("Join") != nullptr && Registry::instance()->find("Join")->name() == "Join");
   CHECK(Registry::instance()->find("NoSuchDwarf") == nullptr);
 
@@ -222,6 +223,9 @@ template <class DwarfClass> static void test_suite() {
 
 static void gpu_tests() {
   test_suite<HashBuild>();
+  test_suite<HashBuildNonBitmask>();      // dwarf_tests.cpp:68, :77-78 (EXPERIMENTAL in the reference)
+  test_suite<SlabHashBuild>();
+  test_suite<CuckooHashBuild>();
   test_suite<Join>();
   test_suite<SlabJoin>();
   test_suite<SlabProbe>();

@@ -121,6 +121,9 @@ typedef struct {
   int32_t device;            /* its CUDA device                                             */
   uint64_t hash_seed;
   uint64_t max_build_rows;   /* dwj_config.max_build_rows                                   */
+  uint32_t hot_probe_keys;   /* 1: the last dwj_probe_pairs over unique build keys found its probe keys skewed (a
+                                sample of 4096 keys put >= 0.6 % into one bucket) and let table sectors into L1  */
+  uint32_t reserved;
 } dwj_info;
 
 DWJ_API int dwj_abi_version(void);

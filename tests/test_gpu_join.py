@@ -545,3 +545,75 @@ def test_segments_pull_and_region_scatter(dwj, oracle, monkeypatch, wide):
         assert m2 == len(want[0])
         for w, x in zip(want, got):
             np.testing.assert_array_equal(w, x)
+
+
+def test_hot_probe_keys_with_unique_build_keys(dwj, oracle):
+    """Zipf(1.0) probe keys over UNIQUE build keys (the staged PAIRS kernel): same rows as the oracle, and the engine
+    notices the skew on the device (a sample of the probe keys) and lets the table sectors into L1 -- while uniform
+    probe keys keep the streaming loads."""
+    rng = np.random.default_rng(321)
+    n = 1 << 18
+    ak = _unique_keys(rng, n, np.uint32)
+    av = np.arange(n, dtype=np.uint32)
+    bk_zipf = ak[zipf_ranks(rng, n, 1 << 20)]
+    bk_unif = ak[rng.integers(0, n, 1 << 20)]
+    bv = np.arange(1 << 20, dtype=np.uint32)
+    with dwj.Engine(n, key_bytes=4, flags=dwj.FLAG_UNIQUE_BUILD_KEYS) as e:
+        dak, dav, dbv = dev(ak), dev(av), dev(bv)
+        e.build(dak, dav, n)
+        ok, oa, ob = (empty_like_dev(len(bv), np.uint32) for _ in range(3))
+        for bk, hot in ((bk_zipf, 1), (bk_unif, 0), (bk_zipf, 1)):
+            m = e.probe_pairs(dev(bk), dbv, len(bk), ok, oa, ob, len(bk))
+            torch.cuda.synchronize()
+            assert e.info()["hot_probe_keys"] == hot
+            want = oracle.sort_join(ak, av, bk, bv)
+            got = pyoracle.canonical_rows(*(host(t, np.uint32)[:m] for t in (ok, oa, ob)))
+            assert m == len(want[0])
+            for w, x in zip(want, got):
+                np.testing.assert_array_equal(w, x)
+
+
+def test_slab_golden_squares(dwj):
+    """ref:tests/slab_tests.cpp:213-283 -- 1000 keys i*i inserted with value == key, then every key is found with its
+    value.  SlabHash's insert / find are served by dwj_build / dwj_probe_* over the sector-bucket table."""
+    keys = (np.arange(1000, dtype=np.uint64) ** 2).astype(np.uint32)
+    keys = keys[keys != 0xFFFFFFFF]
+    with dwj.Engine(len(keys), key_bytes=4, load_factor=0.625, flags=dwj.FLAG_UNIQUE_BUILD_KEYS) as e:      # slab_hash.hpp:57: 0.625 fill
+        dk = dev(keys)
+        e.build(dk, dk, len(keys))
+        flags = torch.zeros(len(keys), dtype=torch.int32, device="cuda")
+        e.probe_contains(dk, len(keys), flags)
+        ok, oa, ob = (empty_like_dev(len(keys), np.uint32) for _ in range(3))
+        e.probe_aligned(dk, dk, len(keys), ok, oa, ob)
+        torch.cuda.synchronize()
+        assert int(flags.sum().item()) == len(keys)
+        np.testing.assert_array_equal(host(oa, np.uint32), keys)          # value == key for every key
+        absent = dev(np.array([2, 3, 5, 999 * 999 + 1], dtype=np.uint32))
+        f2 = torch.ones(4, dtype=torch.int32, device="cuda")
+        e.probe_contains(absent, 4, f2)
+        assert int(f2.sum().item()) == 0
+
+
+def test_aligned_probe_under_duplicate_build_keys(dwj):
+    """SimpleNonOwningHashTable::at returns ONE row per probe key even when the build side holds duplicates
+    (ref:hashtable.hpp:23-40; ref:tests/hash_table_tests.cpp:112-113 pins "first inserted" for a serial insert).  With
+    concurrent inserts the reference itself is racy about which duplicate comes first; the contract tested here is the
+    one both share: exactly one row per probe key, and its payload is the payload of SOME build row with that key."""
+    rng = np.random.default_rng(99)
+    distinct = rng.choice(1 << 30, 5000, replace=False).astype(np.uint32)
+    ak = np.repeat(distinct, 3)
+    rng.shuffle(ak)
+    av = np.arange(len(ak), dtype=np.uint32)
+    bk = np.concatenate([distinct, rng.integers(1 << 30, (1 << 31), 1000).astype(np.uint32)])
+    bv = np.arange(len(bk), dtype=np.uint32)
+    with dwj.Engine(len(ak), key_bytes=4) as e:
+        e.build(dev(ak), dev(av), len(ak))
+        ok, oa, ob = (empty_like_dev(len(bk), np.uint32) for _ in range(3))
+        e.probe_aligned(dev(bk), dev(bv), len(bk), ok, oa, ob)
+        torch.cuda.synchronize()
+    k, a, b = host(ok, np.uint32), host(oa, np.uint32), host(ob, np.uint32)
+    hit = k != 0xFFFFFFFF
+    assert hit[:5000].all() and not hit[5000:].any()
+    np.testing.assert_array_equal(k[:5000], distinct)
+    np.testing.assert_array_equal(ak[a[:5000]], distinct)                # the payload names a build row holding that key
+    np.testing.assert_array_equal(b[:5000], bv[:5000])

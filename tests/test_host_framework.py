@@ -79,7 +79,8 @@ def test_cli_surface(built):
     assert r.returncode == 0
     assert "DWARF_BENCH_ROOT is set to" in r.stdout and "Supported dwarfs:" in r.stdout
     listed = re.findall(r"^\t(\w+)$", r.stdout, flags=re.M)
-    assert listed == ["HashBuild", "Join", "JoinOmnisci", "JoinOmnisciCuda", "SlabJoin", "SlabProbe"]
+    assert listed == ["CuckooHashBuild", "HashBuild", "HashBuildNonBitmask", "Join", "JoinOmnisci", "JoinOmnisciCuda", "SlabHashBuild",
+                      "SlabJoin", "SlabProbe"]
     r = run([cli, "Join", "--help"])
     assert r.returncode == 0 and "--input_size arg" in r.stdout and "--report_path arg" in r.stdout
     r = run([cli, "NoSuchDwarf"])
@@ -118,7 +119,7 @@ def test_cli_join_on_gpu(built, tmp_path):
     for row in lines[1:]:
         cells = row.split(",")
         assert cells[0] == "GPU" and cells[1] == str(4096 * 4) and len(cells) == 6 and all(float(c) >= 0 for c in cells[2:])
-    for name in ("HashBuild", "SlabProbe", "JoinOmnisciCuda", "SlabJoin"):
+    for name in ("HashBuild", "SlabProbe", "JoinOmnisciCuda", "SlabJoin", "HashBuildNonBitmask", "SlabHashBuild", "CuckooHashBuild"):
         r = run([cli, name, "--device=gpu", "--input_size=2048", "--iterations=2"])
         assert r.returncode == 0 and r.stdout.count("Host duration:") == 2, name + r.stdout + r.stderr
 
