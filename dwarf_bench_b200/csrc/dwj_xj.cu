@@ -458,11 +458,10 @@ int dwj_xj_create(dwj_engine *e, const dwj_xj_config *cfg, void *const *blocks, 
   auto bail = [&](int rc) { dwj_xj_destroy(x); if (prev >= 0) cudaSetDevice(prev); return rc; };
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = numerically lowest = highest priority
-  // One priority for all three streams.  Measured on 8 GPUs (profiles/r2_exchange.md): with the partition stream above
-  // the join stream, the local build -- a few hundred microseconds of work at BASELINE config 2 -- did not start before
-  // the LAST probe chunk had been partitioned (table built at 4.0 ms of a 7.6 ms step), and at config 5 the build kernel,
-  // which is the critical path, ran at half speed beside the chunk traffic.  DWJ_XJ_PRIORITY=1 restores the old order.
-  if (!(getenv("DWJ_XJ_PRIORITY") && atoi(getenv("DWJ_XJ_PRIORITY")))) hi = lo;
+  // Partition and transfer streams above the join stream: everything downstream, on every rank, waits for them.
+  // A/B on 8 GPUs (profiles/r2_exchange.md): config 5 29.9 ms with these priorities, 31.6 ms with one priority for all;
+  // config 2 per GPU 7.26 against 8.10 ms.  DWJ_XJ_PRIORITY=0 gives all three streams one priority.
+  if (getenv("DWJ_XJ_PRIORITY") && !atoi(getenv("DWJ_XJ_PRIORITY"))) hi = lo;
   if (cudaStreamCreateWithPriority(&x->s_part, cudaStreamNonBlocking, hi) != cudaSuccess ||
       cudaStreamCreateWithPriority(&x->s_pull, cudaStreamNonBlocking, hi) != cudaSuccess ||
       cudaStreamCreateWithPriority(&x->s_join, cudaStreamNonBlocking, lo) != cudaSuccess)

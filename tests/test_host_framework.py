@@ -141,3 +141,16 @@ def test_dropin_against_reference_framework():
         pytest.skip("oracle/_ref/dropin_join_test not built (needs the reference checkout at build time)")
     r = run([exe])
     assert r.returncode == 0 and "dropin: 0 failures" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_join_over_two_gpus(built):
+    """`dwarf_bench Join --device=gpu --gpus 2`: the C++ host reaches the multi-GPU join (dwj_mg_join_host) and every
+    iteration matches the host's expected rows (no "Incorrect results", exit code 0)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    env = dict(os.environ, DWARF_BENCH_SEED="11", DWJ_XJ_TIMEOUT_MS="10000")
+    r = run([os.path.join(built, "dwarf_bench"), "Join", "--device=gpu", "--gpus", "2", "--input_size", "4096", "300000", "--iterations", "3"], env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Incorrect results" not in r.stderr and r.stdout.count("Build time:") == 6
