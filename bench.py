@@ -416,7 +416,7 @@ def engine_run(args, wname, steps, warmup, device, local_rank, want_e2e, rows_ov
                                           "frac": compulsory / (ms_per_step * 1e-3) / 1e9 / peak,
                                           "model": "(R+S)*(K+P) + M*out_row + T*slot: every input row read once, every result row written once, the table written once"}
     # ---- end to end through the host-buffer entry point -------------------------------------------------------------------
-    if want_e2e and inp.unique_build:
+    if want_e2e:
         def pinned(t):
             h = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
             h.copy_(t)
@@ -768,7 +768,7 @@ def main():
     if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_sub_configs and not overridden:
         line["configs"] = {}
         for w in SUB_CONFIGS:
-            sub = engine_run(args, w, args.sub_steps, 3, device, local_rank, not args.no_e2e and WORKLOADS[w][1] * WORKLOADS[w][3] <= (1 << 31))
+            sub = engine_run(args, w, args.sub_steps, 3, device, local_rank, not args.no_e2e and WORKLOADS[w][1] * WORKLOADS[w][3] <= (1 << 30))
             sub["unit"] = UNIT
             line["configs"][w] = sub
 

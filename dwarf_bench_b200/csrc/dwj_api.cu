@@ -1166,9 +1166,32 @@ uint32_t dwj_region_of(uint64_t key, int32_t key_bytes, uint64_t buckets, uint32
 // Three streams (H2D, compute, D2H) and HOST_STAGES staging slots: the copy engines run continuously while the
 // host only ever waits for a chunk that is two behind the one it just enqueued.  PCIe is full duplex, so the H2D of
 // chunk c+1.. overlaps the probe of chunk c and the D2H of chunk c-1...
+static int join_host_impl(dwj_engine *e, const void *build_keys, const void *build_vals, uint64_t n_build, const void *probe_keys,
+                          const void *probe_vals, uint64_t n_probe, int out_mode, void *out_key, void *out_build_val,
+                          void *out_probe_val, uint64_t out_capacity, uint64_t *n_out, dwj_timing *timing);
+
 int dwj_join_host(dwj_engine *e, const void *build_keys, const void *build_vals, uint64_t n_build, const void *probe_keys,
                   const void *probe_vals, uint64_t n_probe, int out_mode, void *out_key, void *out_build_val,
                   void *out_probe_val, uint64_t out_capacity, uint64_t *n_out, dwj_timing *timing) {
+  const int rc = join_host_impl(e, build_keys, build_vals, n_build, probe_keys, probe_vals, n_probe, out_mode, out_key, out_build_val,
+                                out_probe_val, out_capacity, n_out, timing);
+  if (rc && e) {
+    // An error exit may leave copies queued that target the caller's buffers: nothing of this call is in flight once
+    // it has returned.  The message of the failure is kept.
+    char keep[sizeof(g_err)];
+    memcpy(keep, g_err, sizeof(keep));
+    DeviceGuard g(e->cfg.device);
+    for (auto &st : e->hs)
+      if (st) cudaStreamSynchronize(st);
+    cudaGetLastError();
+    memcpy(g_err, keep, sizeof(keep));
+  }
+  return rc;
+}
+
+static int join_host_impl(dwj_engine *e, const void *build_keys, const void *build_vals, uint64_t n_build, const void *probe_keys,
+                          const void *probe_vals, uint64_t n_probe, int out_mode, void *out_key, void *out_build_val,
+                          void *out_probe_val, uint64_t out_capacity, uint64_t *n_out, dwj_timing *timing) {
   if (int rc = check_engine(e)) return rc;
   if (out_mode < DWJ_OUT_ALIGNED || out_mode > DWJ_OUT_COUNT) return fail(DWJ_ERR_INVALID, "bad out_mode %d", out_mode);
   if ((n_build && (!build_keys || !build_vals)) || (n_probe && (!probe_keys || !probe_vals)))
@@ -1221,69 +1244,98 @@ int dwj_join_host(dwj_engine *e, const void *build_keys, const void *build_vals,
 
   uint64_t produced = 0;       // rows written to the host outputs so far (PAIRS) / matches (COUNT)
   bool overflow = false;
-  const uint64_t n_chunks = (n_probe + chunk_rows - 1) / chunk_rows;
 
-  // Finish chunk c (PAIRS / COUNT): wait for its probe, read its match count, enqueue its D2H at the running offset.
-  auto drain = [&](uint64_t c) -> int {
-    const int st = (int)(c % NS);
-    const uint64_t rows = std::min<uint64_t>(chunk_rows, n_probe - c * chunk_rows);
-    CU(cudaEventSynchronize(ev_done[st]));
-    const unsigned long long cnt = e->h_counts[st];
-    if (out_mode == DWJ_OUT_PAIRS) {
-      if (cnt > chunk_rows)
-        return fail(DWJ_ERR_OVERFLOW,
-                    "a probe chunk of %llu rows produced %llu matches; dwj_join_host stages at most one match per probe "
-                    "row -- use dwj_probe_pairs with device buffers for higher multiplicities",
-                    (unsigned long long)rows, cnt);
-      const uint64_t room = produced < out_capacity ? out_capacity - produced : 0;
-      const uint64_t take = std::min<uint64_t>(cnt, room);
-      if (take < cnt) overflow = true;
-      CU(cudaStreamWaitEvent(s_out, ev_done[st], 0));
-      if (take) {
-        if (out_key) CU(cudaMemcpyAsync((char *)out_key + produced * W, stage_ptr(st, 2), take * W, cudaMemcpyDeviceToHost, s_out));
-        CU(cudaMemcpyAsync((char *)out_build_val + produced * W, stage_ptr(st, 3), take * W, cudaMemcpyDeviceToHost, s_out));
-        CU(cudaMemcpyAsync((char *)out_probe_val + produced * W, stage_ptr(st, 4), take * W, cudaMemcpyDeviceToHost, s_out));
-      }
-    }
-    CU(cudaEventRecord(ev_free[st], s_out));
-    produced += cnt;
-    return DWJ_OK;
-  };
-
-  for (uint64_t c = 0; c < n_chunks; ++c) {
-    const int st = (int)(c % NS);
-    const uint64_t row0 = c * chunk_rows, rows = std::min<uint64_t>(chunk_rows, n_probe - row0);
-    if (c >= (uint64_t)NS) CU(cudaStreamWaitEvent(s_in, ev_free[st], 0));      // the slot's previous chunk has left the device
-    CU(cudaMemcpyAsync(stage_ptr(st, 0), (const char *)probe_keys + row0 * W, rows * W, cudaMemcpyHostToDevice, s_in));
-    CU(cudaMemcpyAsync(stage_ptr(st, 1), (const char *)probe_vals + row0 * W, rows * W, cudaMemcpyHostToDevice, s_in));
-    CU(cudaEventRecord(ev_in[st], s_in));
-    CU(cudaStreamWaitEvent(s_comp, ev_in[st], 0));
-    int rc;
-    if (out_mode == DWJ_OUT_ALIGNED) {
-      rc = dwj_probe_aligned(e, stage_ptr(st, 0), stage_ptr(st, 1), rows, stage_ptr(st, 2), stage_ptr(st, 3), stage_ptr(st, 4), s_comp);
-      if (rc) return rc;
+  if (out_mode == DWJ_OUT_ALIGNED) {
+    const uint64_t n_chunks = (n_probe + chunk_rows - 1) / chunk_rows;
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+      const int st = (int)(c % NS);
+      const uint64_t row0 = c * chunk_rows, rows = std::min<uint64_t>(chunk_rows, n_probe - row0);
+      if (c >= (uint64_t)NS) CU(cudaStreamWaitEvent(s_in, ev_free[st], 0));      // the slot's previous chunk has left the device
+      CU(cudaMemcpyAsync(stage_ptr(st, 0), (const char *)probe_keys + row0 * W, rows * W, cudaMemcpyHostToDevice, s_in));
+      CU(cudaMemcpyAsync(stage_ptr(st, 1), (const char *)probe_vals + row0 * W, rows * W, cudaMemcpyHostToDevice, s_in));
+      CU(cudaEventRecord(ev_in[st], s_in));
+      CU(cudaStreamWaitEvent(s_comp, ev_in[st], 0));
+      if (int rc = dwj_probe_aligned(e, stage_ptr(st, 0), stage_ptr(st, 1), rows, stage_ptr(st, 2), stage_ptr(st, 3), stage_ptr(st, 4), s_comp)) return rc;
       CU(cudaEventRecord(ev_done[st], s_comp));
       CU(cudaStreamWaitEvent(s_out, ev_done[st], 0));
       CU(cudaMemcpyAsync((char *)out_key + row0 * W, stage_ptr(st, 2), rows * W, cudaMemcpyDeviceToHost, s_out));
       CU(cudaMemcpyAsync((char *)out_build_val + row0 * W, stage_ptr(st, 3), rows * W, cudaMemcpyDeviceToHost, s_out));
       CU(cudaMemcpyAsync((char *)out_probe_val + row0 * W, stage_ptr(st, 4), rows * W, cudaMemcpyDeviceToHost, s_out));
       CU(cudaEventRecord(ev_free[st], s_out));
-      continue;
     }
-    if (out_mode == DWJ_OUT_PAIRS)
-      rc = dwj_probe_pairs(e, stage_ptr(st, 0), stage_ptr(st, 1), rows, out_key ? stage_ptr(st, 2) : nullptr, stage_ptr(st, 3),
-                           stage_ptr(st, 4), chunk_rows, (uint64_t *)(d_cnt + st * 8), nullptr, s_comp);
-    else
-      rc = dwj_probe_count(e, stage_ptr(st, 0), rows, (uint64_t *)(d_cnt + st * 8), nullptr, s_comp);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(e->h_counts + st, d_cnt + st * 8, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s_comp));
-    CU(cudaEventRecord(ev_done[st], s_comp));
-    if (c >= (uint64_t)LAG)
-      if (int rc2 = drain(c - LAG)) return rc2;         // two chunks stay queued behind the one the host waits for
+  } else {
+    // PAIRS / COUNT.  A staging slot holds `chunk_rows` result rows.  With duplicate build keys a piece of the probe
+    // relation may produce more: the probe kernel then keeps what fits and still reports the exact count, so the piece is
+    // simply probed AGAIN in smaller pieces -- and the piece size stays reduced (it adapts to the multiplicity of the
+    // data within a piece or two).  In flight: up to LAG + 1 pieces, each {first row, rows, slot}.
+    struct Piece { uint64_t row0, rows; int st; };
+    Piece inflight[NS];
+    uint32_t head = 0, count = 0;                 // ring of pieces enqueued and not yet drained
+    uint64_t next_row = 0, piece_rows = chunk_rows, issued = 0;
+    auto enqueue = [&]() -> int {
+      const int st = (int)(issued % NS);
+      const uint64_t row0 = next_row, rows = std::min<uint64_t>(piece_rows, n_probe - row0);
+      if (issued >= (uint64_t)NS) CU(cudaStreamWaitEvent(s_in, ev_free[st], 0));
+      CU(cudaMemcpyAsync(stage_ptr(st, 0), (const char *)probe_keys + row0 * W, rows * W, cudaMemcpyHostToDevice, s_in));
+      if (out_mode == DWJ_OUT_PAIRS) CU(cudaMemcpyAsync(stage_ptr(st, 1), (const char *)probe_vals + row0 * W, rows * W, cudaMemcpyHostToDevice, s_in));
+      CU(cudaEventRecord(ev_in[st], s_in));
+      CU(cudaStreamWaitEvent(s_comp, ev_in[st], 0));
+      int rc;
+      if (out_mode == DWJ_OUT_PAIRS)
+        rc = dwj_probe_pairs(e, stage_ptr(st, 0), stage_ptr(st, 1), rows, out_key ? stage_ptr(st, 2) : nullptr, stage_ptr(st, 3),
+                             stage_ptr(st, 4), chunk_rows, (uint64_t *)(d_cnt + st * 8), nullptr, s_comp);
+      else
+        rc = dwj_probe_count(e, stage_ptr(st, 0), rows, (uint64_t *)(d_cnt + st * 8), nullptr, s_comp);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(e->h_counts + st, d_cnt + st * 8, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s_comp));
+      CU(cudaEventRecord(ev_done[st], s_comp));
+      inflight[(head + count++) % NS] = Piece{row0, rows, st};
+      next_row = row0 + rows;
+      ++issued;
+      return DWJ_OK;
+    };
+    // Finish the oldest piece: wait for its probe, read its match count, enqueue its D2H at the running offset -- or, if
+    // it produced more rows than a slot holds, drop everything in flight and restart from it with smaller pieces.
+    auto drain = [&]() -> int {
+      const Piece p = inflight[head];
+      CU(cudaEventSynchronize(ev_done[p.st]));
+      const unsigned long long cnt = e->h_counts[p.st];
+      if (out_mode == DWJ_OUT_PAIRS && cnt > chunk_rows) {
+        if (p.rows == 1)
+          return fail(DWJ_ERR_OVERFLOW, "one probe row has %llu matches, more than the %llu rows dwj_join_host stages at a time -- "
+                      "use dwj_probe_pairs with device buffers", cnt, (unsigned long long)chunk_rows);
+        CU(cudaStreamSynchronize(s_comp));          // the younger pieces are discarded with this one
+        for (uint32_t i = 0; i < count; ++i) CU(cudaEventRecord(ev_free[inflight[(head + i) % NS].st], s_comp));
+        count = 0;
+        next_row = p.row0;
+        piece_rows = std::max<uint64_t>(1, p.rows / (2 * ((cnt + chunk_rows - 1) / chunk_rows)));
+        return DWJ_OK;
+      }
+      if (out_mode == DWJ_OUT_PAIRS) {
+        const uint64_t room = produced < out_capacity ? out_capacity - produced : 0;
+        const uint64_t take = std::min<uint64_t>(cnt, room);
+        if (take < cnt) overflow = true;
+        CU(cudaStreamWaitEvent(s_out, ev_done[p.st], 0));
+        if (take) {
+          if (out_key) CU(cudaMemcpyAsync((char *)out_key + produced * W, stage_ptr(p.st, 2), take * W, cudaMemcpyDeviceToHost, s_out));
+          CU(cudaMemcpyAsync((char *)out_build_val + produced * W, stage_ptr(p.st, 3), take * W, cudaMemcpyDeviceToHost, s_out));
+          CU(cudaMemcpyAsync((char *)out_probe_val + produced * W, stage_ptr(p.st, 4), take * W, cudaMemcpyDeviceToHost, s_out));
+        }
+      }
+      CU(cudaEventRecord(ev_free[p.st], s_out));
+      produced += cnt;
+      head = (head + 1) % NS;
+      --count;
+      return DWJ_OK;
+    };
+    while (next_row < n_probe || count) {
+      if (next_row < n_probe && count <= (uint32_t)LAG) {       // LAG pieces stay queued behind the one the host waits for
+        if (int rc = enqueue()) return rc;
+        if (count <= (uint32_t)LAG && next_row < n_probe) continue;
+      }
+      if (int rc = drain()) return rc;
+    }
   }
-  if (out_mode != DWJ_OUT_ALIGNED)
-    for (uint64_t c = n_chunks > (uint64_t)LAG ? n_chunks - LAG : 0; c < n_chunks; ++c)
-      if (int rc = drain(c)) return rc;
   CU(cudaStreamSynchronize(s_comp));
   CU(cudaStreamSynchronize(s_out));
   CU(cudaEventRecord(e->htime[3], s_out));

@@ -617,3 +617,28 @@ def test_aligned_probe_under_duplicate_build_keys(dwj):
     np.testing.assert_array_equal(k[:5000], distinct)
     np.testing.assert_array_equal(ak[a[:5000]], distinct)                # the payload names a build row holding that key
     np.testing.assert_array_equal(b[:5000], bv[:5000])
+
+
+def test_join_host_with_duplicate_build_keys(dwj, oracle):
+    """dwj_join_host(PAIRS) with duplicate build keys: a piece of the probe relation may produce more rows than one
+    staging slot holds (here 3 Mi probe rows x 4 matches = 12 Mi rows against 8 Mi per slot); the piece is probed again
+    in smaller pieces and the result is the oracle's multiset."""
+    rng = np.random.default_rng(8)
+    distinct = rng.choice(1 << 30, 50_000, replace=False).astype(np.uint32)
+    ak = np.repeat(distinct, 4)
+    rng.shuffle(ak)
+    av = np.arange(len(ak), dtype=np.uint32)
+    bk = np.concatenate([distinct[rng.integers(0, len(distinct), 3 << 20)], rng.integers(1 << 30, 1 << 31, 1000).astype(np.uint32)])
+    bv = np.arange(len(bk), dtype=np.uint32)
+    want = oracle.sort_join(ak, av, bk, bv)
+    cap = len(want[0])
+    assert cap == 4 * (3 << 20)
+    ok, oa, ob = (np.zeros(cap, dtype=np.uint32) for _ in range(3))
+    with dwj.Engine(len(ak), key_bytes=4) as e:
+        m, t = e.join_host(ak, av, len(ak), bk, bv, len(bk), dwj.OUT_PAIRS, ok, oa, ob, cap)
+        assert m == cap
+        m2, _ = e.join_host(ak, av, len(ak), bk, bv, len(bk), dwj.OUT_COUNT, None, None, None, 0)
+        assert m2 == cap
+    got = pyoracle.canonical_rows(ok, oa, ob)
+    for w, x in zip(want, got):
+        np.testing.assert_array_equal(w, x)
