@@ -562,6 +562,9 @@ def exchange_run(args, wname, steps, warmup, device, local_rank, world, rank, wa
                    + ", sharded by key hash, fully materialised on every GPU",
                    "table_slots_per_gpu": info["slots"], "table_bytes_per_gpu": info["table_bytes"], "table_regions": info["radix_parts"],
                    "passes_over_key_classes": xinfo["passes"],
+                   "pass_structure": ("per pass and relation: compact the pass's key class out of the input (dwj_filter_rows, one streaming pass), "
+                                      "histogram + 512-way region scatter of the compact copy, then build / probe; the two send slots serve as each "
+                                      "other's scratch") if xinfo["compact_passes"] else None,
                    "one_gpu_note": (f"the 2^31 x 2^31 int64 working set (69 GB input + 69 GB table + 34 GB result) exceeds one GPU's HBM: "
                                     f"the join runs as {xinfo['passes']} passes over key classes, each re-reading both relations and "
                                     f"building a table for one class; all {tuples} input rows are joined and all result rows are resident at the end")
@@ -595,13 +598,17 @@ def exchange_run(args, wname, steps, warmup, device, local_rank, world, rank, wa
     tm = eng.timings()
     last_chunk_rows = n_probe - (xinfo["chunks"] - 1) * xinfo["chunk_rows"] if xinfo["chunks"] > 1 else n_probe
     kept = last_chunk_rows / xinfo["passes"]
-    scatter_bytes = last_chunk_rows * key_bytes + kept * key_bytes + kept * 2 * key_bytes
+    if xinfo["compact_passes"]:       # the scatter runs on the compact copy of the pass's key class: rows in, rows out
+        scatter_bytes, scatter_model = kept * 4 * key_bytes, "kept rows * (K+P) read + kept rows * (K+P) written (the pass's key class was compacted first)"
+    else:
+        scatter_bytes = last_chunk_rows * key_bytes + kept * key_bytes + kept * 2 * key_bytes
+        scatter_model = "chunk rows * K (every key is read) + kept rows * P (payloads of the pass's class) + kept rows * (K+P) written"
     kernels = {}
     if tm.partition_ms > 0:
         kernels["partition_scatter_many_kernel"] = {
             "ms": tm.partition_ms, "launches_per_step": xinfo["passes"] * (1 + xinfo["chunks"]),
             "algorithmic_bytes": scatter_bytes, "gbs": scatter_bytes / tm.partition_ms / 1e6,
-            "model": "chunk rows * K (every key is read) + kept rows * P (payloads of the pass's class) + kept rows * (K+P) written"}
+            "model": scatter_model}
     if tm.probe_kernel_ms > 0:
         pk = kept * 2 * key_bytes + kept * 2 * key_bytes       # rows in (about one chunk's share lands here), result rows out
         kernels["probe_pairs_staged_kernel"] = {"ms": tm.probe_kernel_ms, "launches_per_step": xinfo["passes"] * xinfo["chunks"],

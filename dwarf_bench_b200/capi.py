@@ -27,7 +27,7 @@ SYMBOLS = ("dwj_abi_version", "dwj_last_error", "dwj_create", "dwj_destroy", "dw
            "dwj_join_host", "dwj_partition", "dwj_partition_hist", "dwj_partition_of",
            "dwj_xpart_regions", "dwj_xpart_hist", "dwj_xpart_hist2", "dwj_xpart_scatter", "dwj_build_grouped",
            "dwj_probe_pairs_grouped", "dwj_build_segments", "dwj_probe_pairs_segments", "dwj_region_scatter_segments",
-           "dwj_set_option", "dwj_clear_table", "dwj_xj_block_bytes", "dwj_xj_create", "dwj_xj_destroy", "dwj_xj_describe", "dwj_xj_join",
+           "dwj_set_option", "dwj_clear_table", "dwj_filter_rows", "dwj_xj_block_bytes", "dwj_xj_create", "dwj_xj_destroy", "dwj_xj_describe", "dwj_xj_join",
            "dwj_xj_sync_timings", "dwj_xj_plan_send", "dwj_xj_plan_recv", "dwj_region_of", "dwj_mg_create", "dwj_mg_destroy", "dwj_mg_describe", "dwj_mg_join", "dwj_mg_join_host")
 ABI_VERSION = 2
 OPT_APPEND_OUTPUT, OPT_PASS_FILTER = 1, 2
@@ -64,7 +64,8 @@ class XjConfig(C.Structure):
 
 class XjInfo(C.Structure):
     _fields_ = [("regions", C.c_uint32), ("fold_regions", C.c_uint32), ("chunks", C.c_uint32), ("ring", C.c_uint32),
-                ("passes", C.c_uint32), ("direct_pull", C.c_uint32), ("copy_pull", C.c_uint32), ("chunk_rows", C.c_uint64), ("block_bytes", C.c_uint64),
+                ("passes", C.c_uint32), ("direct_pull", C.c_uint32), ("copy_pull", C.c_uint32), ("compact_passes", C.c_uint32), ("reserved", C.c_uint32),
+                ("chunk_rows", C.c_uint64), ("block_bytes", C.c_uint64),
                 ("landing_bytes", C.c_uint64)]
 
 
@@ -145,6 +146,7 @@ def load_library():
     lib.dwj_region_scatter_segments.argtypes = [vp, u32, vpp, vpp, u64p, u64p, vp, vp, vp]
     lib.dwj_set_option.argtypes = [vp, C.c_int, u64]
     lib.dwj_clear_table.argtypes = [vp, vp]
+    lib.dwj_filter_rows.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp]
     lib.dwj_xj_block_bytes.argtypes = [vp, C.POINTER(XjConfig), u64p]
     lib.dwj_xj_create.argtypes = [vp, C.POINTER(XjConfig), vpp, C.POINTER(vp)]
     lib.dwj_xj_destroy.argtypes = [vp]
@@ -336,6 +338,10 @@ class Engine:
 
     def xpart_hist2(self, d_keys, n_rows: int, n_ranks: int, d_counts, stream=None) -> None:
         self._check(self.lib.dwj_xpart_hist2(self._h, _ptr(d_keys), n_rows, n_ranks, _ptr(d_counts), _stream(stream)))
+
+    def filter_rows(self, d_keys, d_vals, n_rows: int, d_out_keys, d_out_vals, d_n_out, stream=None) -> None:
+        self._check(self.lib.dwj_filter_rows(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, _ptr(d_out_keys), _ptr(d_out_vals),
+                                             _ptr(d_n_out), _stream(stream)))
 
     def clear_table(self, stream=None) -> None:
         self._check(self.lib.dwj_clear_table(self._h, _stream(stream)))

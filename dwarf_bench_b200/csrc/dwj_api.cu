@@ -439,6 +439,29 @@ int region_scatter_segments_impl(dwj_engine *e, const uint64_t *h_start_rows, vo
   return rc;
 }
 
+template <int W>
+int filter_rows_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, void *ok, void *ov, uint64_t *d_n_out, cudaStream_t s) {
+  using K = typename dwj::KeyT<W>::type;
+  dwj::PartitionArgs<W> a = partition_args<W>(e, keys, vals, n, 0, dwj::PART_BY_HASH, 0);      // one partition; a.filter = the pass filter
+  a.out_keys = (K *)ok;
+  a.out_vals = (K *)ov;
+  a.cursor = (unsigned long long *)d_n_out;                // the single partition's write cursor IS the row count
+  CU(cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), s));
+  if (!n) return DWJ_OK;
+  if (!a.filter.mask) {                                    // no filter: everything is kept
+    CU(cudaMemcpyAsync(ok, keys, n * W, cudaMemcpyDeviceToDevice, s));
+    if (vals) CU(cudaMemcpyAsync(ov, vals, n * W, cudaMemcpyDeviceToDevice, s));
+    dwj::stage_value_kernel<<<1, 1, 0, s>>>((unsigned long long *)d_n_out, (unsigned long long)n);
+    CU(cudaGetLastError());
+    return DWJ_OK;
+  }
+  constexpr int THREADS = 256, ITEMS = 8;
+  const uint64_t tiles = (n + (uint64_t)THREADS * ITEMS - 1) / ((uint64_t)THREADS * ITEMS);
+  const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)e->prop.multiProcessorCount * 8);
+  CU(launch(e, dwj::filter_rows_kernel<W, THREADS, ITEMS>, dim3(grid), dim3(THREADS), s, a, false));
+  return DWJ_OK;
+}
+
 // grouped: the caller's rows are already grouped by table region (dwj_build_grouped); `grouped_offsets` (device,
 // regions + 1 entries, may be null) are the regions' row ranges for the look-ahead.
 template <int W> int build_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, cudaStream_t s, bool grouped = false,
@@ -1115,6 +1138,16 @@ int dwj_xpart_hist2(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t
   const uint32_t mode = e->region_bits ? dwj::PART_BY_BOTH : dwj::PART_BY_HASH;
   return e->W == 4 ? partition_hist_impl<4>(e, d_keys, n_rows, bits, mode, rb, d_counts, (cudaStream_t)stream)
                    : partition_hist_impl<8>(e, d_keys, n_rows, bits, mode, rb, d_counts, (cudaStream_t)stream);
+}
+
+int dwj_filter_rows(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *d_out_keys, void *d_out_vals,
+                    uint64_t *d_n_out, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  if (!d_n_out || (n_rows && (!d_keys || !d_out_keys))) return fail(DWJ_ERR_INVALID, "null filter argument");
+  if ((d_vals == nullptr) != (d_out_vals == nullptr)) return fail(DWJ_ERR_INVALID, "d_vals and d_out_vals must both be given or both be null");
+  DeviceGuard g(e->cfg.device);
+  return e->W == 4 ? filter_rows_impl<4>(e, d_keys, d_vals, n_rows, d_out_keys, d_out_vals, d_n_out, (cudaStream_t)stream)
+                   : filter_rows_impl<8>(e, d_keys, d_vals, n_rows, d_out_keys, d_out_vals, d_n_out, (cudaStream_t)stream);
 }
 
 int dwj_clear_table(dwj_engine *e, void *stream) {

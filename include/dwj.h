@@ -251,6 +251,14 @@ DWJ_API int dwj_region_scatter_segments(dwj_engine *e, uint32_t n_segments, cons
  * device), rank-major.  The senders count for the receivers.  n_ranks: 1, 2, 4 or 8.  Asynchronous. */
 DWJ_API int dwj_xpart_hist2(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t n_ranks, uint64_t *d_counts, void *stream);
 
+/* The rows of the current pass filter's key class (all rows without a filter), copied to d_out_keys / d_out_vals in no
+ * particular order; *d_n_out (device, uint64) = rows kept.  The out columns must hold n_rows rows in the worst case.  One
+ * streaming pass, no histogram: a join that runs as passes over key classes (DWJ_OPT_PASS_FILTER) on ONE GPU compacts a
+ * relation's class first and partitions the compact copy -- the many-way scatter writes full tiles again instead of the
+ * class's half.  d_vals / d_out_vals may both be NULL.  Asynchronous. */
+DWJ_API int dwj_filter_rows(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *d_out_keys, void *d_out_vals,
+                    uint64_t *d_n_out, void *stream);
+
 /* Clears the table on `stream` AHEAD of the next dwj_build* call, which then waits for this clear instead of doing its own:
  * the clear (a pure HBM write of the whole table) can overlap whatever produces the build rows -- a partition pass, an
  * exchange -- on another stream.  The table must not be probed between the two calls.  Asynchronous. */
@@ -307,6 +315,9 @@ typedef struct {
                                  scatter groups them first (ranks x regions > 512, or duplicate build keys)      */
   uint32_t copy_pull;         /* 1: a copy kernel first moves the rows out of the senders' slots over NVLink (world > 1);
                                  0: the consuming kernels read the slots themselves (world == 1, DWJ_XJ_FUSED_PULL=1) */
+  uint32_t compact_passes;    /* 1: one GPU, passes > 1, one probe chunk: every pass first compacts its key class out of
+                                 the input (dwj_filter_rows) and partitions the compact copy                    */
+  uint32_t reserved;
   uint64_t chunk_rows;
   uint64_t block_bytes;       /* = dwj_xj_block_bytes                                                            */
   uint64_t landing_bytes;     /* local buffers of the region-scatter receive path                                */

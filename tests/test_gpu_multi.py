@@ -53,6 +53,22 @@ def test_mg_join_virtual_ranks(tmp_path, world, key_bytes, pull, passes, regions
         assert res["info"]["regions"] > 1
 
 
+@pytest.mark.parametrize("key_bytes,passes", [(8, 2), (4, 4)])
+def test_one_gpu_passes_compact_then_partition(tmp_path, key_bytes, passes):
+    """world == 1, passes > 1, one probe chunk: the local path of dwj_xj_join (dwj_filter_rows compacts a relation's key
+    class, the compact copy is partitioned by table region, the slots serve as each other's scratch) -- the way the
+    2^31 x 2^31 join runs on one GPU.  Three consecutive joins against the oracle."""
+    out = tmp_path / "res.json"
+    env = _env(True)
+    env["DWJ_TEST_CHUNK_ROWS"] = "1000000"
+    r = subprocess.run([sys.executable, WORKER, "virtual", "1", str(key_bytes), "direct", str(passes), str(out)],
+                       env=env, capture_output=True, text=True, timeout=150)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.load(open(out))
+    assert all(s["same"] and s["rows"] == s["want"] for s in res["steps"]), res
+    assert res["info"]["chunks"] == 1 and res["info"]["passes"] == passes and res["info"]["regions"] > 1
+
+
 @pytest.mark.parametrize("key_bytes,pull,passes", [(4, "direct", 1), (8, "direct", 1), (8, "scatter", 1), (4, "scatter", 2)])
 def test_pull_exchange_two_ranks(tmp_path, oracle, key_bytes, pull, passes):
     if torch.cuda.device_count() < 2:
