@@ -146,7 +146,7 @@ def load_library():
     lib.dwj_region_scatter_segments.argtypes = [vp, u32, vpp, vpp, u64p, u64p, vp, vp, vp]
     lib.dwj_set_option.argtypes = [vp, C.c_int, u64]
     lib.dwj_clear_table.argtypes = [vp, vp]
-    lib.dwj_filter_rows.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp]
+    lib.dwj_filter_rows.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, vp]
     lib.dwj_xj_block_bytes.argtypes = [vp, C.POINTER(XjConfig), u64p]
     lib.dwj_xj_create.argtypes = [vp, C.POINTER(XjConfig), vpp, C.POINTER(vp)]
     lib.dwj_xj_destroy.argtypes = [vp]
@@ -339,9 +339,9 @@ class Engine:
     def xpart_hist2(self, d_keys, n_rows: int, n_ranks: int, d_counts, stream=None) -> None:
         self._check(self.lib.dwj_xpart_hist2(self._h, _ptr(d_keys), n_rows, n_ranks, _ptr(d_counts), _stream(stream)))
 
-    def filter_rows(self, d_keys, d_vals, n_rows: int, d_out_keys, d_out_vals, d_n_out, stream=None) -> None:
+    def filter_rows(self, d_keys, d_vals, n_rows: int, d_out_keys, d_out_vals, d_n_out, d_region_counts=None, stream=None) -> None:
         self._check(self.lib.dwj_filter_rows(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, _ptr(d_out_keys), _ptr(d_out_vals),
-                                             _ptr(d_n_out), _stream(stream)))
+                                             _ptr(d_n_out), _ptr(d_region_counts), _stream(stream)))
 
     def clear_table(self, stream=None) -> None:
         self._check(self.lib.dwj_clear_table(self._h, _stream(stream)))

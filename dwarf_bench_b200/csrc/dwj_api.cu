@@ -440,15 +440,19 @@ int region_scatter_segments_impl(dwj_engine *e, const uint64_t *h_start_rows, vo
 }
 
 template <int W>
-int filter_rows_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, void *ok, void *ov, uint64_t *d_n_out, cudaStream_t s) {
+int filter_rows_impl(dwj_engine *e, const void *keys, const void *vals, uint64_t n, void *ok, void *ov, uint64_t *d_n_out,
+                     uint64_t *d_region_counts, cudaStream_t s) {
   using K = typename dwj::KeyT<W>::type;
-  dwj::PartitionArgs<W> a = partition_args<W>(e, keys, vals, n, 0, dwj::PART_BY_HASH, 0);      // one partition; a.filter = the pass filter
+  // the partition id only serves the optional region histogram; a.filter = the pass filter
+  dwj::PartitionArgs<W> a = partition_args<W>(e, keys, vals, n, d_region_counts ? e->region_bits : 0, dwj::PART_BY_BUCKET, 0);
   a.out_keys = (K *)ok;
   a.out_vals = (K *)ov;
-  a.cursor = (unsigned long long *)d_n_out;                // the single partition's write cursor IS the row count
+  a.cursor = (unsigned long long *)d_n_out;                // the write cursor IS the row count
+  a.hist = (unsigned long long *)d_region_counts;
   CU(cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), s));
+  if (d_region_counts) CU(cudaMemsetAsync(d_region_counts, 0, sizeof(uint64_t) << e->region_bits, s));
   if (!n) return DWJ_OK;
-  if (!a.filter.mask) {                                    // no filter: everything is kept
+  if (!a.filter.mask && !d_region_counts) {                // no filter, no histogram: a copy
     CU(cudaMemcpyAsync(ok, keys, n * W, cudaMemcpyDeviceToDevice, s));
     if (vals) CU(cudaMemcpyAsync(ov, vals, n * W, cudaMemcpyDeviceToDevice, s));
     dwj::stage_value_kernel<<<1, 1, 0, s>>>((unsigned long long *)d_n_out, (unsigned long long)n);
@@ -1141,13 +1145,13 @@ int dwj_xpart_hist2(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t
 }
 
 int dwj_filter_rows(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *d_out_keys, void *d_out_vals,
-                    uint64_t *d_n_out, void *stream) {
+                    uint64_t *d_n_out, uint64_t *d_region_counts, void *stream) {
   if (int rc = check_engine(e)) return rc;
   if (!d_n_out || (n_rows && (!d_keys || !d_out_keys))) return fail(DWJ_ERR_INVALID, "null filter argument");
   if ((d_vals == nullptr) != (d_out_vals == nullptr)) return fail(DWJ_ERR_INVALID, "d_vals and d_out_vals must both be given or both be null");
   DeviceGuard g(e->cfg.device);
-  return e->W == 4 ? filter_rows_impl<4>(e, d_keys, d_vals, n_rows, d_out_keys, d_out_vals, d_n_out, (cudaStream_t)stream)
-                   : filter_rows_impl<8>(e, d_keys, d_vals, n_rows, d_out_keys, d_out_vals, d_n_out, (cudaStream_t)stream);
+  return e->W == 4 ? filter_rows_impl<4>(e, d_keys, d_vals, n_rows, d_out_keys, d_out_vals, d_n_out, d_region_counts, (cudaStream_t)stream)
+                   : filter_rows_impl<8>(e, d_keys, d_vals, n_rows, d_out_keys, d_out_vals, d_n_out, d_region_counts, (cudaStream_t)stream);
 }
 
 int dwj_clear_table(dwj_engine *e, void *stream) {

@@ -554,9 +554,9 @@ int dwj_xj_timings(dwj_xj *x, dwj_xj_timing *t) {
 }
 
 // One pass over one key class on ONE GPU with nothing to exchange (world == 1, passes > 1, one probe chunk): the class's
-// rows of a relation are first compacted out of the input (dwj_filter_rows: one streaming pass, no histogram) into the
-// slot the other relation is not using, counted and partitioned by table region from the compact copy (full tiles, no
-// filter in the 512-way scatter), then built / probed through one segment per region.  Everything on one stream: on one
+// rows of a relation are first compacted out of the input (dwj_filter_rows: one streaming pass that also counts the kept
+// rows per table region) into the slot the other relation is not using, then partitioned by table region from the
+// compact copy (full tiles, no filter in the 512-way scatter) and built / probed through one segment per region.  Everything on one stream: on one
 // GPU the step is work-bound, there is nothing to overlap with.  Measured on the 2^31 x 2^31 int64 join: the
 // pass-filtered 512-way scatter ran at 1.8 TB/s of real DRAM traffic (half of every tile dropped) and was 47 % of the step.
 static int xj_pass_local(dwj_xj *x, uint32_t pass, const void *bk, const void *bv, uint64_t n_build, const void *pk, const void *pv,
@@ -577,9 +577,10 @@ static int xj_pass_local(dwj_xj *x, uint32_t pass, const void *bk, const void *b
     const uint64_t n = rel ? n_probe : n_build;
     char *tk = slot_k[1 - rel], *tv = slot_v[1 - rel];
     XRC(dwj_set_option(e, DWJ_OPT_PASS_FILTER, filter_on));
-    XRC(dwj_filter_rows(e, k, v, n, tk, tv, (uint64_t *)d_live, s));
+    XRC(dwj_filter_rows(e, k, v, n, tk, tv, (uint64_t *)d_live, (uint64_t *)x->d_counts, s));      // + the kept rows per table region
     XRC(dwj_set_option(e, DWJ_OPT_PASS_FILTER, 0));
     XCU(cudaMemcpyAsync(h_live, d_live, 8, cudaMemcpyDeviceToHost, s));
+    XCU(cudaMemcpyAsync(x->h_counts, x->d_counts, (uint64_t)G * 8, cudaMemcpyDeviceToHost, s));
     XCU(cudaStreamSynchronize(s));
     const uint64_t live = *h_live;
     if (live > x->slot_rows[rel])
@@ -588,9 +589,6 @@ static int xj_pass_local(dwj_xj *x, uint32_t pass, const void *bk, const void *b
     if (!rel && live > x->info.max_build_rows && (double)live > 0.9 * (double)x->info.slots)
       return xfail(DWJ_ERR_CAPACITY, "key class %u holds %llu build rows, the table was created for %llu", pass, (unsigned long long)live,
                    (unsigned long long)x->info.max_build_rows);
-    XRC(dwj_xpart_hist2(e, tk, live, 1, (uint64_t *)x->d_counts, s));
-    XCU(cudaMemcpyAsync(x->h_counts, x->d_counts, (uint64_t)G * 8, cudaMemcpyDeviceToHost, s));
-    XCU(cudaStreamSynchronize(s));
     if (timed && !rel) XCU(cudaEventRecord(x->ev_t[1], s));
     dwj_xj_plan_send(1, G, G, slot_base_row(x, rel), (const uint64_t *)x->h_counts, start.data());
     if (!rel) XRC(dwj_clear_table(e, s));

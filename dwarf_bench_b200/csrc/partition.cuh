@@ -396,6 +396,8 @@ __global__ void __launch_bounds__(PART_THREADS) partition_hist_red_kernel(Partit
 // a shared-memory prefix over the warps and ONE global reservation per tile of THREADS * ITEMS rows place the warps, and
 // every store instruction writes one contiguous run.  Output order is arbitrary.  No ranking, no staging: this is a
 // stream compaction, not a partition (the many-way kernel with one partition ran it at 3.2 TB/s).
+// With a.hist set the kernel also counts the kept rows per table region (partition id of mode a.mode, 2^log2_parts <= 512
+// bins, RED.shared) -- the histogram the region scatter of the compact copy needs, without another pass over it.
 template <int W, int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS) filter_rows_kernel(PartitionArgs<W> a) {
   using K = typename KeyT<W>::type;
@@ -403,6 +405,10 @@ __global__ void __launch_bounds__(THREADS) filter_rows_kernel(PartitionArgs<W> a
   constexpr uint64_t TILE = (uint64_t)THREADS * ITEMS;
   __shared__ unsigned int s_cnt[WARPS];
   __shared__ unsigned long long s_base;
+  __shared__ unsigned int s_bins[PART_MAX];
+  const uint32_t bins = a.hist ? 1u << a.log2_parts : 0u;
+  for (uint32_t i = threadIdx.x; i < bins; i += THREADS) s_bins[i] = 0;
+  __syncthreads();
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
   const bool with_vals = a.vals != nullptr;
   const uint64_t tiles = (a.n + TILE - 1) / TILE;
@@ -442,11 +448,14 @@ __global__ void __launch_bounds__(THREADS) filter_rows_kernel(PartitionArgs<W> a
         const unsigned long long pos = at + __popc(mask[j] & lt);
         store_stream(a.out_keys + pos, k[j]);
         if (with_vals) store_stream(a.out_vals + pos, v[j]);
+        if (bins) atomicAdd(&s_bins[part_id<W>(a, k[j])], 1u);
       }
       at += __popc(mask[j]);
     }
     __syncthreads();                                // s_cnt / s_base are reused by the next tile
   }
+  for (uint32_t i = threadIdx.x; i < bins; i += THREADS)
+    if (s_bins[i]) atomicAdd(a.hist + i, (unsigned long long)s_bins[i]);
 }
 
 // ---- histogram for at most 8 partitions ------------------------------------------------------------------------

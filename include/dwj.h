@@ -255,9 +255,11 @@ DWJ_API int dwj_xpart_hist2(dwj_engine *e, const void *d_keys, uint64_t n_rows, 
  * particular order; *d_n_out (device, uint64) = rows kept.  The out columns must hold n_rows rows in the worst case.  One
  * streaming pass, no histogram: a join that runs as passes over key classes (DWJ_OPT_PASS_FILTER) on ONE GPU compacts a
  * relation's class first and partitions the compact copy -- the many-way scatter writes full tiles again instead of the
- * class's half.  d_vals / d_out_vals may both be NULL.  Asynchronous. */
+ * class's half.  d_region_counts (optional; device, dwj_info.radix_parts uint64) receives the kept rows per table
+ * region, i.e. what dwj_xpart_hist2 with one rank would count on the compact copy.  d_vals / d_out_vals may both be NULL.
+ * Asynchronous. */
 DWJ_API int dwj_filter_rows(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *d_out_keys, void *d_out_vals,
-                    uint64_t *d_n_out, void *stream);
+                    uint64_t *d_n_out, uint64_t *d_region_counts, void *stream);
 
 /* Clears the table on `stream` AHEAD of the next dwj_build* call, which then waits for this clear instead of doing its own:
  * the clear (a pure HBM write of the whole table) can overlap whatever produces the build rows -- a partition pass, an

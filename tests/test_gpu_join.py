@@ -642,3 +642,44 @@ def test_join_host_with_duplicate_build_keys(dwj, oracle):
     got = pyoracle.canonical_rows(ok, oa, ob)
     for w, x in zip(want, got):
         np.testing.assert_array_equal(w, x)
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_filter_rows_compaction(dwj, monkeypatch, wide):
+    """dwj_filter_rows: the rows of one key class leave in one streaming pass, with their per-region counts; the four
+    classes together are exactly the input rows, and every kept row belongs to the class asked for."""
+    monkeypatch.setenv("DWJ_PARTITION_MIN_MB", "0")
+    monkeypatch.setenv("DWJ_REGION_MB", "0.125")
+    from dwarf_bench_b200 import capi
+    lib = capi.load_library()
+    rng = np.random.default_rng(17 + wide)
+    dt = np.uint64 if wide else np.uint32
+    W = dt().itemsize
+    n = 300_007
+    k = rng.integers(0, 2**31, n).astype(dt)
+    v = np.arange(n, dtype=dt)
+    with dwj.Engine(100_000, key_bytes=W) as e:
+        info = e.info()
+        G = info["radix_parts"]
+        buckets = info["slots"] // info["slots_per_bucket"]
+        dk, dv = dev(k), dev(v)
+        ok, ov = empty_like_dev(n, dt), empty_like_dev(n, dt)
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        rc = torch.zeros(G, dtype=torch.int64, device="cuda")
+        seen = np.zeros(n, dtype=bool)
+        for p in range(4):
+            e.set_pass_filter(0, 2, p)
+            e.filter_rows(dk, dv, n, ok, ov, cnt, rc)
+            torch.cuda.synchronize()
+            m = int(cnt.item())
+            kk, vv = host(ok, dt)[:m], host(ov, dt)[:m]
+            assert int(rc.sum().item()) == m
+            np.testing.assert_array_equal(k[vv.astype(np.int64)], kk)            # payloads still sit beside their keys
+            assert not seen[vv.astype(np.int64)].any()
+            seen[vv.astype(np.int64)] = True
+            cls = [lib.dwj_partition_of(int(x), W, 4, 42) for x in kk[:300]]      # class = the two top bits of the partition hash
+            assert set(cls) == {p}
+            reg = np.bincount([lib.dwj_region_of(int(x), W, buckets, G.bit_length() - 1, 42) for x in kk[:2000]], minlength=G)
+            assert (rc.cpu().numpy() >= reg).all()
+        e.set_pass_filter(0, 0, 0)
+        assert seen.all()
