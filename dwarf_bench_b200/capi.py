@@ -27,7 +27,7 @@ SYMBOLS = ("dwj_abi_version", "dwj_last_error", "dwj_create", "dwj_destroy", "dw
            "dwj_join_host", "dwj_partition", "dwj_partition_hist", "dwj_partition_of",
            "dwj_xpart_regions", "dwj_xpart_hist", "dwj_xpart_hist2", "dwj_xpart_scatter", "dwj_build_grouped",
            "dwj_probe_pairs_grouped", "dwj_build_segments", "dwj_probe_pairs_segments", "dwj_region_scatter_segments",
-           "dwj_set_option", "dwj_clear_table", "dwj_filter_rows", "dwj_xj_block_bytes", "dwj_xj_create", "dwj_xj_destroy", "dwj_xj_describe", "dwj_xj_join",
+           "dwj_set_option", "dwj_clear_table", "dwj_filter_rows", "dwj_aggregate_sum", "dwj_xj_block_bytes", "dwj_xj_create", "dwj_xj_destroy", "dwj_xj_describe", "dwj_xj_join",
            "dwj_xj_sync_timings", "dwj_xj_plan_send", "dwj_xj_plan_recv", "dwj_region_of", "dwj_mg_create", "dwj_mg_destroy", "dwj_mg_describe", "dwj_mg_join", "dwj_mg_join_host")
 ABI_VERSION = 2
 OPT_APPEND_OUTPUT, OPT_PASS_FILTER = 1, 2
@@ -146,6 +146,7 @@ def load_library():
     lib.dwj_region_scatter_segments.argtypes = [vp, u32, vpp, vpp, u64p, u64p, vp, vp, vp]
     lib.dwj_set_option.argtypes = [vp, C.c_int, u64]
     lib.dwj_clear_table.argtypes = [vp, vp]
+    lib.dwj_aggregate_sum.argtypes = [vp, vp, vp, u64, vp]
     lib.dwj_filter_rows.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, vp]
     lib.dwj_xj_block_bytes.argtypes = [vp, C.POINTER(XjConfig), u64p]
     lib.dwj_xj_create.argtypes = [vp, C.POINTER(XjConfig), vpp, C.POINTER(vp)]
@@ -342,6 +343,10 @@ class Engine:
     def filter_rows(self, d_keys, d_vals, n_rows: int, d_out_keys, d_out_vals, d_n_out, d_region_counts=None, stream=None) -> None:
         self._check(self.lib.dwj_filter_rows(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, _ptr(d_out_keys), _ptr(d_out_vals),
                                              _ptr(d_n_out), _ptr(d_region_counts), _stream(stream)))
+
+    def aggregate_sum(self, d_keys, d_vals, n_rows: int, stream=None) -> None:
+        """GROUP BY key, SUM(value) into the table; read back with probe_aligned / probe_contains."""
+        self._check(self.lib.dwj_aggregate_sum(self._h, _ptr(d_keys), _ptr(d_vals), n_rows, _stream(stream)))
 
     def clear_table(self, stream=None) -> None:
         self._check(self.lib.dwj_clear_table(self._h, _stream(stream)))

@@ -10,6 +10,7 @@
 
 #include <cuda_runtime.h>
 
+#include "aggregate.cuh"
 #include "build.cuh"
 #include "partition.cuh"
 #include "probe.cuh"
@@ -1152,6 +1153,35 @@ int dwj_filter_rows(dwj_engine *e, const void *d_keys, const void *d_vals, uint6
   DeviceGuard g(e->cfg.device);
   return e->W == 4 ? filter_rows_impl<4>(e, d_keys, d_vals, n_rows, d_out_keys, d_out_vals, d_n_out, d_region_counts, (cudaStream_t)stream)
                    : filter_rows_impl<8>(e, d_keys, d_vals, n_rows, d_out_keys, d_out_vals, d_n_out, d_region_counts, (cudaStream_t)stream);
+}
+
+int dwj_aggregate_sum(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *stream) {
+  if (int rc = check_engine(e)) return rc;
+  if (n_rows && (!d_keys || !d_vals)) return fail(DWJ_ERR_INVALID, "null aggregation column");
+  DeviceGuard g(e->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaEventRecord(e->ev_build[0], s));
+  CU(cudaMemsetAsync(e->table, 0xFF, e->table_bytes, s));
+  CU(cudaEventRecord(e->ev_buildk[0], s));
+  if (n_rows) {
+    const uint64_t tiles = (n_rows + (uint64_t)dwj::AGG_THREADS * dwj::AGG_ROWS - 1) / ((uint64_t)dwj::AGG_THREADS * dwj::AGG_ROWS);
+    const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)e->prop.multiProcessorCount * 4);
+    if (e->W == 4) {
+      dwj::AggArgs<4> a{(const uint32_t *)d_keys, (const uint32_t *)d_vals, n_rows, e->table, e->buckets - 1, e->cfg.hash_seed};
+      CU(launch(e, dwj::aggregate_kernel<4>, dim3(grid), dim3(dwj::AGG_THREADS), s, a, false));
+    } else {
+      dwj::AggArgs<8> a{(const uint64_t *)d_keys, (const uint64_t *)d_vals, n_rows, e->table, e->buckets - 1, e->cfg.hash_seed};
+      CU(launch(e, dwj::aggregate_kernel<8>, dim3(grid), dim3(dwj::AGG_THREADS), s, a, false));
+    }
+  }
+  CU(cudaEventRecord(e->ev_buildk[1], s));
+  CU(cudaEventRecord(e->ev_build[1], s));
+  e->launches_build = 2;
+  e->have_build = true;
+  e->build_rows = n_rows;
+  e->built = true;
+  e->pre_cleared = false;
+  return DWJ_OK;
 }
 
 int dwj_clear_table(dwj_engine *e, void *stream) {

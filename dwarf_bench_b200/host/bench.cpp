@@ -9,12 +9,15 @@ DwarfBenchException::DwarfBenchException(const std::string &message) : message_(
 const char *DwarfBenchException::what() const noexcept { return message_.c_str(); }
 
 DwarfBench::DwarfImpl DwarfBench::dwarfToImpl(Dwarf dwarf) {
-  return dwarf == Dwarf::Join ? DwarfImpl::JoinOmnisci : DwarfImpl::Unsupported;   // bench.cpp:112-113
+  if (dwarf == Dwarf::Join) return DwarfImpl::JoinOmnisci;                          // bench.cpp:112-113
+  if (dwarf == Dwarf::GroupBy) return DwarfImpl::GroupBy;                           // bench.cpp:115-116
+  return DwarfImpl::Unsupported;
 }
 
 std::string DwarfBench::dwarfToString(DwarfImpl dwarf, DeviceType device) {
   switch (dwarf) {
   case JoinOmnisci: return device == DeviceType::CPU ? "JoinOmnisci" : "JoinOmnisciCuda";   // bench.cpp:45-47
+  case GroupBy: return device == DeviceType::CPU ? "GroupBy" : "GroupByCuda";               // bench.cpp:22-23
   case Join: return "Join";
   case HashBuild: return "HashBuild";
   case SlabProbe: return "SlabProbe";

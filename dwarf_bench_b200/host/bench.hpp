@@ -3,7 +3,7 @@
 //
 // Differences, all on the Join path: Dwarf::Join with DeviceType::GPU runs (the reference asserts,
 // bench.cpp:40-44) and is served by the B200 engine; DeviceType::CPU throws DwarfBenchException (this build has
-// no CPU path).  Scan / GroupBy / Sort are outside this build's scope and throw DwarfBenchException.
+// no CPU path).  Join and GroupBy are served; Scan / Sort are outside this build's scope and throw DwarfBenchException.
 #pragma once
 
 #include <stdexcept>
@@ -51,7 +51,7 @@ public:
   std::vector<Measurement> makeMeasurements(const RunConfig &conf);
 
 private:
-  enum DwarfImpl { HashBuild, Join, JoinOmnisci, SlabProbe, Unsupported };
+  enum DwarfImpl { GroupBy, HashBuild, Join, JoinOmnisci, SlabProbe, Unsupported };
   DwarfImpl dwarfToImpl(Dwarf dwarf);
   std::string dwarfToString(DwarfImpl dwarf, DeviceType device);
 };

@@ -281,6 +281,72 @@ B200_BUILD_ONLY_DWARF(HashBuildNonBitmask, 0.9, false)
 B200_BUILD_ONLY_DWARF(SlabHashBuild, 0.625, false)
 B200_BUILD_ONLY_DWARF(CuckooHashBuild, 0.25, true)
 
+// ---- GroupBy / GroupByCuda: hash aggregation (groupby/groupby.cpp:24-112) -----------------------------------------------
+// keys in [0, groups_count), values in [1, 10000]; output[g] = SUM(value) of group g (uint32 wrap-around).  Timed as the
+// reference: both "kernels" -- the aggregation (ht.add, :60-72) and the read-back (ht.at, :84-92) -- inside host_time.
+// The expected sums are always checked (the reference only does under !NDEBUG).
+namespace {
+void groupby_run(const size_t buf_size, Meter &meter) {
+  // As the reference (:26): the caller passes a GroupByRunOptions -- main.cpp:87-90, bench.cpp:80 and the dwarf tests do.
+  const auto &base = static_cast<const GroupByRunOptions &>(meter.opts());
+  const size_t groups_count = std::max<size_t>(base.groups_count, 1);
+  const std::vector<uint32_t> host_src_vals = helpers::make_random<uint32_t>(buf_size);                        // :30-31
+  const std::vector<uint32_t> host_src_keys = helpers::make_random<uint32_t>(buf_size, 0, groups_count - 1);   // :32-33
+  std::vector<uint32_t> expected(groups_count, 0);                                                             // :8-19
+  for (size_t i = 0; i < buf_size; ++i) expected[host_src_keys[i]] += host_src_vals[i];
+  std::vector<uint32_t> present(groups_count, 0);
+  for (uint32_t k : host_src_keys) present[k] = 1;
+  std::vector<uint32_t> group_ids(groups_count);
+  std::iota(group_ids.begin(), group_ids.end(), 0u);
+  announce_device();
+  b200::Engine eng(std::max<size_t>(groups_count, 1), DWJ_FLAG_UNIQUE_BUILD_KEYS);            // the table holds one slot per group
+  DeviceColumn keys(buf_size * 4), vals(buf_size * 4), ids(groups_count * 4), ok(groups_count * 4), osum(groups_count * 4), oid(groups_count * 4);
+  if (cudaMemcpy(ids.ptr, group_ids.data(), groups_count * 4, kH2D) != 0) throw std::runtime_error("cudaMemcpy H2D failed");
+  for (unsigned it = 0; it < base.iterations; ++it) {
+    auto result = std::make_unique<Result>();
+    const auto host_start = Clock::now();                                                    // :59
+    if (cudaMemcpy(keys.ptr, host_src_keys.data(), buf_size * 4, kH2D) != 0 || cudaMemcpy(vals.ptr, host_src_vals.data(), buf_size * 4, kH2D) != 0)
+      throw std::runtime_error("cudaMemcpy H2D failed");
+    b200::Engine::check(dwj_aggregate_sum(eng.get(), keys.ptr, vals.ptr, buf_size, nullptr));                  // ht.add(sk[idx], sv[idx]) :70
+    b200::Engine::check(dwj_probe_aligned(eng.get(), ids.ptr, ids.ptr, groups_count, ok.ptr, osum.ptr, oid.ptr, nullptr));   // ht.at(...) :87-90
+    std::vector<uint32_t> output(groups_count, 0), found(groups_count, 0);
+    if (cudaMemcpy(output.data(), osum.ptr, groups_count * 4, kD2H) != 0 || cudaMemcpy(found.data(), ok.ptr, groups_count * 4, kD2H) != 0)
+      throw std::runtime_error("cudaMemcpy D2H failed");
+    result->host_time = Clock::now() - host_start;                                           // :93-98
+    dwj_timing t{};
+    b200::Engine::check(dwj_timings(eng.get(), &t));
+    result->kernel_time = ms(t.build_ms + t.probe_ms);
+    result->iterations = 1;
+    result->bytes = result->bytes_per_iteration = buf_size * 2 * sizeof(uint32_t);
+    for (size_t g = 0; g < groups_count; ++g) {
+      const bool hit = found[g] != empty_element;                                            // a group no row fell into has no slot: sum 0
+      if (hit != (present[g] != 0) || (hit ? output[g] : 0u) != expected[g]) {
+        std::cerr << "Incorrect results" << std::endl;                                       // :102-105
+        result->valid = false;
+        break;
+      }
+    }
+    meter.add_result(DwarfParams{{"buf_size", std::to_string(buf_size)}}, std::move(result));
+  }
+}
+}  // namespace
+
+GroupBy::GroupBy() : Dwarf("GroupBy") {}
+void GroupBy::_run(const size_t buf_size, Meter &meter) { groupby_run(buf_size, meter); }
+void GroupBy::run(const RunOptions &opts) {
+  b200::require_gpu(opts, name());
+  for (auto size : opts.input_size) _run(size, meter());
+}
+void GroupBy::init(const RunOptions &opts) { std_init(*this, opts); }
+
+GroupByCuda::GroupByCuda() : Dwarf("GroupByCuda") {}                                         // the name bench.cpp:22-23 asks for on GPU
+void GroupByCuda::_run(const size_t buf_size, Meter &meter) { groupby_run(buf_size, meter); }
+void GroupByCuda::run(const RunOptions &opts) {
+  b200::require_gpu(opts, name());
+  for (auto size : opts.input_size) _run(size, meter());
+}
+void GroupByCuda::init(const RunOptions &opts) { std_init(*this, opts); }
+
 // ---- SlabProbe: untimed build, timed find (probe/slab_probe.cpp:9-107) ------------------------------------------
 SlabProbe::SlabProbe() : Dwarf("SlabProbe") {}
 void SlabProbe::_run(const size_t buf_size, Meter &meter) {

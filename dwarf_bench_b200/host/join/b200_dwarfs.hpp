@@ -8,6 +8,7 @@
 //   SlabJoin        join/slab_join.cpp       Join's flow (the reference's slab variant); here the same table
 //   JoinOmnisci     join/join_omnisci.cpp    one-to-many join on row ids, keys in [1,10000]
 //   JoinOmnisciCuda join/join_omnisci.hpp    the name bench.cpp:45-47 asks for on GPU
+//   GroupBy, GroupByCuda  groupby/groupby.cpp  hash aggregation SUM(value) BY key (dwj_aggregate_sum), keys in [0, groups_count)
 // device=cpu is refused (std::logic_error): the engine has no CPU path by design.
 #pragma once
 #include "common/common.hpp"
@@ -50,5 +51,7 @@ B200_DECLARE_DWARF(HashBuildNonBitmask)
 B200_DECLARE_DWARF(SlabHashBuild)
 B200_DECLARE_DWARF(CuckooHashBuild)
 B200_DECLARE_DWARF(SlabProbe)
+B200_DECLARE_DWARF(GroupBy)
+B200_DECLARE_DWARF(GroupByCuda)
 B200_DECLARE_DWARF(JoinOmnisci)
 B200_DECLARE_DWARF(JoinOmnisciCuda)

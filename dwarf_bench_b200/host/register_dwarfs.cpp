@@ -7,6 +7,8 @@
 // this twice is harmless (the CLI and makeMeasurements may both call it in one process).
 void populate_registry() {
   auto registry = Registry::instance();
+  registry->registerd(new GroupBy());
+  registry->registerd(new GroupByCuda());
   registry->registerd(new HashBuild());
   registry->registerd(new HashBuildNonBitmask());
   registry->registerd(new SlabHashBuild());

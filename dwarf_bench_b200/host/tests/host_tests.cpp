@@ -146,7 +146,7 @@ static void framework_tests() {
   populate_registry();                                                     // idempotent
   std::set<std::string> names;
   for (const auto &dw : *Registry::instance()) names.insert(dw.first);
-  CHECK((names == std::set<std::string>{"CuckooHashBuild", "HashBuild", "HashBuildNonBitmask", "Join", "JoinOmnisci", "JoinOmnisciCuda",
+  CHECK((names == std::set<std::string>{"CuckooHashBuild", "GroupBy", "GroupByCuda", "HashBuild", "HashBuildNonBitmask", "Join", "JoinOmnisci", "JoinOmnisciCuda",
                                         "SlabHashBuild", "SlabJoin", "SlabProbe"}));
   CHECK(Registry::instance()->find("Join") != nullptr && Registry::instance()->find("Join")->name() == "Join");
   CHECK(Registry::instance()->find("NoSuchDwarf") == nullptr);
@@ -200,10 +200,11 @@ static void framework_tests() {
 // ---- tests/dwarf_tests/dwarf_tests.cpp ----------------------------------------------------------------------------------
 template <class DwarfClass> static void test_dwarf(size_t size) {
   StdoutCapture c;
-  RunOptions opts;
-  opts.device_ty = RunOptions::GPU;
-  opts.input_size = {size};
-  opts.iterations = 10;                                                    // utils.cpp:19-27
+  RunOptions plain;
+  plain.device_ty = RunOptions::GPU;
+  plain.input_size = {size};
+  plain.iterations = 10;                                                   // utils.cpp:19-27
+  const GroupByRunOptions opts(plain, 64, 1024);                           // utils.cpp: get_gpu_test_opts_groupby (every dwarf accepts the subclass)
   std::unique_ptr<Dwarf> dwarf = std::make_unique<DwarfClass>();
   dwarf->init(opts);
   dwarf->run(opts);
@@ -222,6 +223,8 @@ template <class DwarfClass> static void test_suite() {
 }
 
 static void gpu_tests() {
+  test_suite<GroupBy>();                  // dwarf_tests.cpp:68 (GENERATE_TEST_SUITE_GROUPBY)
+  test_suite<GroupByCuda>();
   test_suite<HashBuild>();
   test_suite<HashBuildNonBitmask>();      // dwarf_tests.cpp:68, :77-78 (EXPERIMENTAL in the reference)
   test_suite<SlabHashBuild>();

@@ -25,6 +25,8 @@
  *   dwj_probe_count      size of that row list (join_helpers.hpp:21-25 get_size)
  *   dwj_join_host        the whole timed region join/join.cpp:45-113 with the
  *                        implicit sycl::buffer H2D/D2H copies made explicit
+ *   dwj_aggregate_sum    kernel `hash_build` of the GroupBy dwarf groupby/groupby.cpp:60-72
+ *                        = NonOwningHashTableNonBitmask::add hashtable.hpp:136-153
  *   dwj_timings          HashJoinResult{build_time,probe_time,host_time,
  *                        kernel_time}  common/result.hpp:11-33
  *   dwj_partition*, dwj_xpart_*, dwj_*_grouped, dwj_*_segments, dwj_xj_*, dwj_mg_*
@@ -250,6 +252,14 @@ DWJ_API int dwj_region_scatter_segments(dwj_engine *e, uint32_t n_segments, cons
  * whether or not dwj_xpart_regions() folds them into the scatter: d_counts[n_ranks * dwj_info.radix_parts] (uint64,
  * device), rank-major.  The senders count for the receivers.  n_ranks: 1, 2, 4 or 8.  Asynchronous. */
 DWJ_API int dwj_xpart_hist2(dwj_engine *e, const void *d_keys, uint64_t n_rows, uint32_t n_ranks, uint64_t *d_counts, void *stream);
+
+/* Hash aggregation -- GROUP BY key, SUM(value): the table is cleared and ends up holding one (key, sum) slot per distinct
+ * key; sums wrap at the value width.  Replaces kernel `hash_build` of the GroupBy dwarf (groupby/groupby.cpp:60-72) =
+ * NonOwningHashTableNonBitmask::add (common/dpcpp/hashtable.hpp:136-153).  Read the result back with dwj_probe_aligned
+ * (d_out_build_val = the sum of a queried key; SimpleNonOwningHashTable::at as in groupby.cpp:84-92) or
+ * dwj_probe_contains.  max_build_rows of the engine bounds the number of DISTINCT keys.  Rows are first combined per
+ * CTA in shared memory, so a handful of groups does not serialise on a handful of global addresses.  Asynchronous. */
+DWJ_API int dwj_aggregate_sum(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *stream);
 
 /* The rows of the current pass filter's key class (all rows without a filter), copied to d_out_keys / d_out_vals in no
  * particular order; *d_n_out (device, uint64) = rows kept.  The out columns must hold n_rows rows in the worst case.  One

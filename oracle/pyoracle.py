@@ -309,3 +309,13 @@ def canonical_rows(*cols):
         return tuple(cols)
     order = np.lexsort(tuple(reversed(cols)))
     return tuple(c[order] for c in cols)
+
+
+def groupby_sum(keys, vals, groups_count: int):
+    """expected_GroupBy (ref:groupby/groupby.cpp:8-19) with f = x + y: result[k] += v over all rows, in the value type's
+    wrap-around arithmetic.  TEST INFRASTRUCTURE ONLY."""
+    keys, vals = np.asarray(keys), np.asarray(vals)
+    dt = vals.dtype
+    out = np.zeros(groups_count, dtype=np.uint64)
+    np.add.at(out, keys.astype(np.int64), vals.astype(np.uint64))
+    return (out & np.uint64(np.iinfo(dt).max)).astype(dt)

@@ -683,3 +683,34 @@ def test_filter_rows_compaction(dwj, monkeypatch, wide):
             assert (rc.cpu().numpy() >= reg).all()
         e.set_pass_filter(0, 0, 0)
         assert seen.all()
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_groupby_sum(dwj, wide):
+    """dwj_aggregate_sum (the GroupBy dwarf's kernel, ref:groupby/groupby.cpp:60-72): the reference's own 50-row vector
+    (ref:tests/hash_table_tests.cpp:236-247), then 20 groups x 3 Mi rows (the library facade's shape, bench.cpp:80), then
+    200 000 groups (beyond the per-CTA shared-memory tables), wrap-around sums, an absent group -- against the oracle."""
+    from test_oracle_golden import GROUPBY_KEYS, GROUPBY_VALS
+    dt = np.uint64 if wide else np.uint32
+    rng = np.random.default_rng(4 + wide)
+    cases = [(np.array(GROUPBY_KEYS, dtype=dt), np.array(GROUPBY_VALS, dtype=dt), 9),
+             (rng.integers(0, 20, 3 << 20).astype(dt), rng.integers(1, 10001, 3 << 20).astype(dt), 20),
+             (rng.integers(0, 200_000, 1 << 20).astype(dt), rng.integers(0, np.iinfo(dt).max, 1 << 20, dtype=dt), 200_001)]
+    for keys, vals, groups in cases:
+        want = pyoracle.groupby_sum(keys, vals, groups)
+        present = np.zeros(groups, dtype=bool)
+        present[keys.astype(np.int64)] = True
+        with dwj.Engine(groups, key_bytes=dt().itemsize, flags=dwj.FLAG_UNIQUE_BUILD_KEYS) as e:
+            e.aggregate_sum(dev(keys), dev(vals), len(keys))
+            ids = np.arange(groups, dtype=dt)
+            dids = dev(ids)
+            ok, osum, oid = (empty_like_dev(groups, dt) for _ in range(3))
+            e.probe_aligned(dids, dids, groups, ok, osum, oid)
+            flags = torch.zeros(groups, dtype=torch.int32, device="cuda")
+            e.probe_contains(dids, groups, flags)
+            torch.cuda.synchronize()
+        found = host(ok, dt) != np.iinfo(dt).max
+        np.testing.assert_array_equal(found, present)
+        np.testing.assert_array_equal(flags.cpu().numpy().astype(bool), present)
+        np.testing.assert_array_equal(host(osum, dt)[present], want[present])
+        assert (want[~present] == 0).all()

@@ -79,7 +79,7 @@ def test_cli_surface(built):
     assert r.returncode == 0
     assert "DWARF_BENCH_ROOT is set to" in r.stdout and "Supported dwarfs:" in r.stdout
     listed = re.findall(r"^\t(\w+)$", r.stdout, flags=re.M)
-    assert listed == ["CuckooHashBuild", "HashBuild", "HashBuildNonBitmask", "Join", "JoinOmnisci", "JoinOmnisciCuda", "SlabHashBuild",
+    assert listed == ["CuckooHashBuild", "GroupBy", "GroupByCuda", "HashBuild", "HashBuildNonBitmask", "Join", "JoinOmnisci", "JoinOmnisciCuda", "SlabHashBuild",
                       "SlabJoin", "SlabProbe"]
     r = run([cli, "Join", "--help"])
     assert r.returncode == 0 and "--input_size arg" in r.stdout and "--report_path arg" in r.stdout

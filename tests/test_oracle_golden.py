@@ -147,3 +147,22 @@ def test_omnisci_one_to_many(oracle):
         expect = set(np.nonzero(ak == bk[j])[0].tolist())
         got = set(ids[int(off[j]):int(off[j]) + int(cnt[j])].tolist())
         assert got == expect and len(got) == int(cnt[j])
+
+
+# ref:tests/hash_table_tests.cpp:236-247 (GroupByHashTable.GroupByFunctions): 50 rows, 9 groups
+GROUPBY_KEYS = [0, 1, 2, 0, 3, 4, 0, 5, 0, 1, 8, 7, 2, 4, 5, 7, 1, 2, 4, 6, 2, 4, 1, 4, 6, 2, 4, 6, 8, 1, 8, 8, 8, 8, 8, 8, 8, 8, 8,
+                1, 1, 2, 3, 4, 5, 6, 7, 8, 0, 0]
+GROUPBY_VALS = [12, 19, 1, 4, 30, 21, 3, 8, 6, 19, 1, 1, 2, 0, 4, 4, 0, 5, 0, 1, 0, 1, 2, 0, 3, 4, 0, 5, 0, 1, 1, 3, 1, 3, 1, 0, 23, 11, 0,
+                1, 33, 91, 12, 321, 12, 9, 99, 65, 7, 4]
+
+
+def test_groupby_oracle_on_the_reference_vector():
+    """The group sums of the reference's own GroupBy table test, computed as its loop does (:248-250), equal the oracle's."""
+    from oracle import pyoracle
+    answers = [0] * 9
+    for k, v in zip(GROUPBY_KEYS, GROUPBY_VALS):
+        answers[k] += v
+    got = pyoracle.groupby_sum(np.array(GROUPBY_KEYS, dtype=np.uint32), np.array(GROUPBY_VALS, dtype=np.uint32), 9)
+    assert got.tolist() == answers == [36, 75, 103, 42, 343, 24, 18, 104, 109]
+    wrap = pyoracle.groupby_sum(np.array([0, 0, 1], dtype=np.uint32), np.array([0xFFFFFFFF, 2, 5], dtype=np.uint32), 2)
+    assert wrap.tolist() == [1, 5]                     # uint32 wrap-around, as the reference's uint32_t sums
