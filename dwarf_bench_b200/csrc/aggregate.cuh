@@ -38,16 +38,16 @@ DWJ_D uint32_t agg_cas(uint32_t *p, uint32_t cmp, uint32_t val) { return atomicC
 DWJ_D void agg_add(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 DWJ_D void agg_add(uint32_t *p, uint32_t v) { atomicAdd(p, v); }
 
-// table[key] += val in the global bucket table (level 2).
-template <int W> DWJ_D void global_add(const AggArgs<W> &a, typename KeyT<W>::type key, typename KeyT<W>::type val) {
+// table[key] += val in a global bucket table (level 2 of the aggregation; the count pass of the one-to-many build, csr.cuh).
+template <int W> DWJ_D void table_add(void *table, uint64_t bucket_mask, uint64_t seed, typename KeyT<W>::type key, typename KeyT<W>::type val) {
   using K = typename KeyT<W>::type;
   using A = typename std::conditional<W == 4, uint32_t, unsigned long long>::type;
   constexpr int SLOTS = Bucket<W>::SLOTS;
   constexpr K EMPTY = ~(K)0;
   if (key == EMPTY) return;                                   // the reserved key (table.cuh)
-  uint64_t b = slot_hash(key, a.seed) & a.bucket_mask;
+  uint64_t b = slot_hash(key, seed) & bucket_mask;
   for (;;) {
-    A *slot = reinterpret_cast<A *>((char *)a.table + (b << 5));
+    A *slot = reinterpret_cast<A *>((char *)table + (b << 5));
 #pragma unroll 1
     for (int i = 0; i < SLOTS; ++i) {
       A *kp = slot + 2 * i;
@@ -58,8 +58,11 @@ template <int W> DWJ_D void global_add(const AggArgs<W> &a, typename KeyT<W>::ty
       }
       if (cur == (A)key) { agg_add(kp + 1, (A)val); return; }
     }
-    b = (b + 1) & a.bucket_mask;                              // bucket full of other keys: next sector
+    b = (b + 1) & bucket_mask;                                // bucket full of other keys: next sector
   }
+}
+template <int W> DWJ_D void global_add(const AggArgs<W> &a, typename KeyT<W>::type key, typename KeyT<W>::type val) {
+  table_add<W>(a.table, a.bucket_mask, a.seed, key, val);
 }
 
 template <int W>

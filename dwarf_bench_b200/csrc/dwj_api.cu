@@ -12,6 +12,7 @@
 
 #include "aggregate.cuh"
 #include "build.cuh"
+#include "csr.cuh"
 #include "partition.cuh"
 #include "probe.cuh"
 
@@ -77,6 +78,10 @@ struct dwj_engine {
   void *table = nullptr;
   unsigned int *fill = nullptr;                // per-bucket ticket counters of the build (build.cuh)
   uint64_t slots = 0, buckets = 0, table_bytes = 0;
+  // one-to-many engines (no DWJ_FLAG_UNIQUE_BUILD_KEYS): the payload runs of csr.cuh; `csr` says the last build made them
+  void *runs = nullptr;
+  uint64_t runs_granules = 0;
+  bool csr = false;
   uint64_t build_rows = 0;
   bool built = false;
   bool l2_window = false;
@@ -521,7 +526,21 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
       }
     }
     CU(cudaEventRecord(e->ev_buildk[0], s));
-    if (tiles) CU(launch(e, dwj::build_kernel<W, ROWS>, dim3((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull)), dim3(256), s, a, true));
+    const dim3 grid((unsigned)std::min<uint64_t>(tiles, 0x7fffffffull));
+    if (e->runs) {                      // one-to-many engine: count -> offsets -> fill (csr.cuh)
+      unsigned long long *cursor = e->counter + 5;
+      CU(cudaMemsetAsync(cursor, 0, 2 * sizeof(unsigned long long), s));      // cursor, overflow flag
+      if (tiles) CU(launch(e, dwj::csr_count_kernel<W, ROWS>, grid, dim3(256), s, a, true));
+      dwj::CsrOffsetArgs<W> oa{e->table, e->buckets, (K *)e->runs, cursor, e->runs_granules, (unsigned int *)(e->counter + 6)};
+      CU(launch(e, dwj::csr_offsets_kernel<W>, dim3((unsigned)((e->buckets + 255) / 256)), dim3(256), s, oa, true));
+      if (tiles) {
+        dwj::csr_fill_kernel<W, ROWS><<<grid, dim3(256), 0, s>>>(a, (K *)e->runs);
+        CU(cudaGetLastError());
+      }
+      e->launches_build += 3;
+    } else if (tiles) {
+      CU(launch(e, dwj::build_kernel<W, ROWS>, grid, dim3(256), s, a, true));
+    }
     CU(cudaEventRecord(e->ev_buildk[1], s));
     if (e->pending_segs) CU(cudaEventRecord(e->seg_done[seg_slot], s));
     e->launches_build += 2;
@@ -531,6 +550,7 @@ template <int W> int build_impl(dwj_engine *e, const void *keys, const void *val
   e->have_build = true;
   e->build_rows = n;
   e->built = true;
+  e->csr = e->runs != nullptr;
   return DWJ_OK;
 }
 
@@ -553,10 +573,17 @@ int simple_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
   return DWJ_OK;
 }
 
-// PAIRS with non-unique build keys: one look-back descriptor (or one atomic) per CTA tile, rows written from registers.
-template <int W, bool ORDERED>
-int multi_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
-  constexpr int THREADS = 256, ITEMS = W == 4 ? 4 : 2, MINB = 4;
+// PAIRS over a one-to-many table: one look-back descriptor (or one atomic) per CTA tile.  Shapes = threads per CTA, probe
+// rows per thread, min CTAs per SM (DWJ_MULTI_SHAPE selects one; the default is the sweep's winner, profiles/r2_csr.md).
+struct MultiShape { int threads, items, minb; };
+constexpr MultiShape MULTI_SHAPES_4[] = {{256, 4, 4}, {256, 4, 3}, {256, 2, 5}, {512, 2, 2}, {256, 2, 6}, {256, 1, 6}, {256, 1, 8}, {128, 2, 12}};
+constexpr MultiShape MULTI_SHAPES_8[] = {{256, 2, 4}, {256, 2, 3}, {256, 1, 6}, {512, 1, 2}, {256, 1, 7}, {256, 1, 5}, {256, 1, 8}, {128, 1, 12}};
+constexpr int DEFAULT_MULTI_SHAPE = 2;
+
+template <int W, bool ORDERED, int SHAPE>
+int multi_launch_shape(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
+  constexpr MultiShape S = W == 4 ? MULTI_SHAPES_4[SHAPE] : MULTI_SHAPES_8[SHAPE];
+  constexpr int THREADS = S.threads, ITEMS = S.items, MINB = S.minb;
   constexpr uint64_t TILE = (uint64_t)THREADS * ITEMS;
   const uint64_t tiles = (a.n + TILE - 1) / TILE;
   a.num_tiles = tiles;
@@ -579,6 +606,21 @@ int multi_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
     e->launches_probe++;
   }
   return DWJ_OK;
+}
+
+template <int W, bool ORDERED>
+int multi_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
+  static const int shape = getenv("DWJ_MULTI_SHAPE") ? atoi(getenv("DWJ_MULTI_SHAPE")) : DEFAULT_MULTI_SHAPE;
+  switch (shape) {
+  case 1: return multi_launch_shape<W, ORDERED, 1>(e, a, s);
+  case 3: return multi_launch_shape<W, ORDERED, 3>(e, a, s);
+  case 4: return multi_launch_shape<W, ORDERED, 4>(e, a, s);
+  case 5: return multi_launch_shape<W, ORDERED, 5>(e, a, s);
+  case 6: return multi_launch_shape<W, ORDERED, 6>(e, a, s);
+  case 7: return multi_launch_shape<W, ORDERED, 7>(e, a, s);
+  case 0: return multi_launch_shape<W, ORDERED, 0>(e, a, s);
+  default: return multi_launch_shape<W, ORDERED, 2>(e, a, s);
+  }
 }
 
 template <int W, bool ORDERED, bool WITH_KEY, int SHAPE>
@@ -666,7 +708,9 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
   a.out_flags = flags;
   a.capacity = capacity;
   a.n_matches = d_n ? (unsigned long long *)d_n : e->counter;
-  const bool unique = (e->cfg.flags & DWJ_FLAG_UNIQUE_BUILD_KEYS) != 0;
+  a.runs = e->csr ? (const K *)e->runs : nullptr;
+  // one-to-many tables come from the builds of engines without the flag; what dwj_aggregate_sum leaves holds distinct keys
+  const bool unique = (e->cfg.flags & DWJ_FLAG_UNIQUE_BUILD_KEYS) != 0 || !e->csr;
   CU(cudaEventRecord(e->ev_probe[0], s));
   int rc;
   uint32_t extra_launches = 0;
@@ -718,6 +762,11 @@ int probe_impl(dwj_engine *e, int mode, const void *keys, const void *vals, uint
     CU(cudaMemcpyAsync(&total, a.n_matches, sizeof(total), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     *h_n = total;
+    if (e->csr) {                       // the last one-to-many build ran out of run space (csr_offsets_kernel): keys were dropped
+      unsigned int overflow = 0;
+      CU(cudaMemcpy(&overflow, e->counter + 6, sizeof(overflow), cudaMemcpyDeviceToHost));
+      if (overflow) return fail(DWJ_ERR_CAPACITY, "the last build held more rows than the %llu the one-to-many engine was created for", (unsigned long long)e->cfg.max_build_rows);
+    }
     if (mode == dwj::PROBE_PAIRS && total > capacity)
       return fail(DWJ_ERR_OVERFLOW, "join produced %llu rows, output capacity is %llu", total, (unsigned long long)capacity);
   }
@@ -768,6 +817,14 @@ int dwj_create(const dwj_config *cfg, dwj_engine **out) {
   if (me != cudaSuccess) return bail(fail(DWJ_ERR_OOM, "cudaMalloc of a %llu-byte table failed: %s", (unsigned long long)e->table_bytes, cudaGetErrorString(me)));
   if (cudaMalloc((void **)&e->fill, e->buckets * sizeof(unsigned int)) != cudaSuccess)
     return bail(fail(DWJ_ERR_OOM, "cudaMalloc of the %llu-byte ticket array failed", (unsigned long long)(e->buckets * sizeof(unsigned int))));
+  if (!(cfg->flags & DWJ_FLAG_UNIQUE_BUILD_KEYS)) {      // payload runs: header + payloads per key, 32-byte granules (csr.cuh)
+    const uint64_t g = 32u / (uint32_t)e->W, rows = std::max<uint64_t>(cfg->max_build_rows, 1);
+    e->runs_granules = ((1 + g) * rows + g - 1) / g + 1;
+    if (e->W == 4 && e->runs_granules >= 0xFFFFFFFFull)
+      return bail(fail(DWJ_ERR_INVALID, "a one-to-many engine with 4-byte keys holds at most %llu build rows", (unsigned long long)(0xFFFFFFFFull * g / (1 + g) - 2)));
+    if (cudaMalloc(&e->runs, e->runs_granules * 32) != cudaSuccess)
+      return bail(fail(DWJ_ERR_OOM, "cudaMalloc of %llu bytes for the one-to-many payload runs failed", (unsigned long long)(e->runs_granules * 32)));
+  }
   if (cudaMalloc(&e->xpart_cursor, dwj::PART_MAX * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&e->pull_cursor, dwj::PART_MAX * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&e->counter, 64) != cudaSuccess || cudaMalloc(&e->part_scratch, (3 * dwj::PART_MAX + 1) * sizeof(unsigned long long)) != cudaSuccess)
     return bail(fail(DWJ_ERR_OOM, "scratch allocation failed"));
   for (int i = 0; i < 2; ++i)
@@ -826,6 +883,7 @@ int dwj_destroy(dwj_engine *e) {
   if (e->l2_window) cudaCtxResetPersistingL2Cache();
   cudaFree(e->table);
   cudaFree(e->fill);
+  cudaFree(e->runs);
   cudaFree(e->tile_state);
   cudaFree(e->counter);
   cudaFree(e->part_scratch);
@@ -895,7 +953,7 @@ int dwj_build(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_
   if (n_rows && (!d_keys || !d_vals)) return fail(DWJ_ERR_INVALID, "null build column");
   // under a pass filter only one key class in 2^pass_bits is inserted (classes are hash bits: an even split)
   const uint64_t expect = e->filter.mask ? n_rows / ((uint64_t)e->filter.mask + 1) : n_rows;
-  if (expect > e->cfg.max_build_rows && (double)expect > 0.9 * (double)e->slots)
+  if (expect > e->cfg.max_build_rows && ((double)expect > 0.9 * (double)e->slots || e->runs))     // payload runs are sized for max_build_rows
     return fail(DWJ_ERR_CAPACITY, "%llu build rows exceed the table created for %llu", (unsigned long long)expect,
                 (unsigned long long)e->cfg.max_build_rows);
   DeviceGuard g(e->cfg.device);
@@ -1048,7 +1106,7 @@ int dwj_xpart_scatter(dwj_engine *e, const void *d_keys, const void *d_vals, uin
 int dwj_build_grouped(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, const uint64_t *d_region_offsets, void *stream) {
   if (int rc = check_engine(e)) return rc;
   if (n_rows && (!d_keys || !d_vals)) return fail(DWJ_ERR_INVALID, "null build column");
-  if (n_rows > e->cfg.max_build_rows && (double)n_rows > 0.9 * (double)e->slots)
+  if (n_rows > e->cfg.max_build_rows && ((double)n_rows > 0.9 * (double)e->slots || e->runs))
     return fail(DWJ_ERR_CAPACITY, "%llu build rows exceed the table created for %llu", (unsigned long long)n_rows,
                 (unsigned long long)e->cfg.max_build_rows);
   DeviceGuard g(e->cfg.device);
@@ -1093,7 +1151,7 @@ int dwj_build_segments(dwj_engine *e, uint32_t n_segments, const void *const *se
   uint64_t total = 0;
   if (int rc = check_segments(n_segments, seg_keys, seg_rows, &total)) return rc;
   if (!seg_vals) return fail(DWJ_ERR_INVALID, "null build payload segments");
-  if (total > e->cfg.max_build_rows && (double)total > 0.9 * (double)e->slots)
+  if (total > e->cfg.max_build_rows && ((double)total > 0.9 * (double)e->slots || e->runs))
     return fail(DWJ_ERR_CAPACITY, "%llu build rows exceed the table created for %llu", (unsigned long long)total,
                 (unsigned long long)e->cfg.max_build_rows);
   DeviceGuard g(e->cfg.device);
@@ -1180,6 +1238,7 @@ int dwj_aggregate_sum(dwj_engine *e, const void *d_keys, const void *d_vals, uin
   e->have_build = true;
   e->build_rows = n_rows;
   e->built = true;
+  e->csr = false;                       // slot payloads are sums, not run offsets
   e->pre_cleared = false;
   return DWJ_OK;
 }
@@ -1268,7 +1327,7 @@ static int join_host_impl(dwj_engine *e, const void *build_keys, const void *bui
   if (out_mode == DWJ_OUT_PAIRS && out_capacity && (!out_build_val || !out_probe_val))
     return fail(DWJ_ERR_INVALID, "PAIRS output needs the two payload columns");
   if (out_mode != DWJ_OUT_ALIGNED && !n_out) return fail(DWJ_ERR_INVALID, "n_out is required");
-  if (n_build > e->cfg.max_build_rows && (double)n_build > 0.9 * (double)e->slots)
+  if (n_build > e->cfg.max_build_rows && ((double)n_build > 0.9 * (double)e->slots || e->runs))
     return fail(DWJ_ERR_CAPACITY, "%llu build rows exceed the table created for %llu", (unsigned long long)n_build,
                 (unsigned long long)e->cfg.max_build_rows);
   DeviceGuard g(e->cfg.device);

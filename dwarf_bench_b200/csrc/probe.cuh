@@ -11,6 +11,8 @@
 // warp is one contiguous 128 B (4-byte keys) / 256 B (8-byte keys) request, and each thread has
 // ITEMS independent random-sector loads in flight.
 #pragma once
+#include <type_traits>
+
 #include "table.cuh"
 
 namespace dwj {
@@ -39,6 +41,8 @@ template <int W> struct ProbeArgs {
                                    // partition pass); `n` is then an upper bound that sizes the grid
   const unsigned int *hot_keys;    // staged kernel: non-null and *hot_keys != 0 => the probe keys are skewed
                                    // (probe_skew_sample_kernel): bucket sectors are then allowed into L1
+  const K *runs;                   // non-null: one-to-many table (csr.cuh) -- the table holds distinct keys and a slot's
+                                   // payload is the granule index of the key's run [count | payloads...] in runs[]
 };
 template <int W> DWJ_D uint64_t probe_rows(const ProbeArgs<W> &a) {
   return a.n_dev ? min((uint64_t)__ldg(a.n_dev), a.n) : a.n;
@@ -123,56 +127,6 @@ DWJ_D bool find_first(const void *table, uint64_t mask, uint64_t b, const Bucket
   return find_first_overflow<W, K>(table, mask, b, key, payload);
 }
 
-// All hits (seq_join semantics): calls emit(payload) for every equal build row, returns the count.
-template <int W, class K, class F>
-DWJ_D uint32_t for_each_match(const void *table, uint64_t mask, uint64_t b, Bucket<W> bk, K key, F emit) {
-  uint32_t c = 0;
-  for (;;) {
-#pragma unroll
-    for (int i = 0; i < Bucket<W>::SLOTS; ++i)
-      if (bk.match(i, key)) { emit(bk.payload(i)); ++c; }
-    if (bk.any_empty()) return c;
-    b = (b + 1) & mask;
-    bk = load_bucket_ro<W>(table, b);
-  }
-}
-// Count every equal build row and keep the payloads of the first four in registers (selects, no indexed array), so
-// that the common case -- a handful of duplicates -- is emitted without walking the chain a second time.
-template <int W, class K>
-DWJ_D uint32_t collect_matches(const void *table, uint64_t mask, uint64_t b, Bucket<W> bk, K key, K (&pl)[4]) {
-  uint32_t c = 0;
-  for (;;) {
-#pragma unroll
-    for (int i = 0; i < Bucket<W>::SLOTS; ++i) {
-      const bool m = bk.match(i, key);
-      const K p = bk.payload(i);
-      pl[0] = m && c == 0 ? p : pl[0];
-      pl[1] = m && c == 1 ? p : pl[1];
-      pl[2] = m && c == 2 ? p : pl[2];
-      pl[3] = m && c == 3 ? p : pl[3];
-      c += m ? 1u : 0u;
-    }
-    if (bk.any_empty()) return c;
-    b = (b + 1) & mask;
-    bk = load_bucket_ro<W>(table, b);
-  }
-}
-template <int W, class K>
-DWJ_D uint32_t count_matches(const void *table, uint64_t mask, uint64_t b, Bucket<W> bk, K key, K &first_payload) {
-  uint32_t c = 0;
-  for (;;) {
-#pragma unroll
-    for (int i = 0; i < Bucket<W>::SLOTS; ++i) {
-      const bool m = bk.match(i, key);
-      if (m && c == 0) first_payload = bk.payload(i);
-      c += m ? 1u : 0u;
-    }
-    if (bk.any_empty()) return c;
-    b = (b + 1) & mask;
-    bk = load_bucket_ro<W>(table, b);
-  }
-}
-
 // ---- warp-centric kernel: ALIGNED / CONTAINS / COUNT ---------------------------------------------------
 // No inter-warp communication is needed for these shapes, so there are no CTA barriers at all: a warp takes
 // tiles of 32*ITEMS consecutive rows (every column access is one contiguous 128 B / 256 B request) and the
@@ -202,11 +156,17 @@ DWJ_D void simple_round(const ProbeArgs<W> &a, uint64_t base, unsigned lane, uns
     const uint64_t row = base + (uint64_t)j * 32 + lane;
     K payload = SENTINEL;
     if constexpr (MODE == PROBE_COUNT) {
-      if (key[j] != SENTINEL)
-        local_count += UNIQUE ? (find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload) ? 1u : 0u)
-                              : count_matches<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload);
+      if (key[j] != SENTINEL) {
+        if (UNIQUE) local_count += find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload) ? 1u : 0u;
+        else local_count += find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload) && payload != SENTINEL
+                                ? (unsigned long long)__ldg(a.runs + (uint64_t)payload * CsrGeom<W>::G) : 0ull;   // the run's header
+      }
     } else {
-      const bool hit = find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload) && key[j] != SENTINEL;
+      bool hit = find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], payload) && key[j] != SENTINEL;
+      if (MODE == PROBE_ALIGNED && a.runs) {        // one-to-many table: ONE of the key's build rows (the first of its run)
+        hit = hit && payload != SENTINEL;
+        if (hit) payload = __ldg(a.runs + (uint64_t)payload * CsrGeom<W>::G + 1);
+      }
       if (!(FULL || j * 32 + lane < rows)) continue;
       if constexpr (MODE == PROBE_CONTAINS) {
         store_stream(a.out_flags + row, hit ? 1u : 0u);
@@ -240,13 +200,17 @@ __global__ void __launch_bounds__(256) probe_simple_kernel(ProbeArgs<W> a) {
 }
 
 // ---- CTA-tile PAIRS kernel for NON-unique build keys (every equal build row is emitted) -----------------
-// One look-back descriptor per tile; rows are written straight from registers (a probe row may have any
-// number of matches, so they cannot be staged in a fixed amount of shared memory).
+// The table is a one-to-many table (csr.cuh): a probe row finds its key once (first hit, as with unique keys) and reads
+// the count and the first payloads of the key's run with one 16-byte load.  One look-back descriptor (or one atomic)
+// per tile.  A tile whose result rows fit four per probe row is staged in shared memory and written with contiguous
+// stores; a tile with more (high multiplicity) is emitted run by run, a warp copying each run cooperatively.
 template <int W, bool ORDERED, int THREADS, int ITEMS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeArgs<W> a) {
   using K = typename KeyT<W>::type;
+  using V = typename std::conditional<W == 4, uint4, ulonglong2>::type;      // 16 bytes of staged rows
   constexpr int TILE = THREADS * ITEMS;
   constexpr int WARPS = THREADS / 32;
+  constexpr int VEC = 16 / W;
   constexpr K SENTINEL = ~(K)0;
   __shared__ unsigned long long s_tile;
   __shared__ unsigned long long s_base;
@@ -259,26 +223,33 @@ __global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeA
   a.n = probe_rows(a);
   const bool full = base + TILE <= a.n;
 
-  K key[ITEMS], pval[ITEMS], pl[ITEMS][4];
-  Bucket<W> bk[ITEMS];
-  uint64_t hb[ITEMS];
+  K key[ITEMS], pval[ITEMS], pl[ITEMS][4], g[ITEMS];      // g: granule index of the key's run
   uint32_t cnt[ITEMS], off[ITEMS];
+  {
+    Bucket<W> bk[ITEMS];
+    uint64_t hb[ITEMS];
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const uint64_t row = base + (uint64_t)j * THREADS + t;
-    const bool live = full || row < a.n;
-    key[j] = live ? load_stream(a.keys + row) : SENTINEL;
-    pval[j] = live ? load_stream(a.vals + row) : SENTINEL;
-  }
+    for (int j = 0; j < ITEMS; ++j) {
+      const uint64_t row = base + (uint64_t)j * THREADS + t;
+      const bool live = full || row < a.n;
+      key[j] = live ? load_stream(a.keys + row) : SENTINEL;
+      pval[j] = live ? load_stream(a.vals + row) : SENTINEL;
+    }
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    hb[j] = slot_hash(key[j], a.seed) & a.bucket_mask;
-    bk[j] = load_bucket_ro<W>(a.table, hb[j]);
+    for (int j = 0; j < ITEMS; ++j) {
+      hb[j] = slot_hash(key[j], a.seed) & a.bucket_mask;
+      bk[j] = load_bucket_ro<W>(a.table, hb[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      g[j] = SENTINEL;
+      if (key[j] == SENTINEL || !find_first<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], g[j])) g[j] = SENTINEL;
+    }
   }
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     pl[j][0] = pl[j][1] = pl[j][2] = pl[j][3] = SENTINEL;
-    cnt[j] = key[j] != SENTINEL ? collect_matches<W, K>(a.table, a.bucket_mask, hb[j], bk[j], key[j], pl[j]) : 0u;
+    cnt[j] = g[j] != SENTINEL ? csr_head<K>(a.runs + (uint64_t)g[j] * CsrGeom<W>::G, pl[j]) : 0u;
     uint32_t incl = cnt[j];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -314,7 +285,7 @@ __global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeA
   // Common case -- the tile's result rows fit the staging buffer (4 per probe row): every thread drops its matches at
   // their tile-relative positions in shared memory and the CTA then writes the tile's rows with contiguous stores.
   // Straight from registers, lane l's i-th match lands 4 rows from lane l+1's: every store instruction of a warp
-  // touched four times the sectors it filled (config 3: 13.2 ms for 8.5 GB of result rows).
+  // touched four times the sectors it filled.
   extern __shared__ __align__(16) unsigned char s_stage_raw[];
   constexpr uint32_t STAGE = TILE * 4;
   if (tile_total <= STAGE) {
@@ -322,22 +293,39 @@ __global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeA
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
       if (cnt[j] == 0) continue;
-      if (cnt[j] <= 4) {
+      const uint32_t o = off[j];
+      if (cnt[j] == 4 && (o & (VEC - 1)) == 0) {
+        // Exactly four matches at a 16-byte boundary (BASELINE config 3: every key four times): 16-byte shared stores.
+        // Word by word, lane l writes word 4 l + i -- four lanes per bank on every store instruction.
+        if constexpr (W == 4) {
+          *reinterpret_cast<V *>(s_ob + o) = make_uint4(pl[j][0], pl[j][1], pl[j][2], pl[j][3]);
+          *reinterpret_cast<V *>(s_op + o) = make_uint4(pval[j], pval[j], pval[j], pval[j]);
+          if (a.out_key) *reinterpret_cast<V *>(s_ok + o) = make_uint4(key[j], key[j], key[j], key[j]);
+        } else {
+          *reinterpret_cast<V *>(s_ob + o) = make_ulonglong2(pl[j][0], pl[j][1]);
+          *reinterpret_cast<V *>(s_ob + o + 2) = make_ulonglong2(pl[j][2], pl[j][3]);
+          *reinterpret_cast<V *>(s_op + o) = make_ulonglong2(pval[j], pval[j]);
+          *reinterpret_cast<V *>(s_op + o + 2) = make_ulonglong2(pval[j], pval[j]);
+          if (a.out_key) {
+            *reinterpret_cast<V *>(s_ok + o) = make_ulonglong2(key[j], key[j]);
+            *reinterpret_cast<V *>(s_ok + o + 2) = make_ulonglong2(key[j], key[j]);
+          }
+        }
+      } else if (cnt[j] <= 4) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (i < (int)cnt[j]) {
-            s_ob[off[j] + i] = pl[j][i];
-            s_op[off[j] + i] = pval[j];
-            if (a.out_key) s_ok[off[j] + i] = key[j];
+            s_ob[o + i] = pl[j][i];
+            s_op[o + i] = pval[j];
+            if (a.out_key) s_ok[o + i] = key[j];
           }
-      } else {
-        uint32_t o = off[j];
-        for_each_match<W, K>(a.table, a.bucket_mask, hb[j], load_bucket_ro<W>(a.table, hb[j]), key[j], [&](K p) {
-          s_ob[o] = p;
-          s_op[o] = pval[j];
-          if (a.out_key) s_ok[o] = key[j];
-          ++o;
-        });
+      } else {                                        // a longer run: read it where it lies
+        const K *run = a.runs + (uint64_t)g[j] * CsrGeom<W>::G + 1;
+        for (uint32_t i = 0; i < cnt[j]; ++i) {
+          s_ob[o + i] = __ldg(run + i);
+          s_op[o + i] = pval[j];
+          if (a.out_key) s_ok[o + i] = key[j];
+        }
       }
     }
     __syncthreads();
@@ -350,28 +338,27 @@ __global__ void __launch_bounds__(THREADS, MINB) probe_pairs_multi_kernel(ProbeA
     }
     return;
   }
+  // High multiplicity (more than 4 result rows per probe row on average): the warp emits its rows' runs one after the
+  // other, 32 lanes copying a run with contiguous loads and stores -- possible because a key's payloads are contiguous.
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
-    if (cnt[j] == 0) continue;
-    unsigned long long o = out_base + off[j];
-    if (cnt[j] <= 4) {                                // the matches are in registers
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (i < (int)cnt[j] && (fits || o + i < a.capacity)) {
-          if (a.out_key) store_stream(a.out_key + o + i, key[j]);
-          store_stream(a.out_build_val + o + i, pl[j][i]);
-          store_stream(a.out_probe_val + o + i, pval[j]);
+    const unsigned long long run = (unsigned long long)(a.runs + (uint64_t)(cnt[j] ? g[j] : 0) * CsrGeom<W>::G + 1);
+    unsigned m = __ballot_sync(0xffffffffu, cnt[j] != 0);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t c = __shfl_sync(0xffffffffu, cnt[j], src);
+      const unsigned long long o = __shfl_sync(0xffffffffu, out_base + off[j], src);
+      const K *rp = reinterpret_cast<const K *>(__shfl_sync(0xffffffffu, run, src));
+      const K kk = (K)__shfl_sync(0xffffffffu, (unsigned long long)key[j], src);
+      const K pv = (K)__shfl_sync(0xffffffffu, (unsigned long long)pval[j], src);
+      for (uint32_t i = lane; i < c; i += 32) {
+        if (fits || o + i < a.capacity) {
+          if (a.out_key) store_stream(a.out_key + o + i, kk);
+          store_stream(a.out_build_val + o + i, __ldg(rp + i));
+          store_stream(a.out_probe_val + o + i, pv);
         }
       }
-    } else {                                          // re-walk the (cache-warm) chain, emit every equal build row
-      for_each_match<W, K>(a.table, a.bucket_mask, hb[j], load_bucket_ro<W>(a.table, hb[j]), key[j], [&](K p) {
-        if (fits || o < a.capacity) {
-          if (a.out_key) store_stream(a.out_key + o, key[j]);
-          store_stream(a.out_build_val + o, p);
-          store_stream(a.out_probe_val + o, pval[j]);
-        }
-        ++o;
-      });
     }
   }
 }

@@ -178,6 +178,34 @@ DWJ_D uint32_t find_segment(const Seg *segs, uint32_t n_segs, unsigned long long
   return lo;
 }
 
+// ---- one-to-many runs (csr.cuh) ------------------------------------------------------------------------------------
+// Engines without DWJ_FLAG_UNIQUE_BUILD_KEYS keep distinct keys in the bucket table; a slot's payload field is the index of
+// the 32-byte GRANULE (one sector) where the key's run [count | payload 0 | payload 1 | ...] starts in the `runs` array.
+template <int W> struct CsrGeom {
+  static constexpr uint32_t G = 32 / W;                                    // words per granule
+  DWJ_HD static uint64_t granules(uint64_t count) { return (count + G) / G; }  // header + count payloads, rounded up
+};
+
+// Count and first payloads of a key's run with ONE 32-byte load, like a bucket: the count and the first 7 (4-byte keys)
+// or 3 (8-byte keys) payloads.  pl[] receives up to four payloads; longer runs are read by the emitting code.
+template <class K> DWJ_D uint32_t csr_head(const K *run, K (&pl)[4]) {
+  if constexpr (sizeof(K) == 4) {
+    const Bucket<4> h = load_bucket_ro<4>(run, 0);
+    pl[0] = h.f[1];
+    pl[1] = h.f[2];
+    pl[2] = h.f[3];
+    pl[3] = h.f[4];
+    return h.f[0];
+  } else {
+    const Bucket<8> h = load_bucket_ro<8>(run, 0);
+    pl[0] = h.f[1];
+    pl[1] = h.f[2];
+    pl[2] = h.f[3];
+    if (h.f[0] > 3) pl[3] = __ldg(run + 4);
+    return (uint32_t)min(h.f[0], 0xFFFFFFFFull);
+  }
+}
+
 // ---- streaming column access ---------------------------------------------------------------
 template <class T> DWJ_D T load_stream(const T *p) { return __ldcs(p); }   // ld.global.cs: evict-first
 template <class T> DWJ_D void store_stream(T *p, T v) { __stcs(p, v); }    // st.global.cs

@@ -65,7 +65,12 @@ extern "C" {
 #define DWJ_FLAG_UNIQUE_BUILD_KEYS 0x1u /* build keys are distinct: a probe row stops at its
                                            first hit (SimpleNonOwningHashTable::at semantics).
                                            Without it every equal build row is matched
-                                           (seq_join semantics).                           */
+                                           (seq_join semantics) and the engine builds a
+                                           ONE-TO-MANY table: distinct keys in the table, the
+                                           payloads of each key in one contiguous run -- the
+                                           layout of OmniSci::HashTable
+                                           (common/dpcpp/omnisci_hashtable.hpp:80-192).  Such
+                                           an engine holds at most max_build_rows rows.     */
 #define DWJ_FLAG_L2_PERSIST 0x2u        /* pin the table in L2 with an access-policy window
                                            when it fits the device's persisting-L2 limit    */
 #define DWJ_FLAG_NO_PARTITION 0x8u      /* never radix-partition inputs by table region (keeps
@@ -136,7 +141,9 @@ DWJ_API int dwj_destroy(dwj_engine *e);
 DWJ_API int dwj_get_info(const dwj_engine *e, dwj_info *info);
 
 /* Insert n_rows (key, payload) pairs from DEVICE columns into a freshly cleared table.
- * Duplicate keys each take their own slot (as hashtable.hpp:15-21 does).  `stream` is a
+ * DWJ_FLAG_UNIQUE_BUILD_KEYS engines give every row its own slot (as hashtable.hpp:15-21 does);
+ * the others count the rows per distinct key, lay the keys' payload runs out and fill them
+ * (three kernels, no host round trip; omnisci_hashtable.hpp:80-192).  `stream` is a
  * cudaStream_t (NULL = the legacy default stream).  Asynchronous. */
 DWJ_API int dwj_build(dwj_engine *e, const void *d_keys, const void *d_vals, uint64_t n_rows, void *stream);
 

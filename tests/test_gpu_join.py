@@ -183,6 +183,62 @@ def test_heavy_multiplicity(dwj, oracle):
         np.testing.assert_array_equal(w, x)
 
 
+@pytest.mark.parametrize("wide", [False, True])
+def test_one_to_many_runs_of_every_length(dwj, oracle, wide):
+    """The one-to-many table (csr.cuh; ref:common/dpcpp/omnisci_hashtable.hpp:80-192): build keys with 1..6, 40 and 3000
+    duplicates, so that runs end inside the first 16-byte granule, span several, and are emitted both from the staging
+    buffer and by the warp-cooperative copy; PAIRS in probe-row order, COUNT and ALIGNED against the oracle."""
+    rng = np.random.default_rng(23 + wide)
+    dt = np.uint64 if wide else np.uint32
+    distinct = rng.choice(1 << 30, 30_000, replace=False).astype(dt)
+    mult = rng.integers(1, 7, len(distinct))                   # 3.3 result rows per probe row: most tiles fit the staging buffer
+    mult[:3] = (40, 3000, 40)
+    ak = np.repeat(distinct, mult)
+    rng.shuffle(ak)
+    av = rng.permutation(len(ak)).astype(dt)                      # a payload names its build row
+    order = np.argsort(av)
+    bk = np.concatenate([distinct[rng.integers(3, len(distinct), 40_000)], rng.integers(1 << 30, 1 << 31, 3000).astype(dt),
+                         distinct[:3], distinct[1:2].repeat(5)])
+    rng.shuffle(bk[:43_000])                                      # the 3000-fold key stays at the end: one tile far beyond the staging buffer
+    bv = np.arange(len(bk), dtype=dt) + 7
+    want = oracle.sort_join(ak, av, bk, bv)
+    with dwj.Engine(len(ak), key_bytes=dt().itemsize) as e:
+        dak, dav, dbk, dbv = dev(ak), dev(av), dev(bk), dev(bv)
+        e.build(dak, dav, len(ak))
+        assert e.probe_count(dbk, len(bk)) == len(want[0])
+        cap = len(want[0])
+        ok, oa, ob = (empty_like_dev(cap, dt) for _ in range(3))
+        assert e.probe_pairs(dbk, dbv, len(bk), ok, oa, ob, cap) == cap
+        torch.cuda.synchronize()
+        k, a, b = host(ok, dt)[:cap], host(oa, dt)[:cap], host(ob, dt)[:cap]
+        assert (np.diff(b.astype(np.int64)) >= 0).all()           # probe-row order (ordered output is the default)
+        np.testing.assert_array_equal(ak[order[a.astype(np.int64)]], k)      # every payload belongs to a build row with that key
+        for w, x in zip(want, pyoracle.canonical_rows(k, a, b)):
+            np.testing.assert_array_equal(w, x)
+        # a second build into the same engine (runs and cursor are reused), fewer rows
+        e.build(dak, dav, 5000)
+        want2 = oracle.sort_join(ak[:5000], av[:5000], bk, bv)
+        assert e.probe_count(dbk, len(bk)) == len(want2[0])
+        m = e.probe_pairs(dbk, dbv, len(bk), None, oa, ob, cap)
+        torch.cuda.synchronize()
+        got2 = pyoracle.canonical_rows(bk[host(ob, dt)[:m].astype(np.int64) - 7], host(oa, dt)[:m], host(ob, dt)[:m])
+        for w, x in zip(want2, got2):
+            np.testing.assert_array_equal(w, x)
+        # ALIGNED: one row per probe key, its payload one of the key's build rows
+        n = len(bk)
+        ok, oa, ob = (empty_like_dev(n, dt) for _ in range(3))
+        e.build(dak, dav, len(ak))
+        e.probe_aligned(dbk, dbv, n, ok, oa, ob)
+        torch.cuda.synchronize()
+        k, a = host(ok, dt), host(oa, dt)
+        present = np.isin(bk, distinct)
+        assert ((k != np.iinfo(dt).max) == present).all()
+        np.testing.assert_array_equal(ak[order[a[present].astype(np.int64)]], bk[present])
+        with pytest.raises(dwj.DwjError) as ei:                    # the payload runs are sized for max_build_rows
+            e.build(dev(np.concatenate([ak, ak[:8]])), dev(np.concatenate([av, av[:8]])), len(ak) + 8)
+        assert ei.value.code == -6
+
+
 @pytest.mark.parametrize("lf", [0.25, 0.5, 0.9])
 def test_u64_random_with_load_factors(dwj, oracle, lf):
     rng = np.random.default_rng(int(lf * 100))

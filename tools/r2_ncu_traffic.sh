@@ -1,5 +1,6 @@
 #!/bin/bash
-O=gpurun_out/r2_run9; mkdir -p $O; rm -f $O/*
+# full GPU test suite, then the per-kernel DRAM traffic of every bench workload (-> profiles/r2_ncu_traffic_*.csv.gz, profiles/traffic.json)
+O=gpurun_out/r2_ncu_traffic; mkdir -p $O; rm -f $O/*
 timeout 600 python -m pytest tests -m gpu -q --timeout 200 --maxfail=5 > $O/pytest.log 2>&1; echo "rc=$?" >> $O/pytest.log; tail -6 $O/pytest.log | cut -c1-300
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
 for w in join_16Mx256M_u32_unique join_16Mx256M_u32_dup4_zipf join_512Mx1G_u64_unique join_256Mx256M_u32_unique; do
