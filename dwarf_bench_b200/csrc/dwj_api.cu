@@ -577,7 +577,7 @@ int simple_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
 // rows per thread, min CTAs per SM (DWJ_MULTI_SHAPE selects one; the default is the sweep's winner, profiles/r2_csr.md).
 struct MultiShape { int threads, items, minb; };
 constexpr MultiShape MULTI_SHAPES_4[] = {{256, 4, 4}, {256, 4, 3}, {256, 2, 5}, {512, 2, 2}, {256, 2, 6}, {256, 1, 6}, {256, 1, 8}, {128, 2, 12}};
-constexpr MultiShape MULTI_SHAPES_8[] = {{256, 2, 4}, {256, 2, 3}, {256, 1, 6}, {512, 1, 2}, {256, 1, 7}, {256, 1, 5}, {256, 1, 8}, {128, 1, 12}};
+constexpr MultiShape MULTI_SHAPES_8[] = {{256, 2, 4}, {256, 2, 3}, {256, 2, 4}, {512, 1, 2}, {256, 1, 7}, {256, 1, 5}, {256, 1, 8}, {128, 1, 12}};   // [2] = [0]: the sweep ran on 4-byte keys
 constexpr int DEFAULT_MULTI_SHAPE = 2;
 
 template <int W, bool ORDERED, int SHAPE>
