@@ -576,8 +576,8 @@ int simple_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
 // PAIRS over a one-to-many table: one look-back descriptor (or one atomic) per CTA tile.  Shapes = threads per CTA, probe
 // rows per thread, min CTAs per SM (DWJ_MULTI_SHAPE selects one; the default is the sweep's winner, profiles/r2_csr.md).
 struct MultiShape { int threads, items, minb; };
-constexpr MultiShape MULTI_SHAPES_4[] = {{256, 4, 4}, {256, 4, 3}, {256, 2, 5}, {512, 2, 2}, {256, 2, 6}, {256, 1, 6}, {256, 1, 8}, {128, 2, 12}};
-constexpr MultiShape MULTI_SHAPES_8[] = {{256, 2, 4}, {256, 2, 3}, {256, 2, 4}, {512, 1, 2}, {256, 1, 7}, {256, 1, 5}, {256, 1, 8}, {128, 1, 12}};   // [2] = [0]: the sweep ran on 4-byte keys
+constexpr MultiShape MULTI_SHAPES_4[] = {{256, 4, 4}, {256, 4, 3}, {256, 2, 5}, {256, 1, 8}};
+constexpr MultiShape MULTI_SHAPES_8[] = {{256, 2, 4}, {256, 2, 3}, {256, 2, 4}, {256, 1, 8}};   // [2] = [0]: the sweep ran on 4-byte keys
 constexpr int DEFAULT_MULTI_SHAPE = 2;
 
 template <int W, bool ORDERED, int SHAPE>
@@ -614,10 +614,6 @@ int multi_launch(dwj_engine *e, dwj::ProbeArgs<W> a, cudaStream_t s) {
   switch (shape) {
   case 1: return multi_launch_shape<W, ORDERED, 1>(e, a, s);
   case 3: return multi_launch_shape<W, ORDERED, 3>(e, a, s);
-  case 4: return multi_launch_shape<W, ORDERED, 4>(e, a, s);
-  case 5: return multi_launch_shape<W, ORDERED, 5>(e, a, s);
-  case 6: return multi_launch_shape<W, ORDERED, 6>(e, a, s);
-  case 7: return multi_launch_shape<W, ORDERED, 7>(e, a, s);
   case 0: return multi_launch_shape<W, ORDERED, 0>(e, a, s);
   default: return multi_launch_shape<W, ORDERED, 2>(e, a, s);
   }
