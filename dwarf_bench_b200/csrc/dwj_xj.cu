@@ -1246,7 +1246,8 @@ int dwj_mg_join_host(dwj_mg *m, const void *build_keys, const void *build_vals, 
   const double slack = m->cfg.recv_slack > 0 ? m->cfg.recv_slack : 1.25;
   const bool with_key = out_key != nullptr;
   const uint64_t rows_b = std::max<uint64_t>(m->cfg.max_build_rows_per_gpu, 1), rows_p = std::max<uint64_t>(m->cfg.max_probe_rows_per_gpu, 1);
-  const uint64_t rows_o = (uint64_t)((double)rows_p * slack) + 1024;    // unique build keys: at most one row per received probe row
+  uint64_t rows_o = (uint64_t)((double)rows_p * slack) + 1024;          // unique build keys: at most one row per received probe row
+  if (!(m->cfg.flags & DWJ_FLAG_UNIQUE_BUILD_KEYS)) rows_o = std::max<uint64_t>(rows_o, out_capacity + 1024);   // any multiplicity: the caller's bound, on every GPU
   if (!m->stage[0] || m->stage_rows_b < rows_b || m->stage_rows_p < rows_p || m->stage_rows_o < rows_o) {
     for (uint32_t r = 0; r < n; ++r) {
       cudaSetDevice(m->cfg.devices[r]);

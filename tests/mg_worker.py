@@ -52,13 +52,18 @@ def main():
         per_b, per_p = -(-n_build // world), -(-n_probe // world)
         o = pyoracle.Oracle()
         res = {"steps": []}
-        with dwj.MultiGpuJoin([0] * world, key_bytes, per_b, per_p, chunk_rows=int(os.environ.get('DWJ_TEST_CHUNK_ROWS', 9_000)), passes=passes,
-                              force_scatter_pull=(pull == "scatter"), recv_slack=1.5) as mg:
+        dup = int(os.environ.get("DWJ_TEST_DUP", "1"))        # > 1: every build key `dup` times, engines without the unique-keys flag
+        with dwj.MultiGpuJoin([0] * world, key_bytes, per_b * dup, per_p, chunk_rows=int(os.environ.get('DWJ_TEST_CHUNK_ROWS', 9_000)), passes=passes,
+                              force_scatter_pull=(pull == "scatter"), recv_slack=1.5,
+                              flags=dwj.FLAG_UNIQUE_BUILD_KEYS if dup == 1 else 0) as mg:
             info = mg.describe(0)
             res["info"] = info
             for step in range(STEPS):
                 ak, av, bk, bv = make_inputs(step, key_bytes, n_build, n_probe)
-                cap = len(bk)
+                if dup > 1:
+                    ak = np.repeat(ak, dup)
+                    av = np.arange(len(ak), dtype=dt)[::-1].copy()
+                cap = len(bk) * dup
                 ok, ob, op = (np.zeros(cap, dtype=dt) for _ in range(3))
                 m, t = mg.join_host(ak, av, bk, bv, ok, ob, op)
                 want = o.sort_join(ak, av, bk, bv)

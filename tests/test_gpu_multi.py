@@ -53,6 +53,21 @@ def test_mg_join_virtual_ranks(tmp_path, world, key_bytes, pull, passes, regions
         assert res["info"]["regions"] > 1
 
 
+@pytest.mark.parametrize("world,key_bytes,passes", [(2, 4, 1), (4, 8, 2)])
+def test_mg_join_virtual_ranks_duplicate_build_keys(tmp_path, world, key_bytes, passes):
+    """Engines without the unique-keys flag behind the exchange: every build key three times (one-to-many tables on the
+    receivers, rows grouped by table region by the pulling scatter), three consecutive joins against the oracle."""
+    out = tmp_path / "res.json"
+    env = _env(True)
+    env["DWJ_TEST_DUP"] = "3"
+    r = subprocess.run([sys.executable, WORKER, "virtual", str(world), str(key_bytes), "scatter", str(passes), str(out)],
+                       env=env, capture_output=True, text=True, timeout=150)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.load(open(out))
+    assert len(res["steps"]) == 3 and all(s["same"] and s["rows"] == s["want"] for s in res["steps"]), res
+    assert res["info"]["direct_pull"] == 0
+
+
 @pytest.mark.parametrize("key_bytes,passes", [(8, 2), (4, 4)])
 def test_one_gpu_passes_compact_then_partition(tmp_path, key_bytes, passes):
     """world == 1, passes > 1, one probe chunk: the local path of dwj_xj_join (dwj_filter_rows compacts a relation's key
