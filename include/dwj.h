@@ -292,16 +292,20 @@ DWJ_API int dwj_clear_table(dwj_engine *e, void *stream);
                                    one GPU runs as 2^pass_bits passes over key CLASSES (the pass_bits bits of the
                                    partition hash below the rank_bits destination-rank bits): while the filter is set,
                                    dwj_build*, dwj_partition*, dwj_xpart_* and the region partition inside dwj_probe_pairs /
-                                   dwj_probe_count skip the rows of every other class.  pass_bits == 0 clears it.       */
+                                   dwj_probe_count skip the rows of every other class.  pass_bits == 0 clears it.
+                                   A one-to-many engine whose class turns out larger than max_build_rows (classes are
+                                   hash bits: an even split, not an exact one) leaves the keys that no longer fit
+                                   unmatched; the next probe that returns a host count reports DWJ_ERR_CAPACITY.        */
 DWJ_API int dwj_set_option(dwj_engine *e, int option, uint64_t value);
 
 /* ---- multi-GPU join -------------------------------------------------------------------------------------------------
  * No reference counterpart (one sycl::queue on one device, join/join.cpp:23-24).  Equal keys must meet on one GPU: both
  * relations are radix-partitioned on the key hash and exchanged over NVLink, then every GPU builds and probes locally.
- * The exchange is a PULL fused into the consuming kernels: a sender groups its rows by destination inside its own
- * peer-mapped block and raises a flag in the peers' memory; the receiver's build / probe (or region-scatter) kernels read
- * their rows straight out of the senders' blocks through segment lists.  Counts and flags travel through the same
- * blocks -- no collective library on the data path.  (csrc/dwj_xj.cu)
+ * The exchange is a PULL: a sender groups its rows by destination inside its own peer-mapped block and raises a flag in
+ * the peers' memory; the receiver copies its rows out of every sender's block with one kernel that reads all peers at
+ * once, then builds / probes the landed rows through segment lists (one GPU, or DWJ_XJ_FUSED_PULL=1: the build / probe /
+ * region-scatter kernels read the senders' blocks themselves).  Counts and flags travel through the same blocks -- no
+ * collective library on the data path.  (csrc/dwj_xj.cu)
  *
  * dwj_xj = one rank (one GPU).  The caller supplies `world` equally sized blocks of dwj_xj_block_bytes() bytes, one in
  * every rank's memory, ALL mapped into this process (blocks[r] = this process's pointer to rank r's block): peer
