@@ -603,6 +603,37 @@ def test_segments_pull_and_region_scatter(dwj, oracle, monkeypatch, wide):
             np.testing.assert_array_equal(w, x)
 
 
+@pytest.mark.parametrize("wide", [False, True])
+def test_build_segments_with_duplicate_keys(dwj, oracle, monkeypatch, wide):
+    """dwj_build_segments on an engine without the unique-keys flag: the three kernels of the one-to-many build read the
+    build rows through the segment list (pieces of several allocations, one empty), table regions forced at test size."""
+    monkeypatch.setenv("DWJ_PARTITION_MIN_MB", "0")
+    monkeypatch.setenv("DWJ_REGION_MB", "0.125")
+    rng = np.random.default_rng(91 + wide)
+    dt = np.uint64 if wide else np.uint32
+    distinct = _unique_keys(rng, 20_000, dt)
+    ak = np.repeat(distinct, rng.integers(1, 6, len(distinct)))
+    rng.shuffle(ak)
+    av = np.arange(len(ak), dtype=dt)
+    bk = np.concatenate([distinct[rng.integers(0, len(distinct), 50_000)], rng.integers(2**62, 2**63, 500).astype(dt) if wide
+                         else rng.integers(2**31, 2**32 - 8, 500).astype(dt)])
+    bv = np.arange(len(bk), dtype=dt)
+    want = oracle.sort_join(ak, av, bk, bv)
+    cuts = [0, 7, 20_001, 20_001, 45_000, len(ak)]
+    parts = [(dev(ak[lo:hi]) if hi > lo else None, dev(av[lo:hi]) if hi > lo else None, hi - lo) for lo, hi in zip(cuts, cuts[1:])]
+    ptr = lambda t: 0 if t is None else t.data_ptr()          # noqa: E731
+    with dwj.Engine(len(ak), key_bytes=dt().itemsize) as e:
+        e.build_segments([ptr(p[0]) for p in parts], [ptr(p[1]) for p in parts], [p[2] for p in parts])
+        dbk, dbv = dev(bk), dev(bv)
+        cap = len(want[0])
+        assert e.probe_count(dbk, len(bk)) == cap
+        ok, oa, ob = (empty_like_dev(cap, dt) for _ in range(3))
+        assert e.probe_pairs(dbk, dbv, len(bk), ok, oa, ob, cap) == cap
+        torch.cuda.synchronize()
+        for w, x in zip(want, pyoracle.canonical_rows(*(host(t, dt)[:cap] for t in (ok, oa, ob)))):
+            np.testing.assert_array_equal(w, x)
+
+
 def test_hot_probe_keys_with_unique_build_keys(dwj, oracle):
     """Zipf(1.0) probe keys over UNIQUE build keys (the staged PAIRS kernel): same rows as the oracle, and the engine
     notices the skew on the device (a sample of the probe keys) and lets the table sectors into L1 -- while uniform
